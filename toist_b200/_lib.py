@@ -1,0 +1,116 @@
+"""ctypes binding of libtoist_b200.so (the C ABI declared in include/toist_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a kernel fails, the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libtoist_b200.so"
+
+MAX_TAPS = 49
+GEMM_FWD, GEMM_DGRAD, GEMM_WGRAD = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
+BF16, F32 = 0, 1
+
+
+class ToistError(RuntimeError):
+    pass
+
+
+class Tensor4(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dim", C.c_int64 * 4), ("stride", C.c_int64 * 4)]
+
+
+class Tap(C.Structure):
+    _fields_ = [("dx", C.c_int16), ("dy", C.c_int16), ("dn", C.c_int16), ("pad_", C.c_int16), ("col", C.c_int32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("a", Tensor4),
+        ("b", Tensor4),
+        ("ext_x", C.c_int32), ("ext_y", C.c_int32), ("ext_n", C.c_int32),
+        ("tile_x", C.c_int32), ("tile_y", C.c_int32), ("tile_n", C.c_int32),
+        ("stride_x", C.c_int32), ("stride_y", C.c_int32),
+        ("n_cols", C.c_int32),
+        ("m_rows", C.c_int32),
+        ("k_per_tap", C.c_int32),
+        ("n_taps", C.c_int32),
+        ("taps", Tap * MAX_TAPS),
+        ("b_batched", C.c_int32),
+        ("batch_y", C.c_int32), ("batch_n", C.c_int32),
+        ("splits", C.c_int32),
+        ("out", C.c_void_p),
+        ("out_dtype", C.c_int32),
+        ("out_sx", C.c_int64), ("out_sy", C.c_int64), ("out_sn", C.c_int64),
+        ("alpha", C.c_float),
+        ("col_scale", C.c_void_p),
+        ("col_shift", C.c_void_p),
+        ("row_scale", C.c_void_p),
+        ("res", C.c_void_p),
+        ("res_dtype", C.c_int32),
+        ("mask", C.c_void_p),
+        ("aux", C.c_void_p),
+        ("act", C.c_int32),
+        ("accumulate", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Loads the shared library once. Raises ToistError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ToistError(
+            f"{_LIB_PATH} is missing: run `python -m toist_b200.build` (nvcc, sm_100a). "
+            "toist_b200 has no CPU or library fallback."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    _declare(lib)
+    if lib.toist_abi_version() != 1:
+        raise ToistError("libtoist_b200.so ABI version mismatch; rebuild")
+    if lib.toist_sizeof_gemm_desc() != C.sizeof(GemmDesc):
+        raise ToistError("toist_gemm_desc layout mismatch between _lib.py and libtoist_b200.so; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().toist_last_error().decode("utf-8", "replace")
+        raise ToistError(f"toist_b200 kernel call failed (status {rc}): {msg}")
+
+
+def _declare(lib: C.CDLL) -> None:
+    i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+    sig = {
+        "toist_abi_version": (C.c_int, []),
+        "toist_last_error": (C.c_char_p, []),
+        "toist_device_ok": (C.c_int, []),
+        "toist_sizeof_gemm_desc": (C.c_size_t, []),
+        "toist_gemm": (C.c_int, [C.POINTER(GemmDesc), vp]),
+    }
+    sig.update(_EXTRA_SIGS(i32, i64, f32, vp))
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def _EXTRA_SIGS(i32, i64, f32, vp):
+    """Signatures of the non-GEMM entry points (kept beside include/toist_b200.h, same order)."""
+    return {}
+
+
+EXPORTED_SYMBOLS = ["toist_abi_version", "toist_last_error", "toist_device_ok", "toist_sizeof_gemm_desc", "toist_gemm"]

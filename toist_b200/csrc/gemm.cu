@@ -1,0 +1,510 @@
+// Implicit-GEMM engine for sm_100a: TMA (SWIZZLE_128B, 4-D shifted boxes with hardware zero fill) -> shared memory
+// -> tcgen05.mma (M = 128, fp32 accumulators in TMEM) -> tcgen05.ld -> fused epilogue -> global.
+//
+// Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (warp w reads TMEM lane quadrant w % 4).  One CTA computes one 128 x BN output tile; two
+// CTAs are co-resident per SM for BN <= 128 so one tile's epilogue overlaps the other's main loop.
+//
+// See include/toist_b200.h for the three traversal modes (FWD / DGRAD / WGRAD) and the epilogue contract.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace toist {
+
+constexpr int kBM = 128;          // rows per tile == TMEM lanes
+constexpr int kBK = 64;           // reduction elements per pipeline stage (64 bf16 = one 128-byte swizzle row)
+constexpr int kABytes = kBM * 128;
+constexpr int kThreads = 192;
+
+struct GemmKParams {
+  int ext_x, ext_y, ext_n;
+  int tile_x, tile_y, tile_n;
+  int tiles_x, tiles_y, tiles_n;
+  int stride_x, stride_y;
+  int n_cols, m_rows;
+  int kblocks;  // FWD/DGRAD: 64-wide reduction blocks per tap
+  int n_taps;
+  int b_batched;
+  int batch_y, batch_n, splits;
+  int n_tiles;  // WGRAD: number of BN-wide column tiles (grid.y = n_taps * n_tiles)
+  void* out;
+  int out_dtype;
+  long long out_sx, out_sy, out_sn;
+  float alpha;
+  const float* col_scale;
+  const float* col_shift;
+  const float* row_scale;
+  const void* res;
+  int res_dtype;
+  const void* mask;
+  void* aux;
+  int act;
+  int accumulate;
+  int vec_ok;  // 1: every row base and column tile is 16-byte aligned for all epilogue pointers
+  toist_tap taps[TOIST_MAX_TAPS];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == TOIST_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == TOIST_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  if (act == TOIST_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ GemmKParams p) {
+  constexpr int kBBytes = BN * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr bool kAMN = (MODE == TOIST_GEMM_WGRAD);
+  constexpr bool kBMN = (MODE != TOIST_GEMM_FWD);
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; dynamic smem only guarantees 16.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---------------- tile decode
+  int x0 = 0, y0 = 0, i0 = 0;  // FWD/DGRAD: pixel-tile origin
+  int n0 = 0, m0 = 0;          // column / row origin of the output tile
+  int tap_w = 0;               // WGRAD: tap handled by this CTA
+  int by = 0, bn = 0;          // WGRAD batch coordinates
+  int it_begin = 0, it_end = 0;
+  if constexpr (MODE != TOIST_GEMM_WGRAD) {
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int tn = t / p.tiles_y;
+    x0 = tx * p.tile_x;
+    y0 = ty * p.tile_y;
+    i0 = tn * p.tile_n;
+    n0 = blockIdx.y * BN;
+    it_begin = 0;
+    it_end = p.n_taps * p.kblocks;
+  } else {
+    m0 = blockIdx.x * kBM;
+    tap_w = blockIdx.y / p.n_tiles;
+    n0 = (blockIdx.y % p.n_tiles) * BN;
+    int z = blockIdx.z;
+    const int split = z % p.splits;
+    z /= p.splits;
+    by = z % p.batch_y;
+    bn = z / p.batch_y;
+    const int total = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int per = (total + p.splits - 1) / p.splits;
+    it_begin = split * per;
+    it_end = min(total, it_begin + per);
+  }
+  const int n_iters = it_end - it_begin;
+
+  // ---------------- one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        if constexpr (MODE != TOIST_GEMM_WGRAD) {
+          const int t = it / p.kblocks;
+          const int kb = it - t * p.kblocks;
+          const toist_tap tp = p.taps[t];
+          tma_load_4d(sa, &tma_a, &full_bar[stage], kb * kBK, x0 * p.stride_x + tp.dx, y0 * p.stride_y + tp.dy,
+                      i0 + tp.dn);
+          const int cy = p.b_batched ? y0 : 0;
+          const int cn = p.b_batched ? i0 : 0;
+          if constexpr (MODE == TOIST_GEMM_FWD) {
+            tma_load_4d(sb, &tma_b, &full_bar[stage], tp.col + kb * kBK, n0, cy, cn);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * 8192, &tma_b, &full_bar[stage], tp.col + n0 + j * 64, kb * kBK, cy, cn);
+          }
+        } else {
+          int t = it;
+          const int px = t % p.tiles_x;
+          t /= p.tiles_x;
+          const int py = t % p.tiles_y;
+          const int pn = t / p.tiles_y;
+          const toist_tap tp = p.taps[tap_w];
+          const int ax = px * p.tile_x, ay = py * p.tile_y, an = pn * p.tile_n;
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(sa + j * 8192, &tma_a, &full_bar[stage], m0 + j * 64, ax, ay + by, an + bn);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, ax * p.stride_x + tp.dx,
+                        ay * p.stride_y + tp.dy + by, an + tp.dn + bn);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    constexpr uint32_t idesc = umma_idesc_bf16(BN, kAMN, kBMN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int ks = 0; ks < kBK / 16; ++ks) {
+          const uint64_t da = kAMN ? umma_smem_desc(sa + ks * 2048, 8192, 1024) : umma_smem_desc(sa + ks * 32, 16, 1024);
+          const uint64_t db = kBMN ? umma_smem_desc(sb + ks * 2048, 8192, 1024) : umma_smem_desc(sb + ks * 32, 16, 1024);
+          umma_f16(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);                 // frees the smem stage once these MMAs retire
+        if (it == n_iters - 1) umma_commit(accum_bar);  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ======================= epilogue (4 warps, one TMEM lane quadrant each) =======================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row of the tile owned by this thread
+    bool row_ok;
+    long long row_off;
+    int row_global;  // index for row_scale
+    if constexpr (MODE != TOIST_GEMM_WGRAD) {
+      const int dx = r % p.tile_x;
+      const int t2 = r / p.tile_x;
+      const int dy = t2 % p.tile_y;
+      const int dn = t2 / p.tile_y;
+      const int x = x0 + dx, y = y0 + dy, n = i0 + dn;
+      row_ok = (x < p.ext_x) && (y < p.ext_y) && (n < p.ext_n);
+      row_off = (long long)x * p.out_sx + (long long)y * p.out_sy + (long long)n * p.out_sn;
+      row_global = 0;
+    } else {
+      const int m = m0 + r;
+      row_ok = m < p.m_rows;
+      row_off = (long long)m * p.out_sx + (long long)by * p.out_sy + (long long)bn * p.out_sn + p.taps[tap_w].col;
+      row_global = m;
+    }
+    const float rscale = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + row_global) : 1.f;
+
+    if (n_iters > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.n_cols) break;  // warp-uniform
+      uint32_t raw[32];
+      if (n_iters > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = 0u;
+      }
+      if (!row_ok) continue;
+      const int ncol = n0 + c0;
+      const long long off = row_off + ncol;
+      const int nvalid = min(32, p.n_cols - ncol);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+      if (p.col_scale != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nvalid) v[i] *= __ldg(p.col_scale + ncol + i);
+      }
+      if (p.col_shift != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < nvalid) v[i] += __ldg(p.col_shift + ncol + i);
+      }
+      if (p.row_scale != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= rscale;
+      }
+      const bool vec = p.vec_ok && nvalid == 32;
+      if (p.res != nullptr) {
+        if (p.res_dtype == TOIST_BF16) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + off;
+          if (vec) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+              v[g * 8 + 0] += f0.x; v[g * 8 + 1] += f0.y; v[g * 8 + 2] += f1.x; v[g * 8 + 3] += f1.y;
+              v[g * 8 + 4] += f2.x; v[g * 8 + 5] += f2.y; v[g * 8 + 6] += f3.x; v[g * 8 + 7] += f3.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) v[i] += __bfloat162float(rp[i]);
+          }
+        } else {
+          const float* rp = reinterpret_cast<const float*>(p.res) + off;
+          if (vec) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 f = __ldg(reinterpret_cast<const float4*>(rp) + g);
+              v[g * 4 + 0] += f.x; v[g * 4 + 1] += f.y; v[g * 4 + 2] += f.z; v[g * 4 + 3] += f.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) v[i] += rp[i];
+          }
+        }
+      }
+      if (p.mask != nullptr) {
+        const __nv_bfloat16* mp = reinterpret_cast<const __nv_bfloat16*>(p.mask) + off;
+        if (vec) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(mp) + g);
+            const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+            if (!(f0.x > 0.f)) v[g * 8 + 0] = 0.f;
+            if (!(f0.y > 0.f)) v[g * 8 + 1] = 0.f;
+            if (!(f1.x > 0.f)) v[g * 8 + 2] = 0.f;
+            if (!(f1.y > 0.f)) v[g * 8 + 3] = 0.f;
+            if (!(f2.x > 0.f)) v[g * 8 + 4] = 0.f;
+            if (!(f2.y > 0.f)) v[g * 8 + 5] = 0.f;
+            if (!(f3.x > 0.f)) v[g * 8 + 6] = 0.f;
+            if (!(f3.y > 0.f)) v[g * 8 + 7] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid && !(__bfloat162float(mp[i]) > 0.f)) v[i] = 0.f;
+        }
+      }
+      if (p.aux != nullptr) {
+        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.aux) + off;
+        if (vec) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+            u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+            u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+            reinterpret_cast<uint4*>(ap)[g] = u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) ap[i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+      if (p.act != TOIST_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+      }
+      if (p.out_dtype == TOIST_BF16) {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+        if (vec) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+            u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+            u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+            reinterpret_cast<uint4*>(op)[g] = u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) op[i] = __float2bfloat16_rn(v[i]);
+        }
+      } else {
+        float* op = reinterpret_cast<float*>(p.out) + off;
+        if (p.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) atomicAdd(op + i, v[i]);
+        } else if (vec) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(op)[g] = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) op[i] = v[i];
+        }
+      }
+    }
+  }
+
+  // ---------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN, int STAGES, int MODE>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKParams& kp, dim3 grid,
+                       cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool configured = false;
+  auto kfn = gemm_kernel<BN, STAGES, MODE>;
+  if (!configured) {
+    TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kfn<<<grid, kThreads, smem, stream>>>(ma, mb, kp);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+template <int MODE>
+static int dispatch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmKParams& kp, dim3 grid,
+                       cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_gemm<256, 4, MODE>(ma, mb, kp, grid, stream);
+    case 128: return launch_gemm<128, 3, MODE>(ma, mb, kp, grid, stream);
+    default:  return launch_gemm<64, 4, MODE>(ma, mb, kp, grid, stream);
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace toist
+
+using namespace toist;
+
+extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  TOIST_REQUIRE(d != nullptr, "toist_gemm: null descriptor");
+  TOIST_REQUIRE(d->mode >= 0 && d->mode <= 2, "toist_gemm: bad mode %d", d->mode);
+  TOIST_REQUIRE(d->out != nullptr && d->a.ptr != nullptr && d->b.ptr != nullptr, "toist_gemm: null tensor");
+  TOIST_REQUIRE(d->n_taps >= (d->mode == TOIST_GEMM_WGRAD ? 1 : 0) && d->n_taps <= TOIST_MAX_TAPS,
+                "toist_gemm: n_taps %d out of range", d->n_taps);
+  TOIST_REQUIRE(d->tile_x >= 1 && d->tile_y >= 1 && d->tile_n >= 1, "toist_gemm: bad tile");
+  TOIST_REQUIRE(d->stride_x >= 1 && d->stride_x <= 8 && d->stride_y >= 1 && d->stride_y <= 8, "toist_gemm: bad stride");
+  TOIST_REQUIRE(d->n_cols >= 1, "toist_gemm: n_cols must be positive");
+  TOIST_REQUIRE(d->ext_x >= 1 && d->ext_y >= 1 && d->ext_n >= 1, "toist_gemm: empty pixel space");
+  TOIST_REQUIRE(!d->accumulate || d->out_dtype == TOIST_F32, "toist_gemm: accumulate needs an f32 output");
+  const int tile_rows = d->tile_x * d->tile_y * d->tile_n;
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.ext_x = d->ext_x; kp.ext_y = d->ext_y; kp.ext_n = d->ext_n;
+  kp.tile_x = d->tile_x; kp.tile_y = d->tile_y; kp.tile_n = d->tile_n;
+  kp.tiles_x = (int)ceil_div(d->ext_x, d->tile_x);
+  kp.tiles_y = (int)ceil_div(d->ext_y, d->tile_y);
+  kp.tiles_n = (int)ceil_div(d->ext_n, d->tile_n);
+  kp.stride_x = d->stride_x; kp.stride_y = d->stride_y;
+  kp.n_cols = d->n_cols; kp.m_rows = d->m_rows;
+  kp.n_taps = d->n_taps;
+  kp.b_batched = d->b_batched;
+  kp.batch_y = d->batch_y > 0 ? d->batch_y : 1;
+  kp.batch_n = d->batch_n > 0 ? d->batch_n : 1;
+  kp.splits = d->splits > 0 ? d->splits : 1;
+  kp.out = d->out; kp.out_dtype = d->out_dtype;
+  kp.out_sx = d->out_sx; kp.out_sy = d->out_sy; kp.out_sn = d->out_sn;
+  kp.alpha = d->alpha;
+  kp.col_scale = d->col_scale; kp.col_shift = d->col_shift; kp.row_scale = d->row_scale;
+  kp.res = d->res; kp.res_dtype = d->res_dtype; kp.mask = d->mask; kp.aux = d->aux;
+  kp.act = d->act; kp.accumulate = d->accumulate;
+  for (int i = 0; i < d->n_taps; ++i) kp.taps[i] = d->taps[i];
+
+  // 16-byte vector path: every row start and every 32-column group must be 16-byte aligned in all streams.
+  bool vec = (d->out_sx % 8 == 0) && (d->out_sy % 8 == 0) && (d->out_sn % 8 == 0) && aligned16(d->out) &&
+             (d->res == nullptr || aligned16(d->res)) && (d->mask == nullptr || aligned16(d->mask)) &&
+             (d->aux == nullptr || aligned16(d->aux));
+  if (d->mode == TOIST_GEMM_WGRAD)
+    for (int i = 0; i < d->n_taps; ++i) vec = vec && (d->taps[i].col % 8 == 0);
+  kp.vec_ok = vec ? 1 : 0;
+
+  // pick the column-tile width: the widest tile that still yields enough CTAs to cover the 148 SMs
+  const int64_t m_tiles = (d->mode == TOIST_GEMM_WGRAD) ? ceil_div(d->m_rows, kBM)
+                                                         : (int64_t)kp.tiles_x * kp.tiles_y * kp.tiles_n;
+  const int64_t z_mult = (d->mode == TOIST_GEMM_WGRAD) ? (int64_t)kp.batch_y * kp.batch_n * kp.splits * d->n_taps : 1;
+  int bn = 64;
+  const int cands[3] = {256, 128, 64};
+  for (int c = 0; c < 3; ++c) {
+    const int cand = cands[c];
+    if (cand > 64 && d->n_cols <= cand / 2) continue;  // more than half the tile would be padding
+    const int64_t ctas = m_tiles * ceil_div(d->n_cols, cand) * z_mult;
+    if (ctas >= 132 || cand == 64) {
+      bn = cand;
+      break;
+    }
+  }
+  const int n_tiles = (int)ceil_div(d->n_cols, bn);
+  kp.n_tiles = n_tiles;
+
+  CUtensorMap ma, mb;
+  uint32_t ones[4] = {1, 1, 1, 1};
+  int rc;
+  if (d->mode != TOIST_GEMM_WGRAD) {
+    TOIST_REQUIRE(tile_rows == kBM, "toist_gemm: FWD/DGRAD pixel tile must hold 128 rows (got %d)", tile_rows);
+    TOIST_REQUIRE(d->k_per_tap >= 1, "toist_gemm: k_per_tap must be positive");
+    kp.kblocks = (int)ceil_div(d->k_per_tap, kBK);
+    uint32_t abox[4] = {64, (uint32_t)(d->tile_x * d->stride_x), (uint32_t)(d->tile_y * d->stride_y),
+                        (uint32_t)d->tile_n};
+    uint32_t aes[4] = {1, (uint32_t)d->stride_x, (uint32_t)d->stride_y, 1};
+    if ((rc = encode_tmap_bf16_4d(&ma, d->a.ptr, d->a.dim, d->a.stride, abox, aes)) != TOIST_OK) return rc;
+    uint32_t bbox_fwd[4] = {64, (uint32_t)bn, 1, 1};
+    uint32_t bbox_dg[4] = {64, 64, 1, 1};
+    if ((rc = encode_tmap_bf16_4d(&mb, d->b.ptr, d->b.dim, d->b.stride,
+                                  d->mode == TOIST_GEMM_FWD ? bbox_fwd : bbox_dg, ones)) != TOIST_OK)
+      return rc;
+    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, 1);
+    if (d->mode == TOIST_GEMM_FWD) return dispatch_bn<TOIST_GEMM_FWD>(bn, ma, mb, kp, grid, stream);
+    return dispatch_bn<TOIST_GEMM_DGRAD>(bn, ma, mb, kp, grid, stream);
+  }
+  TOIST_REQUIRE(tile_rows == kBK, "toist_gemm: WGRAD pixel tile must hold 64 rows (got %d)", tile_rows);
+  TOIST_REQUIRE(d->m_rows >= 1, "toist_gemm: WGRAD needs m_rows");
+  const int64_t total_tiles = (int64_t)kp.tiles_x * kp.tiles_y * kp.tiles_n;
+  if (kp.splits > total_tiles) kp.splits = (int)total_tiles;
+  // every split must own at least one pixel tile
+  while (kp.splits > 1 && (int64_t)(kp.splits - 1) * ceil_div(total_tiles, kp.splits) >= total_tiles) --kp.splits;
+  TOIST_REQUIRE(kp.splits == 1 || d->accumulate, "toist_gemm: WGRAD splits > 1 requires accumulate");
+  uint32_t abox[4] = {64, (uint32_t)d->tile_x, (uint32_t)d->tile_y, (uint32_t)d->tile_n};
+  if ((rc = encode_tmap_bf16_4d(&ma, d->a.ptr, d->a.dim, d->a.stride, abox, ones)) != TOIST_OK) return rc;
+  uint32_t bbox[4] = {64, (uint32_t)(d->tile_x * d->stride_x), (uint32_t)(d->tile_y * d->stride_y),
+                      (uint32_t)d->tile_n};
+  uint32_t bes[4] = {1, (uint32_t)d->stride_x, (uint32_t)d->stride_y, 1};
+  if ((rc = encode_tmap_bf16_4d(&mb, d->b.ptr, d->b.dim, d->b.stride, bbox, bes)) != TOIST_OK) return rc;
+  dim3 grid((unsigned)m_tiles, (unsigned)(n_tiles * d->n_taps), (unsigned)(kp.batch_y * kp.batch_n * kp.splits));
+  return dispatch_bn<TOIST_GEMM_WGRAD>(bn, ma, mb, kp, grid, stream);
+}

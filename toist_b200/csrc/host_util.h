@@ -1,0 +1,36 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "toist_b200.h"
+
+namespace toist {
+
+// Thread-local error text returned by toist_last_error().
+int set_error(int code, const char* fmt, ...);
+
+#define TOIST_CHECK_CUDA(expr)                                                                        \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return ::toist::set_error(TOIST_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                __FILE__, __LINE__);                                                  \
+  } while (0)
+
+#define TOIST_REQUIRE(cond, ...)                                        \
+  do {                                                                  \
+    if (!(cond)) return ::toist::set_error(TOIST_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Encodes a rank-4 bf16 tensor map (SWIZZLE_128B, zero OOB fill).  dims/strides in elements (stride[0] == 1),
+// box extents in elements *before* applying elem_stride (TMA loads ceil(box / elem_stride) per dimension).
+int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
+                        const uint32_t box[4], const uint32_t elem_stride[4]);
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace toist
