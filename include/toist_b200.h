@@ -112,6 +112,100 @@ typedef struct toist_gemm_desc {
 /* Launches the product described by `d` on `stream`. */
 int toist_gemm(const toist_gemm_desc* d, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HungarianMatcher (reference models/matcher.py:39-87, util/box_ops.py:11-61)
+ *   targets are passed padded: tgt_boxes [B, t_max, 4] cxcywh, tgt_count [B], posmap [B, t_max, n_classes]
+ *   logits [L, B, Q, n_classes], boxes [L, B, Q, 4]  ->  cost [L, B, Q, t_max]  (fp32, reference operation order)
+ * ------------------------------------------------------------------------------------------------------------ */
+int toist_match_cost(const float* logits, const float* boxes, const float* tgt_boxes, const int32_t* tgt_count,
+                     const float* posmap, float* cost, int32_t n_layers, int32_t batch, int32_t n_queries,
+                     int32_t n_classes, int32_t t_max, float w_class, float w_bbox, float w_giou, void* stream);
+/* One shortest-augmenting-path solve per (layer, image) problem on the device (float64, scipy tie rules);
+ * match_q [n_problems, t_max] = query assigned to each target (-1 = none); flags[0] |= 1 on NaN / infeasible. */
+int toist_lsap_device(const float* cost, const int32_t* tgt_count, int32_t* match_q, int32_t* flags,
+                      int32_t n_problems, int32_t batch, int32_t n_queries, int32_t t_max, void* stream);
+/* Host LSAP replacing scipy.optimize.linear_sum_assignment (matcher.py:85, mdetr.py:100,539): row-major float64
+ * cost [n_rows, n_cols]; writes min(n_rows, n_cols) pairs sorted by row; returns the pair count or a negative
+ * status (TOIST_ERR_NUMERIC for NaN / -inf entries or an infeasible matrix, scipy's ValueError). */
+int toist_lsap_f64(const double* cost, int32_t n_rows, int32_t n_cols, int64_t* row_ind, int64_t* col_ind);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SetCriterion terms for all decoder layers at once (reference models/mdetr.py:488-518, 601-666, 783-825).
+ * Every kernel also emits the gradient for an upstream gradient of one ("unit" gradients, already divided by
+ * num_boxes[0]); pass null gradient pointers for inference.
+ * ------------------------------------------------------------------------------------------------------------ */
+int toist_token_ce(const float* logits, const int32_t* match_q, const int32_t* tgt_count, const float* posmap,
+                   const float* num_boxes, float* row_loss, float* dlogits, int32_t n_layers, int32_t batch,
+                   int32_t n_queries, int32_t n_classes, int32_t t_max, float eos_coef, void* stream);
+int toist_box_loss(const float* boxes, const int32_t* match_q, const int32_t* tgt_count, const float* tgt_boxes,
+                   const float* num_boxes, float* pair_l1, float* pair_giou, float* dboxes_l1, float* dboxes_giou,
+                   int32_t n_layers, int32_t batch, int32_t n_queries, int32_t t_max, void* stream);
+int toist_cardinality(const float* logits, int32_t* card, int32_t n_layers, int32_t batch, int32_t n_queries,
+                      int32_t n_classes, void* stream);
+int toist_contrastive_align(const float* proj_queries, const float* proj_tokens, const int32_t* match_q,
+                            const int32_t* tgt_count, const uint8_t* tok_pos, const float* num_boxes, float* img_loss,
+                            float* dpq, float* dpt, int32_t n_layers, int32_t batch, int32_t n_queries,
+                            int32_t n_tokens, int32_t dim, int32_t t_max, float temperature, void* stream);
+/* out [5, L]: loss_ce, loss_bbox, loss_giou, cardinality_error, loss_contrastive_align (img_loss may be null) */
+int toist_criterion_reduce(const float* row_loss, const float* pair_l1, const float* pair_giou, const int32_t* card,
+                           const float* img_loss, const int32_t* tgt_count, const float* num_boxes, float* out,
+                           int32_t n_layers, int32_t batch, int32_t n_queries, int32_t t_max, void* stream);
+/* reduce == 0: y[l, i] = x[l, i] * g[l];  reduce == 1: y[i] = sum_l x[l, i] * g[l] */
+int toist_scale_layers(const float* x, const float* g, float* y, int32_t n_layers, int64_t n, int32_t reduce,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HBM-bound helpers
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct toist_prep_item {
+  const float* src;       /* fp32 master weight, [rows, cols] row-major */
+  void* dst;              /* bf16 shadow, leading dimension ldd */
+  const float* row_scale; /* optional FrozenBatchNorm scale folded per output channel (backbone.py:48-58) */
+  int32_t rows, cols, ldd;
+  int32_t first_block; /* prefix sum of ceil(rows * cols / 2048) over the preceding items */
+} toist_prep_item;
+int toist_weight_prep(const void* items_dev, int32_t n_items, int32_t total_blocks, void* stream);
+int toist_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int toist_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+int toist_add_bf16(const void* a, const void* b, const void* c /* may be null */, void* out, int64_t n, void* stream);
+/* 7x7 stride-2 pad-3 stem (torchvision resnet conv1 via backbone.py:75): fp32 NCHW -> bf16 patches [N*Ho*Wo, ldk] */
+int toist_stem_im2col(const float* images, void* patches, int32_t n, int32_t h, int32_t w, int32_t ldk, void* stream);
+int toist_maxpool3x3s2(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+int toist_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t cols, int64_t ld, void* stream);
+int toist_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream);
+/* out = (dy + dy2) * (y > 0), bf16; dy2 may be null (ReLU derivative at a residual join, torchvision Bottleneck) */
+int toist_relu_bwd(const void* dy, const void* dy2, const void* y, void* out, int64_t n, void* stream);
+int toist_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+int toist_sum_mid(const void* x, int32_t dtype, float* out, int32_t a, int32_t r, int32_t c, int32_t accumulate,
+                  void* stream);
+int toist_bcast_mid(const float* x, void* out, int32_t a, int32_t r, int32_t c, void* stream);
+int toist_nchw_to_nhwc(const float* x, void* y, int32_t n, int32_t c, int32_t hw, void* stream);
+int toist_nhwc_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Row-wise normalisation / softmax / embeddings (transformer.py:279-280,346-349,484; mdetr.py:430-433;
+ * nn.MultiheadAttention softmax with key padding; position_encoding.py:30-49; RobertaEmbeddings)
+ * ------------------------------------------------------------------------------------------------------------ */
+int toist_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, void* y_bf16,
+                        float* y_f32, float* mean, float* rstd, int64_t rows, int32_t n, float eps, void* stream);
+int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const void* x, int32_t x_dtype,
+                        const float* mean, const float* rstd, const float* gamma, void* dx, int32_t dx_dtype,
+                        float* dgamma, float* dbeta, int64_t rows, int32_t n, void* stream);
+int toist_l2norm_fwd(const float* x, float* y, float* nrm, int64_t rows, int32_t n, float eps, void* stream);
+int toist_l2norm_bwd(const float* dy, const float* y, const float* nrm, float* dx, int64_t rows, int32_t n,
+                     void* stream);
+int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* probs, int64_t rows, int32_t sk,
+                           int32_t ld_s, int32_t ld_p, int32_t rows_per_batch, void* stream);
+int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores, int64_t rows, int32_t sk,
+                           int32_t ld_s, int32_t ld_p, float scale, void* stream);
+int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t batch, int32_t h, int32_t w,
+                   int32_t num_pos_feats, float temperature, void* stream);
+int toist_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out,
+                       int32_t* pos_ids, int32_t batch, int32_t len, int32_t dim, int32_t pad_id, void* stream);
+int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, const int32_t* pos_ids, float* dword,
+                        float* dpos, float* dtype0, int32_t rows, int32_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,25 +92,36 @@ def check(rc: int) -> None:
         raise ToistError(f"toist_b200 kernel call failed (status {rc}): {msg}")
 
 
+_HEADER = Path(__file__).resolve().parent.parent / "include" / "toist_b200.h"
+_SCALARS = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "float": C.c_float, "size_t": C.c_size_t}
+
+
+def parse_header():
+    """Returns {symbol: (restype, [argtypes])} for every prototype in include/toist_b200.h, so the binding cannot
+    drift from the declared C ABI."""
+    import re
+
+    text = _HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|size_t|const char\*)\s+(toist_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = C.c_char_p if ret == "const char*" else _SCALARS[ret]
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(C.POINTER(GemmDesc) if "toist_gemm_desc" in a else C.c_void_p)
+                else:
+                    ctype = a.replace("const ", "").split()[0]
+                    argtypes.append(_SCALARS[ctype])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
 def _declare(lib: C.CDLL) -> None:
-    i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
-    sig = {
-        "toist_abi_version": (C.c_int, []),
-        "toist_last_error": (C.c_char_p, []),
-        "toist_device_ok": (C.c_int, []),
-        "toist_sizeof_gemm_desc": (C.c_size_t, []),
-        "toist_gemm": (C.c_int, [C.POINTER(GemmDesc), vp]),
-    }
-    sig.update(_EXTRA_SIGS(i32, i64, f32, vp))
-    for name, (res, args) in sig.items():
-        fn = getattr(lib, name)
+    for name, (res, args) in parse_header().items():
+        fn = getattr(lib, name)  # AttributeError here means the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-
-
-def _EXTRA_SIGS(i32, i64, f32, vp):
-    """Signatures of the non-GEMM entry points (kept beside include/toist_b200.h, same order)."""
-    return {}
-
-
-EXPORTED_SYMBOLS = ["toist_abi_version", "toist_last_error", "toist_device_ok", "toist_sizeof_gemm_desc", "toist_gemm"]

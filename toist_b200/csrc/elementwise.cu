@@ -1,0 +1,404 @@
+// HBM-bound helper kernels: casts / weight preparation, stem im2col, max-pool, bias-gradient column sums,
+// activation derivatives, broadcasts.  All vectorised to 16-byte accesses where the layout allows it.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace toist {
+
+// ------------------------------------------------------------------------------------------------ weight prep
+// dst[r, c] = bf16(src[r, c] * row_scale[r])  for one or many [rows, cols] fp32 matrices (dst leading dim ldd).
+struct PrepItem {
+  const float* src;
+  __nv_bfloat16* dst;
+  const float* row_scale;  // may be null
+  int rows, cols, ldd;
+  int first_block;  // prefix of blocks (each block handles 2048 elements)
+};
+
+__global__ void weight_prep_kernel(const PrepItem* __restrict__ items, int n_items) {
+  // binary search the item owning this block
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PrepItem it = items[lo];
+  const long long total = (long long)it.rows * it.cols;
+  const long long base = (long long)(blockIdx.x - it.first_block) * 2048;
+  if (it.ldd == it.cols && it.row_scale == nullptr && (it.cols % 8 == 0)) {
+    const long long i = base + (long long)threadIdx.x * 8;
+    if (i + 8 <= total) {
+      const float4 a = *reinterpret_cast<const float4*>(it.src + i);
+      const float4 b = *reinterpret_cast<const float4*>(it.src + i + 4);
+      uint4 u;
+      u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w); u.z = pack_bf16(b.x, b.y); u.w = pack_bf16(b.z, b.w);
+      *reinterpret_cast<uint4*>(it.dst + i) = u;
+      return;
+    }
+  }
+  for (int k = 0; k < 8; ++k) {
+    const long long i = base + (long long)threadIdx.x * 8 + k;
+    if (i >= total) break;
+    const int r = (int)(i / it.cols), c = (int)(i % it.cols);
+    const float s = it.row_scale ? it.row_scale[r] : 1.f;
+    it.dst[(long long)r * it.ldd + c] = __float2bfloat16_rn(it.src[i] * s);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i);
+    const float4 b = *reinterpret_cast<const float4*>(src + i + 4);
+    uint4 u;
+    u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w); u.z = pack_bf16(b.x, b.y); u.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(dst + i) = u;
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16_rn(src[k]);
+  }
+}
+
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + i);
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+    *reinterpret_cast<float4*>(dst + i) = make_float4(f0.x, f0.y, f1.x, f1.y);
+    *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = __bfloat162float(src[k]);
+  }
+}
+
+// out = a + b (bf16), optional third addend c; 8 elements per thread
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 ua = *reinterpret_cast<const uint4*>(a + i), ub = *reinterpret_cast<const uint4*>(b + i);
+    uint4 uc = make_uint4(0, 0, 0, 0);
+    if (c) uc = *reinterpret_cast<const uint4*>(c + i);
+    const uint32_t* pa = &ua.x; const uint32_t* pb = &ub.x; const uint32_t* pc = &uc.x;
+    uint4 uo; uint32_t* po = &uo.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = unpack_bf16(pa[k]), fb = unpack_bf16(pb[k]), fc = unpack_bf16(pc[k]);
+      po[k] = pack_bf16(fa.x + fb.x + fc.x, fa.y + fb.y + fc.y);
+    }
+    *reinterpret_cast<uint4*>(out + i) = uo;
+  } else {
+    for (long long k = i; k < n; ++k)
+      out[k] = __float2bfloat16_rn(__bfloat162float(a[k]) + __bfloat162float(b[k]) + (c ? __bfloat162float(c[k]) : 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stem im2col
+// images fp32 NCHW [N,3,H,W] -> patches bf16 [N*Ho*Wo, ldk] for the 7x7/2 pad-3 stem conv; column = (ky*7+kx)*3+c.
+__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W,
+                                   int Ho, int Wo, int ldk) {
+  const long long pix = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= (long long)N * Ho * Wo) return;
+  const int ox = (int)(pix % Wo);
+  const int oy = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  __nv_bfloat16* o = out + pix * ldk;
+  for (int col = lane; col < ldk; col += 32) {
+    float v = 0.f;
+    if (col < 147) {
+      const int c = col % 3, kx = (col / 3) % 7, ky = col / 21;
+      const int iy = oy * 2 + ky - 3, ix = ox * 2 + kx - 3;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((long long)n * 3 + c) * H + iy) * W + ix];
+    }
+    o[col] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ max pool 3x3/2 pad 1
+// NHWC bf16; each thread handles 8 channels of one output pixel
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                    int W, int C, int Ho, int Wo) {
+  const int cg = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Ho * Wo * cg) return;
+  const int c8 = (int)(idx % cg);
+  long long p = idx / cg;
+  const int ox = (int)(p % Wo); p /= Wo;
+  const int oy = (int)(p % Ho);
+  const int n = (int)(p / Ho);
+  float m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = oy * 2 + dy - 1;
+    if (iy < 0 || iy >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = ox * 2 + dx - 1;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)n * H + iy) * W + ix) * C + c8 * 8);
+      const uint32_t* pu = &u.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(pu[k]);
+        m[2 * k] = fmaxf(m[2 * k], f.x);
+        m[2 * k + 1] = fmaxf(m[2 * k + 1], f.y);
+      }
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(m[0], m[1]); o.y = pack_bf16(m[2], m[3]); o.z = pack_bf16(m[4], m[5]); o.w = pack_bf16(m[6], m[7]);
+  *reinterpret_cast<uint4*>(y + (((long long)n * Ho + oy) * Wo + ox) * C + c8 * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[c] += sum_r x[r, c]   (bias gradients).  grid = (ceil(C/64), row_chunks), block = (64, 4)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long R, int C, long long ld,
+                              int rows_per_block) {
+  const int c = blockIdx.x * 64 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  float acc = 0.f;
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      if constexpr (sizeof(T) == 2) acc += __bfloat162float(x[r * ld + c]);
+      else acc += x[r * ld + c];
+    }
+  __shared__ float red[4][64];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) atomicAdd(out + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ activation grads
+// dpre = dy * gelu'(pre)   (erf GELU), bf16
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
+                                __nv_bfloat16* __restrict__ dx, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = __bfloat162float(pre[i]);
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * (cdf + x * pdf));
+}
+
+// dz = (dy + dy2) * (y > 0), bf16, 8 elements per thread
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
+                                const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 ua = *reinterpret_cast<const uint4*>(dy + i), uy = *reinterpret_cast<const uint4*>(y + i);
+    uint4 ub = make_uint4(0, 0, 0, 0);
+    if (dy2) ub = *reinterpret_cast<const uint4*>(dy2 + i);
+    const uint32_t* pa = &ua.x; const uint32_t* pb = &ub.x; const uint32_t* py = &uy.x;
+    uint4 uo; uint32_t* po = &uo.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = unpack_bf16(pa[k]), fb = unpack_bf16(pb[k]), fy = unpack_bf16(py[k]);
+      po[k] = pack_bf16(fy.x > 0.f ? fa.x + fb.x : 0.f, fy.y > 0.f ? fa.y + fb.y : 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + i) = uo;
+  } else {
+    for (long long k = i; k < n; ++k) {
+      const float g = __bfloat162float(dy[k]) + (dy2 ? __bfloat162float(dy2[k]) : 0.f);
+      out[k] = __float2bfloat16_rn(__bfloat162float(y[k]) > 0.f ? g : 0.f);
+    }
+  }
+}
+
+// dx = dy * y * (1 - y), fp32 (sigmoid output y)
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                   long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dx[i] = dy[i] * y[i] * (1.f - y[i]);
+}
+
+// out[a, c] (+)= sum_r x[a, r, c]   (e.g. query_embed gradient summed over the batch); bf16 or fp32 in, fp32 out
+template <typename T>
+__global__ void sum_mid_kernel(const T* __restrict__ x, float* __restrict__ out, int A, int R, int C, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)A * C) return;
+  const int a = (int)(i / C), c = (int)(i % C);
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) {
+    if constexpr (sizeof(T) == 2) acc += __bfloat162float(x[((long long)a * R + r) * C + c]);
+    else acc += x[((long long)a * R + r) * C + c];
+  }
+  if (accumulate) out[i] += acc; else out[i] = acc;
+}
+
+// out[a, r, c] = x[a, c]  (bf16 out; x fp32) — query_embed broadcast over the batch
+__global__ void bcast_mid_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int A, int R, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)A * R * C) return;
+  const int c = (int)(i % C);
+  const int a = (int)(i / ((long long)R * C));
+  out[i] = __float2bfloat16_rn(x[(long long)a * C + c]);
+}
+
+// NCHW fp32 -> NHWC bf16 and back (boundary conversions for tensors handed to / taken from the caller)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * C * HW) return;
+  const int c = (int)(i % C);
+  const long long p = i / C;
+  const int hw = (int)(p % HW);
+  const int n = (int)(p / HW);
+  y[i] = __float2bfloat16_rn(x[((long long)n * C + c) * HW + hw]);
+}
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int N, int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * C * HW) return;
+  const int hw = (int)(i % HW);
+  const long long p = i / HW;
+  const int c = (int)(p % C);
+  const int n = (int)(p / C);
+  y[i] = __bfloat162float(x[((long long)n * HW + hw) * C + c]);
+}
+
+}  // namespace toist
+
+using namespace toist;
+
+static inline unsigned nblk(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" {
+
+// items: device array of toist PrepItem-compatible records (see toist_b200.h toist_prep_item); total_blocks = sum of
+// ceil(rows*cols / 2048) over items.
+int toist_weight_prep(const void* items_dev, int32_t n_items, int32_t total_blocks, void* stream) {
+  TOIST_REQUIRE(items_dev != nullptr && n_items > 0 && total_blocks > 0, "toist_weight_prep: bad arguments");
+  weight_prep_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PrepItem*>(items_dev),
+                                                                     n_items);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  TOIST_REQUIRE(src && dst, "toist_cast_f32_bf16: null pointer");
+  if (n == 0) return TOIST_OK;
+  cast_f32_bf16_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
+  TOIST_REQUIRE(src && dst, "toist_cast_bf16_f32: null pointer");
+  if (n == 0) return TOIST_OK;
+  cast_bf16_f32_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, n);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {
+  TOIST_REQUIRE(a && b && out, "toist_add_bf16: null pointer");
+  if (n == 0) return TOIST_OK;
+  add_bf16_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                                   (const __nv_bfloat16*)c, (__nv_bfloat16*)out, n);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_stem_im2col(const float* images, void* patches, int32_t n, int32_t h, int32_t w, int32_t ldk, void* stream) {
+  TOIST_REQUIRE(images && patches && ldk >= 147 && ldk % 8 == 0, "toist_stem_im2col: bad arguments");
+  const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
+  const long long pix = (long long)n * ho * wo;
+  stem_im2col_kernel<<<nblk(pix, 8), 256, 0, (cudaStream_t)stream>>>(images, (__nv_bfloat16*)patches, n, h, w, ho, wo,
+                                                                     ldk);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_maxpool3x3s2(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream) {
+  TOIST_REQUIRE(x && y && c % 8 == 0, "toist_maxpool3x3s2: channels must be a multiple of 8");
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  maxpool3x3s2_kernel<<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                          n, h, w, c, ho, wo);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t cols, int64_t ld, void* stream) {
+  TOIST_REQUIRE(x && out, "toist_colsum: null pointer");
+  if (rows == 0) return TOIST_OK;
+  int chunks = (int)((rows + 511) / 512);
+  if (chunks > 256) chunks = 256;
+  const int rpb = (int)((rows + chunks - 1) / chunks);
+  dim3 grid((cols + 63) / 64, chunks), block(64, 4);
+  if (dtype == TOIST_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
+  else
+    colsum_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, out, rows, cols, ld, rpb);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream) {
+  TOIST_REQUIRE(dy && pre && dx, "toist_gelu_bwd: null pointer");
+  if (n == 0) return TOIST_OK;
+  gelu_bwd_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre,
+                                                                  (__nv_bfloat16*)dx, n);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_relu_bwd(const void* dy, const void* dy2, const void* y, void* out, int64_t n, void* stream) {
+  TOIST_REQUIRE(dy && y && out, "toist_relu_bwd: null pointer");
+  if (n == 0) return TOIST_OK;
+  relu_bwd_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
+                                                                   (const __nv_bfloat16*)y, (__nv_bfloat16*)out, n);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+  TOIST_REQUIRE(dy && y && dx, "toist_sigmoid_bwd: null pointer");
+  if (n == 0) return TOIST_OK;
+  sigmoid_bwd_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_sum_mid(const void* x, int32_t dtype, float* out, int32_t a, int32_t r, int32_t c, int32_t accumulate,
+                  void* stream) {
+  TOIST_REQUIRE(x && out, "toist_sum_mid: null pointer");
+  const long long n = (long long)a * c;
+  if (n == 0) return TOIST_OK;
+  if (dtype == TOIST_BF16)
+    sum_mid_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, a, r, c, accumulate);
+  else
+    sum_mid_kernel<float><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, out, a, r, c, accumulate);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_bcast_mid(const float* x, void* out, int32_t a, int32_t r, int32_t c, void* stream) {
+  TOIST_REQUIRE(x && out, "toist_bcast_mid: null pointer");
+  const long long n = (long long)a * r * c;
+  if (n == 0) return TOIST_OK;
+  bcast_mid_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, a, r, c);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_nchw_to_nhwc(const float* x, void* y, int32_t n, int32_t c, int32_t hw, void* stream) {
+  TOIST_REQUIRE(x && y, "toist_nchw_to_nhwc: null pointer");
+  const long long t = (long long)n * c * hw;
+  if (t == 0) return TOIST_OK;
+  nchw_to_nhwc_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, c, hw);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_nhwc_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, void* stream) {
+  TOIST_REQUIRE(x && y, "toist_nhwc_to_nchw: null pointer");
+  const long long t = (long long)n * c * hw;
+  if (t == 0) return TOIST_OK;
+  nhwc_to_nchw_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n, c, hw);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+}  // extern "C"

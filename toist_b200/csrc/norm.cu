@@ -1,0 +1,397 @@
+// Row-wise normalisations and softmax (one warp per row, warp-shuffle reductions, fp32 statistics):
+// LayerNorm fwd/bwd (models/transformer.py:279-280,346-349,484; RoBERTa LayerNorms), L2 normalise fwd/bwd
+// (models/mdetr.py:430-433), key-padding-masked attention softmax fwd/bwd (nn.MultiheadAttention,
+// models/transformer.py:298,378,394), sine position embedding (models/position_encoding.py:30-49),
+// RoBERTa embedding gather / scatter.
+#include <math.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace toist {
+
+constexpr int kMaxPerLane = 32;  // rows up to 1024 wide
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p, long long i) {
+  if constexpr (sizeof(T) == 2) return __bfloat162float(p[i]);
+  else return p[i];
+}
+template <typename T>
+__device__ __forceinline__ void st_from_float(T* p, long long i, float v) {
+  if constexpr (sizeof(T) == 2) p[i] = __float2bfloat16_rn(v);
+  else p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+template <typename TIn>
+__global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y16,
+                                     float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd,
+                                     long long rows, int N, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const TIn* xr = x + row * N;
+  float v[kMaxPerLane];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxPerLane; ++k) {
+    const int c = lane + 32 * k;
+    v[k] = c < N ? ld_as_float(xr, c) : 0.f;
+    s += v[k];
+  }
+  const float mu = warp_sum(s) / (float)N;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxPerLane; ++k) {
+    const int c = lane + 32 * k;
+    const float d = c < N ? v[k] - mu : 0.f;
+    sq += d * d;
+  }
+  const float rs = rsqrtf(warp_sum(sq) / (float)N + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxPerLane; ++k) {
+    const int c = lane + 32 * k;
+    if (c < N) {
+      const float o = (v[k] - mu) * rs * gamma[c] + beta[c];
+      if (y16) y16[row * N + c] = __float2bfloat16_rn(o);
+      if (y32) y32[row * N + c] = o;
+    }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += dy * xhat;  dbeta += dy
+template <typename TX, typename TDy, typename TDx>
+__global__ void layernorm_bwd_kernel(const TDy* __restrict__ dy, const TDy* __restrict__ dy2, const TX* __restrict__ x,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, TDx* __restrict__ dx, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, long long rows, int N) {
+  extern __shared__ float acc[];  // [2][N]
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[kMaxPerLane], g[kMaxPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const int c = lane + 32 * k;
+      if (c < N) {
+        float d = ld_as_float(dy, row * N + c);
+        if (dy2) d += ld_as_float(dy2, row * N + c);
+        xh[k] = (ld_as_float(x, row * N + c) - mu) * rs;
+        g[k] = d * gamma[c];
+        s1 += g[k];
+        s2 += g[k] * xh[k];
+        if (dgamma) {
+          atomicAdd(&acc[c], d * xh[k]);
+          atomicAdd(&acc[N + c], d);
+        }
+      } else {
+        xh[k] = 0.f;
+        g[k] = 0.f;
+      }
+    }
+    s1 = warp_sum(s1) / (float)N;
+    s2 = warp_sum(s2) / (float)N;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const int c = lane + 32 * k;
+      if (c < N) st_from_float(dx, row * N + c, rs * (g[k] - s1 - xh[k] * s2));
+    }
+  }
+  __syncthreads();
+  if (dgamma)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      atomicAdd(dgamma + i, acc[i]);
+      atomicAdd(dbeta + i, acc[N + i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalise
+// y = x / max(||x||, eps) per row (fp32); bwd: dx = (dy - y * (y . dy)) / max(||x||, eps)
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ nrm,
+                                  long long rows, int N, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < N; c += 32) s += x[row * N + c] * x[row * N + c];
+  const float n = fmaxf(sqrtf(warp_sum(s)), eps);
+  if (lane == 0) nrm[row] = n;
+  for (int c = lane; c < N; c += 32) y[row * N + c] = x[row * N + c] / n;
+}
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                  const float* __restrict__ nrm, float* __restrict__ dx, long long rows, int N) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < N; c += 32) s += dy[row * N + c] * y[row * N + c];
+  s = warp_sum(s);
+  const float inv = 1.f / nrm[row];
+  for (int c = lane; c < N; c += 32) dx[row * N + c] = (dy[row * N + c] - y[row * N + c] * s) * inv;
+}
+
+// ------------------------------------------------------------------------------------------------ attention softmax
+// scores fp32 [rows, ld_s] (already scaled) -> P bf16 [rows, ld_p]; rows = B*H*Sq, key mask [B, Sk] (1 = padded)
+__global__ void attn_softmax_fwd_kernel(const float* __restrict__ s, const uint8_t* __restrict__ kmask,
+                                        __nv_bfloat16* __restrict__ p, long long rows, int Sk, int ld_s, int ld_p,
+                                        int rows_per_batch) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + row * ld_s;
+  const uint8_t* km = kmask ? kmask + (row / rows_per_batch) * Sk : nullptr;
+  float mx = -INFINITY;
+  for (int c = lane; c < Sk; c += 32) {
+    const float v = (km && km[c]) ? -INFINITY : sr[c];
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < Sk; c += 32) {
+    const float v = (km && km[c]) ? -INFINITY : sr[c];
+    sum += expf(v - mx);  // all keys masked -> NaN, as in the reference
+  }
+  sum = warp_sum(sum);
+  __nv_bfloat16* pr = p + row * ld_p;
+  for (int c = lane; c < ld_p; c += 32) {
+    float o = 0.f;
+    if (c < Sk) {
+      const float v = (km && km[c]) ? -INFINITY : sr[c];
+      o = expf(v - mx) / sum;
+    }
+    pr[c] = __float2bfloat16_rn(o);
+  }
+}
+
+// dS = P * (dP - sum_k dP * P) * scale   (dP fp32 [rows, ld_s], P bf16, dS bf16 [rows, ld_p])
+__global__ void attn_softmax_bwd_kernel(const float* __restrict__ dp, const __nv_bfloat16* __restrict__ p,
+                                        __nv_bfloat16* __restrict__ ds, long long rows, int Sk, int ld_s, int ld_p,
+                                        float scale) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* dr = dp + row * ld_s;
+  const __nv_bfloat16* pr = p + row * ld_p;
+  float dot = 0.f;
+  for (int c = lane; c < Sk; c += 32) dot += dr[c] * __bfloat162float(pr[c]);
+  dot = warp_sum(dot);
+  __nv_bfloat16* o = ds + row * ld_p;
+  for (int c = lane; c < ld_p; c += 32) {
+    float v = 0.f;
+    if (c < Sk) v = __bfloat162float(pr[c]) * (dr[c] - dot) * scale;
+    o[c] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sine position
+// mask [B,H,W] (1 = padded) -> pos fp32 + bf16 in sequence layout [(y*W+x), B, 2F]; first F = y, last F = x
+__global__ void pos_sine_kernel(const uint8_t* __restrict__ mask, float* __restrict__ pos32,
+                                __nv_bfloat16* __restrict__ pos16, int B, int H, int W, int F, float temperature,
+                                long long ld_rows /* B*2F */) {
+  extern __shared__ float emb[];  // y_embed[H*W], x_embed[H*W]
+  float* ye = emb;
+  float* xe = emb + H * W;
+  const int b = blockIdx.x;
+  const uint8_t* m = mask + (size_t)b * H * W;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    float run = 0.f;
+    for (int y = 0; y < H; ++y) {
+      run += m[y * W + x] ? 0.f : 1.f;
+      ye[y * W + x] = run;
+    }
+  }
+  for (int y = threadIdx.x; y < H; y += blockDim.x) {
+    float run = 0.f;
+    for (int x = 0; x < W; ++x) {
+      run += m[y * W + x] ? 0.f : 1.f;
+      xe[y * W + x] = run;
+    }
+  }
+  __syncthreads();
+  const float scale = 6.283185307179586f, eps = 1e-6f;
+  for (int i = threadIdx.x; i < H * W * 2 * F; i += blockDim.x) {
+    const int c = i % (2 * F);
+    const int pix = i / (2 * F);
+    const int y = pix / W, x = pix % W;
+    const bool is_y = c < F;
+    const int k = is_y ? c : c - F;
+    const float e = is_y ? ye[pix] / (ye[(H - 1) * W + x] + eps) * scale : xe[pix] / (xe[y * W + (W - 1)] + eps) * scale;
+    const float dim_t = powf(temperature, (float)(2 * (k / 2)) / (float)F);
+    const float v = e / dim_t;
+    const float o = (k & 1) ? cosf(v) : sinf(v);
+    const long long off = (long long)pix * ld_rows + (long long)b * 2 * F + c;
+    if (pos32) pos32[off] = o;
+    if (pos16) pos16[off] = __float2bfloat16_rn(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RoBERTa embeddings
+// x[b*L + l, :] = word[id] + pos[pos_id] + type[0];  pos_id = cumsum(id != pad)[l] * (id != pad) + pad
+__global__ void embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
+                                    const float* __restrict__ posw, const float* __restrict__ type0,
+                                    float* __restrict__ out, int* __restrict__ pos_ids, int L, int E, int pad_id) {
+  const int row = blockIdx.x;
+  const int b = row / L, l = row % L;
+  const long long id = ids[row];
+  int cnt = 0;
+  for (int k = 0; k <= l; ++k) cnt += ids[(long long)b * L + k] != pad_id;
+  const int pid = (id != pad_id ? cnt : 0) + pad_id;
+  if (threadIdx.x == 0 && pos_ids) pos_ids[row] = pid;
+  for (int c = threadIdx.x; c < E; c += blockDim.x)
+    out[(long long)row * E + c] = word[id * E + c] + posw[(long long)pid * E + c] + type0[c];
+}
+
+template <typename T>
+__global__ void embed_scatter_kernel(const T* __restrict__ dx, const long long* __restrict__ ids,
+                                     const int* __restrict__ pos_ids, float* __restrict__ dword,
+                                     float* __restrict__ dpos, float* __restrict__ dtype0, int E) {
+  const int row = blockIdx.x;
+  const long long id = ids[row];
+  const int pid = pos_ids[row];
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    const float g = ld_as_float(dx, (long long)row * E + c);
+    if (dword) atomicAdd(dword + id * E + c, g);
+    if (dpos) atomicAdd(dpos + (long long)pid * E + c, g);
+    if (dtype0) atomicAdd(dtype0 + c, g);
+  }
+}
+
+}  // namespace toist
+
+using namespace toist;
+
+extern "C" {
+
+int toist_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, void* y_bf16,
+                        float* y_f32, float* mean, float* rstd, int64_t rows, int32_t n, float eps, void* stream) {
+  TOIST_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "toist_layernorm_fwd: null pointer");
+  TOIST_REQUIRE(n >= 1 && n <= 32 * kMaxPerLane, "toist_layernorm_fwd: width %d unsupported (max 1024)", n);
+  if (rows == 0) return TOIST_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (x_dtype == TOIST_F32)
+    layernorm_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta,
+                                                                        (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, n, eps);
+  else
+    layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, n, eps);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+// dy (and optional dy2, same dtype) are summed; dx dtype selectable; dgamma/dbeta accumulate (may be null together)
+int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const void* x, int32_t x_dtype,
+                        const float* mean, const float* rstd, const float* gamma, void* dx, int32_t dx_dtype,
+                        float* dgamma, float* dbeta, int64_t rows, int32_t n, void* stream) {
+  TOIST_REQUIRE(dy && x && mean && rstd && gamma && dx, "toist_layernorm_bwd: null pointer");
+  TOIST_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "toist_layernorm_bwd: pass both dgamma and dbeta or neither");
+  TOIST_REQUIRE(n >= 1 && n <= 32 * kMaxPerLane, "toist_layernorm_bwd: width %d unsupported (max 1024)", n);
+  if (rows == 0) return TOIST_OK;
+  unsigned grid = (unsigned)((rows + 7) / 8);
+  if (grid > 296) grid = 296;
+  const size_t smem = 2 * (size_t)n * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_BWD(TX, TDY, TDX)                                                                                      \
+  layernorm_bwd_kernel<TX, TDY, TDX><<<grid, 256, smem, st>>>((const TDY*)dy, (const TDY*)dy2, (const TX*)x, mean, \
+                                                              rstd, gamma, (TDX*)dx, dgamma, dbeta, rows, n)
+  const int key = (x_dtype << 2) | (dy_dtype << 1) | dx_dtype;
+  switch (key) {
+    case 0: LN_BWD(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
+    case 1: LN_BWD(__nv_bfloat16, __nv_bfloat16, float); break;
+    case 2: LN_BWD(__nv_bfloat16, float, __nv_bfloat16); break;
+    case 3: LN_BWD(__nv_bfloat16, float, float); break;
+    case 4: LN_BWD(float, __nv_bfloat16, __nv_bfloat16); break;
+    case 5: LN_BWD(float, __nv_bfloat16, float); break;
+    case 6: LN_BWD(float, float, __nv_bfloat16); break;
+    default: LN_BWD(float, float, float); break;
+  }
+#undef LN_BWD
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_l2norm_fwd(const float* x, float* y, float* nrm, int64_t rows, int32_t n, float eps, void* stream) {
+  TOIST_REQUIRE(x && y && nrm, "toist_l2norm_fwd: null pointer");
+  if (rows == 0) return TOIST_OK;
+  l2norm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, y, nrm, rows, n, eps);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_l2norm_bwd(const float* dy, const float* y, const float* nrm, float* dx, int64_t rows, int32_t n,
+                     void* stream) {
+  TOIST_REQUIRE(dy && y && nrm && dx, "toist_l2norm_bwd: null pointer");
+  if (rows == 0) return TOIST_OK;
+  l2norm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dy, y, nrm, dx, rows, n);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* probs, int64_t rows, int32_t sk,
+                           int32_t ld_s, int32_t ld_p, int32_t rows_per_batch, void* stream) {
+  TOIST_REQUIRE(scores && probs && rows_per_batch > 0, "toist_attn_softmax_fwd: bad arguments");
+  if (rows == 0) return TOIST_OK;
+  attn_softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      scores, key_mask, (__nv_bfloat16*)probs, rows, sk, ld_s, ld_p, rows_per_batch);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores, int64_t rows, int32_t sk,
+                           int32_t ld_s, int32_t ld_p, float scale, void* stream) {
+  TOIST_REQUIRE(dprobs && probs && dscores, "toist_attn_softmax_bwd: null pointer");
+  if (rows == 0) return TOIST_OK;
+  attn_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      dprobs, (const __nv_bfloat16*)probs, (__nv_bfloat16*)dscores, rows, sk, ld_s, ld_p, scale);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t batch, int32_t h, int32_t w,
+                   int32_t num_pos_feats, float temperature, void* stream) {
+  TOIST_REQUIRE(mask && (pos_f32 || pos_bf16), "toist_pos_sine: null pointer");
+  const size_t smem = 2 * (size_t)h * w * sizeof(float);
+  TOIST_REQUIRE(smem <= 200 * 1024, "toist_pos_sine: feature map %dx%d too large", h, w);
+  static bool configured = false;
+  if (!configured) {
+    TOIST_CHECK_CUDA(cudaFuncSetAttribute(pos_sine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  pos_sine_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, batch, h, w,
+                                                              num_pos_feats, temperature,
+                                                              (long long)batch * 2 * num_pos_feats);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out,
+                       int32_t* pos_ids, int32_t batch, int32_t len, int32_t dim, int32_t pad_id, void* stream) {
+  TOIST_REQUIRE(ids && word && pos && type0 && out, "toist_embed_gather: null pointer");
+  if (batch * len == 0) return TOIST_OK;
+  embed_gather_kernel<<<batch * len, 256, 0, (cudaStream_t)stream>>>((const long long*)ids, word, pos, type0, out,
+                                                                     pos_ids, len, dim, pad_id);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, const int32_t* pos_ids, float* dword,
+                        float* dpos, float* dtype0, int32_t rows, int32_t dim, void* stream) {
+  TOIST_REQUIRE(dx && ids && pos_ids, "toist_embed_scatter: null pointer");
+  if (rows == 0) return TOIST_OK;
+  if (dx_dtype == TOIST_BF16)
+    embed_scatter_kernel<__nv_bfloat16><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, dim);
+  else
+    embed_scatter_kernel<float><<<rows, 256, 0, (cudaStream_t)stream>>>((const float*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, dim);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+}  // extern "C"

@@ -254,3 +254,325 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, stride: i
          out_strides=(kh * kw * cin, 0, 0), taps=taps, stride=(stride, stride), splits=splits, row_scale=row_scale,
          accumulate=accumulate)
     return dw
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def _L():
+    return _lib.load()
+
+
+def _ck(rc: int, n: int = 1) -> None:
+    _lib.check(rc)
+    _count(n)
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy (contiguous)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x, dtype=torch.bfloat16)
+    _ck(_L().toist_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+def cast_f32(x: torch.Tensor) -> torch.Tensor:
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    y = torch.empty_like(x, dtype=torch.float32)
+    _ck(_L().toist_cast_bf16_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+def add_bf16(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert a.dtype == b.dtype == torch.bfloat16 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    _ck(_L().toist_add_bf16(a.data_ptr(), b.data_ptr(), _ptr(c), out.data_ptr(), a.numel(), _stream()))
+    return out
+
+
+class WeightPrep:
+    """One launch that refreshes every bf16 shadow weight from its fp32 master (optionally folding a per-row scale,
+    e.g. the FrozenBatchNorm scale of the following norm layer)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items = []  # (src, dst, scale, rows, cols, ldd)
+        self._table = None
+        self._blocks = 0
+        self._keep = []
+
+    def add(self, src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, ldd: Optional[int] = None,
+            row_scale: Optional[torch.Tensor] = None) -> None:
+        assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16
+        self.items.append((src, dst, row_scale, rows, cols, ldd or cols))
+        self._table = None
+
+    def _build(self) -> None:
+        import struct
+
+        buf = bytearray()
+        blocks = 0
+        for src, dst, sc, rows, cols, ldd in self.items:
+            buf += struct.pack("<QQQiiii", src.data_ptr(), dst.data_ptr(), 0 if sc is None else sc.data_ptr(), rows,
+                               cols, ldd, blocks)
+            blocks += -(-(rows * cols) // 2048)
+        host = torch.frombuffer(buf, dtype=torch.uint8).clone()
+        self._table = host.to(self.device)
+        self._blocks = blocks
+        self._ptrs = [(s.data_ptr(), d.data_ptr()) for s, d, *_ in self.items]
+
+    def run(self) -> None:
+        if not self.items:
+            return
+        if self._table is None or self._ptrs != [(s.data_ptr(), d.data_ptr()) for s, d, *_ in self.items]:
+            self._build()
+        _ck(_L().toist_weight_prep(self._table.data_ptr(), len(self.items), self._blocks, _stream()))
+
+
+def stem_im2col(images: torch.Tensor, ldk: int = 192) -> torch.Tensor:
+    n, c, h, w = images.shape
+    assert c == 3 and images.dtype == torch.float32 and images.is_contiguous()
+    ho, wo = conv_out_size(h, 7, 2, 3), conv_out_size(w, 7, 2, 3)
+    out = torch.empty((n * ho * wo, ldk), dtype=torch.bfloat16, device=images.device)
+    _ck(_L().toist_stem_im2col(images.data_ptr(), out.data_ptr(), n, h, w, ldk, _stream()))
+    return out
+
+
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, 3, 2, 1), conv_out_size(w, 3, 2, 1)
+    y = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+    _ck(_L().toist_maxpool3x3s2(x.data_ptr(), y.data_ptr(), n, h, w, c, _stream()))
+    return y
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[c] += sum_r x[r, c] (bias gradient)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.float32
+    _ck(_L().toist_colsum(x.data_ptr(), _dt(x), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0), _stream()))
+    return out
+
+
+def gelu_bwd(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    dx = torch.empty_like(dy)
+    _ck(_L().toist_gelu_bwd(dy.data_ptr(), pre.data_ptr(), dx.data_ptr(), dy.numel(), _stream()))
+    return dx
+
+
+def sigmoid_bwd(dy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    dx = torch.empty_like(dy)
+    _ck(_L().toist_sigmoid_bwd(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.numel(), _stream()))
+    return dx
+
+
+def sum_mid(x: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    a, r, c = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((a, c), dtype=torch.float32, device=x.device)
+    _ck(_L().toist_sum_mid(x.data_ptr(), _dt(x), out.data_ptr(), a, r, c, 1 if accumulate else 0, _stream()))
+    return out
+
+
+def bcast_mid(x: torch.Tensor, r: int) -> torch.Tensor:
+    a, c = x.shape
+    out = torch.empty((a, r, c), dtype=torch.bfloat16, device=x.device)
+    _ck(_L().toist_bcast_mid(x.data_ptr(), out.data_ptr(), a, r, c, _stream()))
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _ck(_L().toist_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), n, c, h * w, _stream()))
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _ck(_L().toist_nhwc_to_nchw(x.data_ptr(), y.data_ptr(), n, c, h * w, _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ norms / softmax
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, want_f32: bool = False,
+                  want_bf16: bool = True, save_stats: bool = True):
+    """x [rows, N] (fp32 or bf16) -> (y_bf16 | None, y_f32 | None, mean, rstd)."""
+    rows, n = x.shape
+    assert x.is_contiguous()
+    y16 = torch.empty((rows, n), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    y32 = torch.empty((rows, n), dtype=torch.float32, device=x.device) if want_f32 else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    _ck(_L().toist_layernorm_fwd(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), _ptr(y16), _ptr(y32),
+                                 _ptr(mean), _ptr(rstd), rows, n, eps, _stream()))
+    return y16, y32, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
+                  dy2: Optional[torch.Tensor] = None, dgamma: Optional[torch.Tensor] = None,
+                  dbeta: Optional[torch.Tensor] = None, dx_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    rows, n = x.shape
+    assert dy.is_contiguous() and x.is_contiguous() and (dy2 is None or (dy2.dtype == dy.dtype and dy2.is_contiguous()))
+    dx = torch.empty((rows, n), dtype=dx_dtype, device=x.device)
+    _ck(_L().toist_layernorm_bwd(dy.data_ptr(), _ptr(dy2), _dt(dy), x.data_ptr(), _dt(x), mean.data_ptr(),
+                                 rstd.data_ptr(), gamma.data_ptr(), dx.data_ptr(), _dt(dx), _ptr(dgamma), _ptr(dbeta),
+                                 rows, n, _stream()))
+    return dx
+
+
+def l2norm_fwd(x: torch.Tensor, eps: float = 1e-12):
+    rows, n = x.shape
+    y = torch.empty_like(x)
+    nrm = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _ck(_L().toist_l2norm_fwd(x.data_ptr(), y.data_ptr(), nrm.data_ptr(), rows, n, eps, _stream()))
+    return y, nrm
+
+
+def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, nrm: torch.Tensor) -> torch.Tensor:
+    rows, n = y.shape
+    dx = torch.empty_like(y)
+    _ck(_L().toist_l2norm_bwd(dy.data_ptr(), y.data_ptr(), nrm.data_ptr(), dx.data_ptr(), rows, n, _stream()))
+    return dx
+
+
+def pos_sine(mask_u8: torch.Tensor, num_pos_feats: int, temperature: float = 10000.0):
+    """mask [B,H,W] uint8 -> (pos_f32, pos_bf16) each [H*W, B, 2*num_pos_feats]."""
+    b, h, w = mask_u8.shape
+    assert mask_u8.dtype == torch.uint8 and mask_u8.is_contiguous()
+    p32 = torch.empty((h * w, b, 2 * num_pos_feats), dtype=torch.float32, device=mask_u8.device)
+    p16 = torch.empty((h * w, b, 2 * num_pos_feats), dtype=torch.bfloat16, device=mask_u8.device)
+    _ck(_L().toist_pos_sine(mask_u8.data_ptr(), p32.data_ptr(), p16.data_ptr(), b, h, w, num_pos_feats, temperature,
+                            _stream()))
+    return p32, p16
+
+
+def embed_gather(ids: torch.Tensor, word: torch.Tensor, pos: torch.Tensor, type_w: torch.Tensor, pad_id: int = 1):
+    b, l = ids.shape
+    e = word.shape[1]
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    out = torch.empty((b * l, e), dtype=torch.float32, device=ids.device)
+    pos_ids = torch.empty(b * l, dtype=torch.int32, device=ids.device)
+    _ck(_L().toist_embed_gather(ids.data_ptr(), word.data_ptr(), pos.data_ptr(), type_w.data_ptr(), out.data_ptr(),
+                                pos_ids.data_ptr(), b, l, e, pad_id, _stream()))
+    return out, pos_ids
+
+
+def embed_scatter(dx: torch.Tensor, ids: torch.Tensor, pos_ids: torch.Tensor, dword: Optional[torch.Tensor],
+                  dpos: Optional[torch.Tensor], dtype0: Optional[torch.Tensor]) -> None:
+    rows, e = dx.shape
+    _ck(_L().toist_embed_scatter(dx.data_ptr(), _dt(dx), ids.data_ptr(), pos_ids.data_ptr(), _ptr(dword), _ptr(dpos),
+                                 _ptr(dtype0), rows, e, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ attention (unfused)
+def _ld8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8: Optional[torch.Tensor], nhead: int,
+                  need_probs: bool = True):
+    """Multi-head attention core on packed projections.
+
+    q [Sq, B, E], k [Sk, B, E], v [Sk, B, E]: bf16 views whose last dim is contiguous (they may be column slices of a
+    wider projection output).  Returns (ctx bf16 [Sq, B, E], probs bf16 [B, H, Sq, ld] or None).
+    Three launches: QK^T (fp32 scores, scaled), masked softmax, PV.
+    """
+    sq, b, e = q.shape
+    sk = k.shape[0]
+    d = e // nhead
+    ld = _ld8(sk)
+    dev = q.device
+    scores = torch.empty((b, nhead, sq, ld), dtype=torch.float32, device=dev)
+    gemm(GEMM_FWD, t4(q, (d, sq, nhead, b), (1, q.stride(0), d, q.stride(1))),
+         t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), scores, ext=(sq, nhead, b), tile=(128, 1, 1),
+         n_cols=sk, out_strides=(ld, sq * ld, nhead * sq * ld), k_per_tap=d, b_batched=True, alpha=float(d) ** -0.5)
+    probs = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=dev)
+    _ck(_L().toist_attn_softmax_fwd(scores.data_ptr(), _ptr(key_mask_u8), probs.data_ptr(), b * nhead * sq, sk, ld, ld,
+                                    nhead * sq, _stream()))
+    ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=dev)
+    gemm(GEMM_DGRAD, t4(probs, (sk, sq, nhead, b), (1, ld, sq * ld, nhead * sq * ld)),
+         t4(v, (d, sk, nhead, b), (1, v.stride(0), d, v.stride(1))), ctx, ext=(sq, nhead, b), tile=(128, 1, 1),
+         n_cols=d, out_strides=(b * e, d, e), k_per_tap=sk, b_batched=True)
+    return ctx, (probs if need_probs else None)
+
+
+def attention_bwd(dctx: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, probs: torch.Tensor,
+                  nhead: int, dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor) -> None:
+    """Backward of attention_fwd.  dq/dk/dv are bf16 outputs with the same [S, B, E] indexing as q/k/v (they may be
+    column slices of one packed gradient buffer)."""
+    sq, b, e = q.shape
+    sk = k.shape[0]
+    d = e // nhead
+    ld = probs.shape[-1]
+    dev = q.device
+    sP = (1, ld, sq * ld, nhead * sq * ld)
+    # dV[k] = P^T dO      (WGRAD mode: reduction over queries, batched over (h, b))
+    gemm(GEMM_WGRAD, t4(probs, (sk, sq, nhead, b), sP),
+         t4(dctx, (d, sq, nhead, b), (1, dctx.stride(0), d, dctx.stride(1))), dv, ext=(sq, 1, 1), tile=(64, 1, 1),
+         n_cols=d, m_rows=sk, out_strides=(dv.stride(0), d, dv.stride(1)), batch=(nhead, b))
+    # dP = dO V^T
+    dp = torch.empty((b, nhead, sq, ld), dtype=torch.float32, device=dev)
+    gemm(GEMM_FWD, t4(dctx, (d, sq, nhead, b), (1, dctx.stride(0), d, dctx.stride(1))),
+         t4(v, (d, sk, nhead, b), (1, v.stride(0), d, v.stride(1))), dp, ext=(sq, nhead, b), tile=(128, 1, 1),
+         n_cols=sk, out_strides=(ld, sq * ld, nhead * sq * ld), k_per_tap=d, b_batched=True)
+    ds = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=dev)
+    _ck(_L().toist_attn_softmax_bwd(dp.data_ptr(), probs.data_ptr(), ds.data_ptr(), b * nhead * sq, sk, ld, ld,
+                                    float(d) ** -0.5, _stream()))
+    # dQ = dS K   (DGRAD mode: B = K is MN-major, reduction over keys)
+    gemm(GEMM_DGRAD, t4(ds, (sk, sq, nhead, b), sP), t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), dq,
+         ext=(sq, nhead, b), tile=(128, 1, 1), n_cols=d, out_strides=(dq.stride(0), d, dq.stride(1)), k_per_tap=sk,
+         b_batched=True)
+    # dK = dS^T Q
+    gemm(GEMM_WGRAD, t4(ds, (sk, sq, nhead, b), sP), t4(q, (d, sq, nhead, b), (1, q.stride(0), d, q.stride(1))), dk,
+         ext=(sq, 1, 1), tile=(64, 1, 1), n_cols=d, m_rows=sk, out_strides=(dk.stride(0), d, dk.stride(1)),
+         batch=(nhead, b))
+
+
+# ------------------------------------------------------------------------------------------------ matcher / criterion
+def match_cost(logits: torch.Tensor, boxes: torch.Tensor, tgt_boxes: torch.Tensor, tgt_count: torch.Tensor,
+               posmap: torch.Tensor, w_class: float, w_bbox: float, w_giou: float) -> torch.Tensor:
+    """logits [L,B,Q,C], boxes [L,B,Q,4] fp32; padded targets -> cost [L,B,Q,Tmax] fp32."""
+    L, B, Q, Cc = logits.shape
+    tmax = tgt_boxes.shape[1]
+    cost = torch.empty((L, B, Q, tmax), dtype=torch.float32, device=logits.device)
+    _ck(_L().toist_match_cost(logits.data_ptr(), boxes.data_ptr(), tgt_boxes.data_ptr(), tgt_count.data_ptr(),
+                              posmap.data_ptr(), cost.data_ptr(), L, B, Q, Cc, tmax, w_class, w_bbox, w_giou,
+                              _stream()))
+    return cost
+
+
+def lsap_device(cost: torch.Tensor, tgt_count: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    L, B, Q, tmax = cost.shape
+    match_q = torch.empty((L, B, tmax), dtype=torch.int32, device=cost.device)
+    _ck(_L().toist_lsap_device(cost.data_ptr(), tgt_count.data_ptr(), match_q.data_ptr(), flags.data_ptr(), L * B, B, Q,
+                               tmax, _stream()))
+    return match_q
+
+
+def lsap_host(cost) -> Tuple["np.ndarray", "np.ndarray"]:
+    """scipy.optimize.linear_sum_assignment work-alike on the host (C++ in libtoist_b200.so)."""
+    import numpy as np
+
+    c = np.ascontiguousarray(np.asarray(cost, dtype=np.float64))
+    if c.ndim != 2:
+        raise ValueError("expected a matrix")
+    nr, nc = c.shape
+    n = min(nr, nc)
+    ri = np.zeros(n, dtype=np.int64)
+    ci = np.zeros(n, dtype=np.int64)
+    rc = _L().toist_lsap_f64(c.ctypes.data, nr, nc, ri.ctypes.data, ci.ctypes.data)
+    if rc == -4:
+        raise ValueError(_L().toist_last_error().decode())
+    if rc < 0:
+        _lib.check(rc)
+    return ri, ci
+
+
+def relu_bwd(dy: torch.Tensor, y: torch.Tensor, dy2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(dy + dy2) * (y > 0), bf16."""
+    assert dy.is_contiguous() and y.is_contiguous() and dy.dtype == torch.bfloat16
+    out = torch.empty_like(dy)
+    _ck(_L().toist_relu_bwd(dy.data_ptr(), _ptr(dy2), y.data_ptr(), out.data_ptr(), dy.numel(), _stream()))
+    return out
