@@ -147,10 +147,16 @@ int toist_contrastive_align(const float* proj_queries, const float* proj_tokens,
                             const int32_t* tgt_count, const uint8_t* tok_pos, const float* num_boxes, float* img_loss,
                             float* dpq, float* dpt, int32_t n_layers, int32_t batch, int32_t n_queries,
                             int32_t n_tokens, int32_t dim, int32_t t_max, float temperature, void* stream);
-/* out [5, L]: loss_ce, loss_bbox, loss_giou, cardinality_error, loss_contrastive_align (img_loss may be null) */
+/* out [5, L]: loss_ce, loss_bbox, loss_giou, cardinality_error, loss_contrastive_align (img_loss may be null).
+ * flags (may be null): the word written by toist_lsap_device; when non-zero loss_ce becomes NaN so that the caller's
+ * non-finite-loss guard (engine.py:82-85) fires, mirroring scipy's ValueError without a device synchronisation. */
 int toist_criterion_reduce(const float* row_loss, const float* pair_l1, const float* pair_giou, const int32_t* card,
-                           const float* img_loss, const int32_t* tgt_count, const float* num_boxes, float* out,
-                           int32_t n_layers, int32_t batch, int32_t n_queries, int32_t t_max, void* stream);
+                           const float* img_loss, const int32_t* tgt_count, const float* num_boxes,
+                           const int32_t* flags, float* out, int32_t n_layers, int32_t batch, int32_t n_queries,
+                           int32_t t_max, void* stream);
+/* y[l, i] = x1[l, i] * g1[l] + x2[l, i] * g2[l] */
+int toist_scale_layers2(const float* x1, const float* g1, const float* x2, const float* g2, float* y, int32_t n_layers,
+                        int64_t n, void* stream);
 /* reduce == 0: y[l, i] = x[l, i] * g[l];  reduce == 1: y[i] = sum_l x[l, i] * g[l] */
 int toist_scale_layers(const float* x, const float* g, float* y, int32_t n_layers, int64_t n, int32_t reduce,
                        void* stream);
@@ -164,10 +170,14 @@ typedef struct toist_prep_item {
   const float* row_scale; /* optional FrozenBatchNorm scale folded per output channel (backbone.py:48-58) */
   int32_t rows, cols, ldd;
   int32_t first_block; /* prefix sum of ceil(rows * cols / 2048) over the preceding items */
+  int32_t taps;        /* > 1: src is a conv weight [rows][cols/taps][taps] (OIHW), dst gets [rows][taps][cols/taps] */
+  int32_t pad_;
 } toist_prep_item;
 int toist_weight_prep(const void* items_dev, int32_t n_items, int32_t total_blocks, void* stream);
 int toist_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int toist_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* dst[r, 0:ld] = bf16(src[r, 0:n]), zero padded (rows narrower than 16 bytes cannot be described to TMA) */
+int toist_cast_pad_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n, int32_t ld, void* stream);
 int toist_add_bf16(const void* a, const void* b, const void* c /* may be null */, void* out, int64_t n, void* stream);
 /* 7x7 stride-2 pad-3 stem (torchvision resnet conv1 via backbone.py:75): fp32 NCHW -> bf16 patches [N*Ho*Wo, ldk] */
 int toist_stem_im2col(const float* images, void* patches, int32_t n, int32_t h, int32_t w, int32_t ldk, void* stream);
@@ -182,6 +192,14 @@ int toist_sum_mid(const void* x, int32_t dtype, float* out, int32_t a, int32_t r
 int toist_bcast_mid(const float* x, void* out, int32_t a, int32_t r, int32_t c, void* stream);
 int toist_nchw_to_nhwc(const float* x, void* y, int32_t n, int32_t c, int32_t hw, void* stream);
 int toist_nhwc_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw, void* stream);
+/* dst[a, c, b] = src[a, b, c] (fp32): conv weight gradients [Cout][taps][Cin] -> the parameter's [Cout][Cin][taps] */
+int toist_permute_021(const float* src, float* dst, int32_t a, int32_t b, int32_t c, void* stream);
+/* nearest resize of the padding mask [B,in_h,in_w] -> small_mask [B,out_h,out_w] (models/backbone.py:78) and the
+ * encoder key-padding mask key_mask [B, out_h*out_w + n_text] (transformer.py:102,134,146); text_attention is the
+ * tokenizer's int64 attention_mask [B, n_text] (1 = keep).  Either output may be null. */
+int toist_key_mask(const uint8_t* pad_mask, const int64_t* text_attention, uint8_t* small_mask, uint8_t* key_mask,
+                   int32_t batch, int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w, int32_t n_text,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row-wise normalisation / softmax / embeddings (transformer.py:279-280,346-349,484; mdetr.py:430-433;
@@ -201,10 +219,13 @@ int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores
                            int32_t ld_s, int32_t ld_p, float scale, void* stream);
 int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t batch, int32_t h, int32_t w,
                    int32_t num_pos_feats, float temperature, void* stream);
+/* ids [batch, len]; rows of out / pos_ids / dx are b*len + l, or l*batch + b when seq_first != 0 */
 int toist_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out,
-                       int32_t* pos_ids, int32_t batch, int32_t len, int32_t dim, int32_t pad_id, void* stream);
+                       int32_t* pos_ids, int32_t batch, int32_t len, int32_t dim, int32_t pad_id, int32_t seq_first,
+                       void* stream);
 int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, const int32_t* pos_ids, float* dword,
-                        float* dpos, float* dtype0, int32_t rows, int32_t dim, void* stream);
+                        float* dpos, float* dtype0, int32_t batch, int32_t len, int32_t dim, int32_t seq_first,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -580,8 +580,9 @@ def criterion(cfg: Config, out: dict, tokenized, targets, positive_map: Tensor, 
         if with_masks:
             res["loss_mask" + suffix], res["loss_dice" + suffix] = loss_masks(o["pred_masks"], targets, idx, nb)
         if cfg.contrastive_align_loss:
-            res["loss_contrastive_align" + suffix] = loss_contrastive_align(
-                o["proj_queries"], o["proj_tokens"], tokenized, targets, idx, nb, cfg.temperature_NCE)
+            with torch.no_grad():  # the reference decorates this loss with @torch.no_grad() (models/mdetr.py:600)
+                res["loss_contrastive_align" + suffix] = loss_contrastive_align(
+                    o["proj_queries"], o["proj_tokens"], tokenized, targets, idx, nb, cfg.temperature_NCE)
         return res, idx
 
     nb = num_boxes

@@ -1,0 +1,113 @@
+"""Pins oracle/model.py (our CPU restatement) to the *unmodified* reference modules imported from /root/reference.
+
+Runs in the build container only (the GPU box has no /root/reference): every test carries the `reference` marker and
+is skipped there.  The same reference outputs are frozen into tests/golden/ by tools/make_golden.py so that the pin
+travels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import max_err, rel_err
+from oracle import model as O
+from oracle import shims
+from synth import make_batch
+from toist_b200.tokenizer import CharTokenizer
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not shims.reference_available(), reason="/root/reference not present")]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    torch.set_num_threads(8)
+    tok = CharTokenizer()
+    models = shims.load_reference(tok)
+    args = shims.reference_args(["--backbone", "resnet50"])
+    torch.manual_seed(0)
+    model, criterion, _, weight_dict = models.build_model(args)
+    model.eval()
+    from util.misc import NestedTensor  # the reference's own container
+
+    images, mask, captions, targets, pm = make_batch(2, 224, 8, seed=7, pad=True)
+    with torch.no_grad():
+        mc = model(NestedTensor(images, mask), captions, encode_and_save=True)
+        out = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc)
+        losses = criterion(mc, out, targets, pm, None)
+    return dict(model=model, criterion=criterion, mc=mc, out=out, losses=losses, tok=tok,
+                batch=(images, mask, captions, targets, pm), args=args)
+
+
+def _oracle_run(ref):
+    images, mask, captions, targets, pm = ref["batch"]
+    sd = {k: v.detach() for k, v in ref["model"].state_dict().items()}
+    cfg = O.Config(backbone="resnet50")
+    tokd = ref["tok"](captions)
+    with torch.no_grad():
+        mc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+        out = O.decode(sd, cfg, mc)
+        losses, idx = O.criterion(cfg, out, tokd, targets, pm)
+    return mc, out, losses, idx
+
+
+def test_forward_matches_reference(ref):
+    mc, out, losses, idx = _oracle_run(ref)
+    rmc, rout = ref["mc"], ref["out"]
+    for k in ("text_memory_resized", "img_memory", "pos_embed", "query_embed"):
+        assert rel_err(mc[k], rmc[k]) < 2e-5, k
+    assert torch.equal(mc["mask"], rmc["mask"])
+    for k in ("pred_logits", "pred_boxes", "proj_queries", "proj_tokens"):
+        assert rel_err(out[k], rout[k]) < 5e-5, k
+    for l, aux in enumerate(rout["aux_outputs"]):
+        for k in ("pred_logits", "pred_boxes", "proj_queries"):
+            assert rel_err(out["aux_outputs"][l][k], aux[k]) < 5e-5, (l, k)
+
+
+def test_losses_and_indices_match_reference(ref):
+    _, out, losses, idx = _oracle_run(ref)
+    rl = ref["losses"]
+    assert set(losses) == set(rl)
+    for k, v in rl.items():
+        assert abs(float(losses[k]) - float(v)) <= 2e-4 * max(1.0, abs(float(v))), (k, float(losses[k]), float(v))
+    # indices: run the reference matcher on the reference outputs, layer by layer
+    images, mask, captions, targets, pm = ref["batch"]
+    rout = ref["out"]
+    layers = list(rout["aux_outputs"]) + [rout]
+    oidx = idx[1:] + idx[:1]  # oracle returns [main, aux_0, ...]
+    for l, o in enumerate(layers):
+        ridx = ref["criterion"].matcher(o, targets, pm)
+        for (r0, c0), (r1, c1) in zip(ridx, oidx[l]):
+            assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist(), l
+
+
+def test_matcher_cost_matches_reference_ops(ref):
+    from util import box_ops  # reference
+
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(50, 4, generator=g) * 0.4 + 0.1
+    b = torch.rand(7, 4, generator=g) * 0.4 + 0.1
+    r = box_ops.generalized_box_iou(box_ops.box_cxcywh_to_xyxy(a), box_ops.box_cxcywh_to_xyxy(b))
+    o = O.pairwise_giou(O.box_cxcywh_to_xyxy(a), O.box_cxcywh_to_xyxy(b))
+    assert torch.equal(r, o)
+
+
+def test_lsap_restatement_matches_scipy():
+    from scipy.optimize import linear_sum_assignment
+
+    rng = np.random.RandomState(1)
+    for shape in [(100, 3), (3, 100), (20, 20), (1, 5), (6, 0), (0, 0), (40, 64)]:
+        for trial in range(4):
+            c = rng.rand(*shape)
+            if trial == 1 and c.size:
+                c = np.round(c * 3) / 3
+            if trial == 2 and c.size:
+                c = np.zeros(shape)
+            r0, c0 = linear_sum_assignment(c)
+            r1, c1 = O.lsap(c)
+            assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist(), (shape, trial)
+    with pytest.raises(ValueError):
+        O.lsap(np.array([[np.nan, 0.0]]))
+    with pytest.raises(ValueError):
+        O.lsap(np.full((2, 2), np.inf))

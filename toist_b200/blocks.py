@@ -1,0 +1,368 @@
+"""Forward / backward of the model's blocks written directly against the sm_100a kernels (no autograd in here).
+
+Every `*_fwd` returns `(output, saved)`; the matching `*_bwd` consumes `saved` and the output gradient, returns the
+input gradient(s) and stores parameter gradients (fp32, in the parameter's own layout) into the dict `g` under the
+parameter's name.  `w` maps a parameter name to the tensor the kernels read: the bf16 *shadow* for matrices (kept
+fresh by kernels.WeightPrep, FrozenBatchNorm scales folded in) and the fp32 parameter itself for vectors.  `req`
+is the set of names whose gradient is wanted.
+
+Activations are bf16: [rows, features] for sequences (row = s * B + b, i.e. the reference's [S, B, C] layout) and NHWC
+for the convolutional trunk.  Accumulation, LayerNorm statistics, softmax and every loss are fp32.
+
+Reference semantics: models/transformer.py:270-470 (encoder / decoder layers), transformers' RobertaLayer,
+torchvision Bottleneck + models/backbone.py:21-58, models/mdetr.py:420-433 (heads).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Set, Tuple
+
+import torch
+
+from . import kernels as K
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, GEMM_DGRAD, GEMM_FWD, GEMM_WGRAD
+
+BF = torch.bfloat16
+W = Dict[str, torch.Tensor]
+G = Dict[str, torch.Tensor]
+
+
+def _zeros(shape, dev):
+    return torch.zeros(shape, dtype=torch.float32, device=dev)
+
+
+# ------------------------------------------------------------------------------------------------ linear pieces
+def lin_param_grads(g: G, req: Set[str], wname: str, bname: Optional[str], dy: torch.Tensor, x: torch.Tensor,
+                    w_shape) -> None:
+    """dW = dy^T x, db = column sums of dy (nn.Linear backward)."""
+    if wname in req:
+        dw = _zeros(tuple(w_shape), dy.device)
+        K.linear_wgrad(dy, x, dw)
+        g[wname] = dw
+    if bname is not None and bname in req:
+        db = _zeros((dy.shape[1],), dy.device)
+        K.colsum(dy, db)
+        g[bname] = db
+
+
+def ln_fwd(w: W, pre: str, x: torch.Tensor, eps: float, **kw):
+    return K.layernorm_fwd(x, w[pre + "weight"], w[pre + "bias"], eps, **kw)
+
+
+def ln_bwd(w: W, g: G, req: Set[str], pre: str, dy, x, mean, rstd, dy2=None, dx_dtype=BF):
+    """Accumulates into g[pre+weight/bias] (several LayerNorm applications may share parameters)."""
+    dg = db = None
+    if (pre + "weight") in req:
+        if (pre + "weight") not in g:
+            g[pre + "weight"] = _zeros((x.shape[1],), x.device)
+            g[pre + "bias"] = _zeros((x.shape[1],), x.device)
+        dg, db = g[pre + "weight"], g[pre + "bias"]
+    return K.layernorm_bwd(dy, x, mean, rstd, w[pre + "weight"], dy2=dy2, dgamma=dg, dbeta=db, dx_dtype=dx_dtype)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int):
+    """nn.MultiheadAttention up to (excluding) out_proj.  xq/xk/xv: [rows, E] bf16; xq is xk -> fused q|k GEMM."""
+    E = xq.shape[1]
+    Wi, bi = w[pre + "in_proj_weight"], w[pre + "in_proj_bias"]
+    if xq is xk:
+        qk = K.linear_fwd(xq, Wi[: 2 * E], bi[: 2 * E])
+        q2, k2 = qk[:, :E], qk[:, E:]
+    else:
+        q2 = K.linear_fwd(xq, Wi[:E], bi[:E])
+        k2 = K.linear_fwd(xk, Wi[E: 2 * E], bi[E: 2 * E])
+    v2 = K.linear_fwd(xv, Wi[2 * E:], bi[2 * E:])
+    Sq, Sk = xq.shape[0] // B, xk.shape[0] // B
+    ctx, probs = K.attention_fwd(q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), key_mask, nhead)
+    return ctx.view(Sq * B, E), (xq, xk, xv, q2, k2, v2, probs)
+
+
+def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int, need=(True, True, True)):
+    """Returns (dxq, dxk, dxv); for self-attention (xq is xk) dxq is the gradient of the shared input and dxk None."""
+    xq, xk, xv, q2, k2, v2, probs = saved
+    E = xq.shape[1]
+    Sq, Sk = xq.shape[0] // B, xk.shape[0] // B
+    dev = xq.device
+    Wi = w[pre + "in_proj_weight"]
+    fused = xq is xk
+    if fused:
+        dqk = torch.empty((xq.shape[0], 2 * E), dtype=BF, device=dev)
+        dq2, dk2 = dqk[:, :E], dqk[:, E:]
+    else:
+        dq2 = torch.empty((xq.shape[0], E), dtype=BF, device=dev)
+        dk2 = torch.empty((xk.shape[0], E), dtype=BF, device=dev)
+    dv2 = torch.empty((xv.shape[0], E), dtype=BF, device=dev)
+    K.attention_bwd(dctx.view(Sq, B, E), q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), probs, nhead,
+                    dq2.view(Sq, B, E), dk2.view(Sk, B, E), dv2.view(Sk, B, E))
+    wn, bn = pre + "in_proj_weight", pre + "in_proj_bias"
+    if wn in req:
+        dw = _zeros((3 * E, E), dev)
+        if fused:
+            K.linear_wgrad(dqk, xq, dw[: 2 * E])
+        else:
+            K.linear_wgrad(dq2, xq, dw[:E])
+            K.linear_wgrad(dk2, xk, dw[E: 2 * E])
+        K.linear_wgrad(dv2, xv, dw[2 * E:])
+        g[wn] = dw
+    if bn in req:
+        db = _zeros((3 * E,), dev)
+        if fused:
+            K.colsum(dqk, db[: 2 * E])
+        else:
+            K.colsum(dq2, db[:E])
+            K.colsum(dk2, db[E: 2 * E])
+        K.colsum(dv2, db[2 * E:])
+        g[bn] = db
+    dxq = dxk = dxv = None
+    if fused:
+        if need[0] or need[1]:
+            dxq = K.linear_dgrad(dqk, Wi[: 2 * E])
+    else:
+        if need[0]:
+            dxq = K.linear_dgrad(dq2, Wi[:E])
+        if need[1]:
+            dxk = K.linear_dgrad(dk2, Wi[E: 2 * E])
+    if need[2]:
+        dxv = K.linear_dgrad(dv2, Wi[2 * E:])
+    return dxq, dxk, dxv
+
+
+def _ffn_fwd(w: W, x):
+    h = K.linear_fwd(x, w["linear1.weight"], w["linear1.bias"], act=ACT_RELU)
+    s = K.linear_fwd(h, w["linear2.weight"], w["linear2.bias"], res=x)
+    return s, h
+
+
+def _ffn_bwd(w: W, g: G, req: Set[str], ds, x, h):
+    """ds: gradient of (x + linear2(relu(linear1(x)))); returns dx including the residual path."""
+    lin_param_grads(g, req, "linear2.weight", "linear2.bias", ds, h, w["linear2.weight"].shape)
+    dh = K.linear_dgrad(ds, w["linear2.weight"], mask=h)
+    lin_param_grads(g, req, "linear1.weight", "linear1.bias", dh, x, w["linear1.weight"].shape)
+    return K.linear_dgrad(dh, w["linear1.weight"], res=ds)
+
+
+# ------------------------------------------------------------------------------------------------ encoder layer
+def encoder_layer_fwd(w: W, x, pos, key_mask, nhead: int, B: int):
+    """models/transformer.py:290-304 (post-norm).  x, pos [S*B, E] bf16."""
+    xp = K.add_bf16(x, pos)
+    ctx, sv = mha_fwd(w, "self_attn.", xp, xp, x, key_mask, nhead, B)
+    s1 = K.linear_fwd(ctx, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], res=x)
+    x1, _, m1, r1 = ln_fwd(w, "norm1.", s1, 1e-5)
+    s2, h = _ffn_fwd(w, x1)
+    x2, _, m2, r2 = ln_fwd(w, "norm2.", s2, 1e-5)
+    return x2, (sv, ctx, s1, m1, r1, x1, h, s2, m2, r2)
+
+
+def encoder_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int):
+    sv, ctx, s1, m1, r1, x1, h, s2, m2, r2 = saved
+    ds2 = ln_bwd(w, g, req, "norm2.", dy, s2, m2, r2)
+    dx1 = _ffn_bwd(w, g, req, ds2, x1, h)
+    ds1 = ln_bwd(w, g, req, "norm1.", dx1, s1, m1, r1)
+    lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", ds1, ctx,
+                    w["self_attn.out_proj.weight"].shape)
+    dctx = K.linear_dgrad(ds1, w["self_attn.out_proj.weight"])
+    dxp, _, dxv = mha_bwd(w, g, req, "self_attn.", dctx, sv, nhead, B)
+    return K.add_bf16(ds1, dxp, dxv)  # residual + (q,k) path + v path; pos carries no gradient (sine embedding)
+
+
+# ------------------------------------------------------------------------------------------------ decoder layer
+def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: int):
+    """models/transformer.py:362-408 (post-norm; the text cross-attention is disabled in the reference)."""
+    tq = K.add_bf16(tgt, qpos)
+    ctx1, sv1 = mha_fwd(w, "self_attn.", tq, tq, tgt, None, nhead, B)
+    s1 = K.linear_fwd(ctx1, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], res=tgt)
+    t1, _, m1, r1 = ln_fwd(w, "norm1.", s1, 1e-5)
+    cq = K.add_bf16(t1, qpos)
+    ctx2, sv2 = mha_fwd(w, "cross_attn_image.", cq, mem_pos, mem, key_mask, nhead, B)
+    s2 = K.linear_fwd(ctx2, w["cross_attn_image.out_proj.weight"], w["cross_attn_image.out_proj.bias"], res=t1)
+    t2, _, m2, r2 = ln_fwd(w, "norm3.", s2, 1e-5)
+    s3, h = _ffn_fwd(w, t2)
+    t3, _, m3, r3 = ln_fwd(w, "norm4.", s3, 1e-5)
+    return t3, (sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3)
+
+
+def decoder_layer_bwd(w: W, g: G, req: Set[str], dy, dy2, saved, nhead: int, B: int, need_tgt: bool = True):
+    """dy (+ dy2): gradient of the layer output.  Returns (d_tgt, d_qpos, d_mem_pos, d_mem)."""
+    sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3 = saved
+    ds3 = ln_bwd(w, g, req, "norm4.", dy, s3, m3, r3, dy2=dy2)
+    dt2 = _ffn_bwd(w, g, req, ds3, t2, h)
+    ds2 = ln_bwd(w, g, req, "norm3.", dt2, s2, m2, r2)
+    lin_param_grads(g, req, "cross_attn_image.out_proj.weight", "cross_attn_image.out_proj.bias", ds2, ctx2,
+                    w["cross_attn_image.out_proj.weight"].shape)
+    dctx2 = K.linear_dgrad(ds2, w["cross_attn_image.out_proj.weight"])
+    dcq, dmem_pos, dmem = mha_bwd(w, g, req, "cross_attn_image.", dctx2, sv2, nhead, B)
+    dt1 = K.add_bf16(ds2, dcq)
+    ds1 = ln_bwd(w, g, req, "norm1.", dt1, s1, m1, r1)
+    lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", ds1, ctx1,
+                    w["self_attn.out_proj.weight"].shape)
+    dctx1 = K.linear_dgrad(ds1, w["self_attn.out_proj.weight"])
+    dtq, _, dtv = mha_bwd(w, g, req, "self_attn.", dctx1, sv1, nhead, B, need=(True, True, need_tgt))
+    d_qpos = K.add_bf16(dcq, dtq)
+    d_tgt = K.add_bf16(ds1, dtq, dtv) if need_tgt else None
+    return d_tgt, d_qpos, dmem_pos, dmem
+
+
+# ------------------------------------------------------------------------------------------------ RoBERTa layer
+def roberta_layer_fwd(w: W, x, key_mask, nhead: int, B: int, eps: float):
+    """transformers RobertaLayer (post-LN BERT block, erf GELU).  x [L*B, E] bf16, rows l*B + b."""
+    M, E = x.shape
+    L = M // B
+    Wqkv = w["attention.self.qkv"]
+    qkv = torch.empty((M, 3 * E), dtype=BF, device=x.device)
+    for i, nm in enumerate(("query", "key", "value")):
+        K.linear_fwd(x, Wqkv[i * E:(i + 1) * E], w[f"attention.self.{nm}.bias"], out=qkv[:, i * E:(i + 1) * E])
+    q3, k3, v3 = (qkv[:, i * E:(i + 1) * E].view(L, B, E) for i in range(3))
+    ctx, probs = K.attention_fwd(q3, k3, v3, key_mask, nhead)
+    ctx = ctx.view(M, E)
+    s1 = K.linear_fwd(ctx, w["attention.output.dense.weight"], w["attention.output.dense.bias"], res=x)
+    x1, _, m1, r1 = ln_fwd(w, "attention.output.LayerNorm.", s1, eps)
+    pre = torch.empty((M, w["intermediate.dense.weight"].shape[0]), dtype=BF, device=x.device)
+    h = K.linear_fwd(x1, w["intermediate.dense.weight"], w["intermediate.dense.bias"], act=ACT_GELU, aux=pre)
+    s2 = K.linear_fwd(h, w["output.dense.weight"], w["output.dense.bias"], res=x1)
+    x2, _, m2, r2 = ln_fwd(w, "output.LayerNorm.", s2, eps)
+    return x2, (x, qkv, probs, ctx, s1, m1, r1, x1, pre, h, s2, m2, r2)
+
+
+def roberta_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, need_dx: bool = True):
+    x, qkv, probs, ctx, s1, m1, r1, x1, pre, h, s2, m2, r2 = saved
+    M, E = x.shape
+    L = M // B
+    ds2 = ln_bwd(w, g, req, "output.LayerNorm.", dy, s2, m2, r2)
+    lin_param_grads(g, req, "output.dense.weight", "output.dense.bias", ds2, h, w["output.dense.weight"].shape)
+    dh = K.linear_dgrad(ds2, w["output.dense.weight"])
+    dpre = K.gelu_bwd(dh, pre)
+    lin_param_grads(g, req, "intermediate.dense.weight", "intermediate.dense.bias", dpre, x1,
+                    w["intermediate.dense.weight"].shape)
+    dx1 = K.linear_dgrad(dpre, w["intermediate.dense.weight"], res=ds2)
+    ds1 = ln_bwd(w, g, req, "attention.output.LayerNorm.", dx1, s1, m1, r1)
+    lin_param_grads(g, req, "attention.output.dense.weight", "attention.output.dense.bias", ds1, ctx,
+                    w["attention.output.dense.weight"].shape)
+    dctx = K.linear_dgrad(ds1, w["attention.output.dense.weight"])
+    dqkv = torch.empty((M, 3 * E), dtype=BF, device=x.device)
+    q3, k3, v3 = (qkv[:, i * E:(i + 1) * E].view(L, B, E) for i in range(3))
+    d3 = [dqkv[:, i * E:(i + 1) * E].view(L, B, E) for i in range(3)]
+    K.attention_bwd(dctx.view(L, B, E), q3, k3, v3, probs, nhead, d3[0], d3[1], d3[2])
+    for i, nm in enumerate(("query", "key", "value")):
+        lin_param_grads(g, req, f"attention.self.{nm}.weight", f"attention.self.{nm}.bias",
+                        dqkv[:, i * E:(i + 1) * E], x, (E, E))
+    if not need_dx:
+        return None
+    return K.linear_dgrad(dqkv, w["attention.self.qkv"], res=ds1)
+
+
+# ------------------------------------------------------------------------------------------------ bottleneck
+def bottleneck_fwd(w: W, x, stride: int, has_ds: bool):
+    """torchvision Bottleneck (v1.5: stride on the 3x3) with FrozenBatchNorm folded: conv weights carry the BN scale,
+    the epilogue adds the BN shift (models/backbone.py:48-58).  x NHWC bf16."""
+    y1 = K.conv_fwd(x, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU)
+    y2 = K.conv_fwd(y1, w["conv2.weight"], w["bn2.shift"], stride=stride, pad=1, act=ACT_RELU)
+    idt = K.conv_fwd(x, w["downsample.0.weight"], w["downsample.1.shift"], stride=stride) if has_ds else x
+    out = K.conv_fwd(y2, w["conv3.weight"], w["bn3.shift"], res=idt, act=ACT_RELU)
+    return out, (x, y1, y2)
+
+
+def _conv_wgrad_param(g: G, name: str, dy, x, w_shadow, scale, stride: int, pad: int) -> None:
+    cout, kh, kw, cin = w_shadow.shape
+    dw = _zeros((cout, kh, kw, cin), dy.device)
+    K.conv_wgrad(dy, x, dw, stride=stride, pad=pad, row_scale=scale)
+    if kh * kw > 1:
+        dw = K.permute_021(dw.view(cout, kh * kw, cin))
+    g[name] = dw.view(cout, cin, kh, kw)
+
+
+def bottleneck_bwd(w: W, g: G, req: Set[str], gz, saved, stride: int, has_ds: bool, need_dx: bool):
+    """gz: gradient w.r.t. the pre-ReLU sum (already multiplied by out > 0).  Returns the gradient w.r.t. the block
+    input *already masked by (x > 0)*, i.e. the `gz` of the preceding block."""
+    x, y1, y2 = saved
+    if "conv3.weight" in req:
+        _conv_wgrad_param(g, "conv3.weight", gz, y2, w["conv3.weight"], w["bn3.scale"], 1, 0)
+    g2 = K.conv_dgrad(gz, w["conv3.weight"], y2.shape[1:3], mask=y2)
+    if "conv2.weight" in req:
+        _conv_wgrad_param(g, "conv2.weight", g2, y1, w["conv2.weight"], w["bn2.scale"], stride, 1)
+    g1 = K.conv_dgrad(g2, w["conv2.weight"], y1.shape[1:3], stride=stride, pad=1, mask=y1)
+    if "conv1.weight" in req:
+        _conv_wgrad_param(g, "conv1.weight", g1, x, w["conv1.weight"], w["bn1.scale"], 1, 0)
+    if has_ds and "downsample.0.weight" in req:
+        _conv_wgrad_param(g, "downsample.0.weight", gz, x, w["downsample.0.weight"], w["downsample.1.scale"], stride, 0)
+    if not need_dx:
+        return None
+    gi = K.conv_dgrad(gz, w["downsample.0.weight"], x.shape[1:3], stride=stride) if has_ds else gz
+    return K.conv_dgrad(g1, w["conv1.weight"], x.shape[1:3], res=gi, mask=x)
+
+
+# ------------------------------------------------------------------------------------------------ strided GEMM helpers
+def seq_from_nhwc_fwd(x, wt, bias, out, B: int):
+    """input_proj (models/mdetr.py:351,383) fused with flatten(2).permute(2,0,1) (transformer.py:101):
+    x NHWC [B,H,W,Cin] bf16 -> out rows (y*W + x)*B + b, [H*W*B, Cout] (a row slice of the encoder source)."""
+    n, h, wd, cin = x.shape
+    cout = wt.shape[0]
+    K.gemm(GEMM_FWD, K._nhwc_t4(x), K.t4(wt, (cin, cout, 1, 1), (1, cin, 0, 0)), out, ext=(wd, h, n),
+           tile=K.pick_tile(wd, h, n), n_cols=cout, out_strides=(B * cout, wd * B * cout, cout), k_per_tap=cin,
+           col_shift=bias)
+    return out
+
+
+def _seq_as_nhwc_t4(d, h: int, wd: int, B: int):
+    """[H*W*B, C] sequence rows viewed as the (c, x, y, n) pixel space of an NHWC tensor."""
+    c = d.shape[1]
+    ld = d.stride(0)
+    return K.t4(d, (c, wd, h, B), (1, B * ld, wd * B * ld, ld))
+
+
+def seq_from_nhwc_bwd(g: G, req: Set[str], wname: str, bname: str, dseq, x, wt, need_dx: bool):
+    n, h, wd, cin = x.shape
+    cout = wt.shape[0]
+    a = _seq_as_nhwc_t4(dseq, h, wd, n)
+    if wname in req:
+        dw = _zeros((cout, cin), x.device)
+        tile = K.pick_tile(wd, h, n, 64, 64)
+        ptiles = -(-wd // tile[0]) * -(-h // tile[1]) * -(-n // tile[2])
+        K.gemm(GEMM_WGRAD, a, K._nhwc_t4(x), dw, ext=(wd, h, n), tile=tile, n_cols=cin, m_rows=cout,
+               out_strides=(cin, 0, 0), splits=K._wgrad_splits(cout, cin, 1, ptiles), accumulate=True)
+        g[wname] = dw.view(cout, cin, 1, 1)
+    if bname in req:
+        db = _zeros((cout,), x.device)
+        K.colsum(dseq, db)
+        g[bname] = db
+    if not need_dx:
+        return None
+    dx = torch.empty_like(x)
+    K.gemm(GEMM_DGRAD, a, K.t4(wt, (cin, cout, 1, 1), (1, cin, 0, 0)), dx, ext=(wd, h, n), tile=K.pick_tile(wd, h, n),
+           n_cols=cin, out_strides=(cin, wd * cin, h * wd * cin), k_per_tap=cout)
+    return dx
+
+
+def heads_linear_fwd(hs, wt, bias, L: int, Q: int, B: int, act: int = ACT_NONE):
+    """Linear over decoder states hs [L, Q*B, E] (rows q*B + b) writing fp32 [L, B, Q, N]: the hs.transpose(1, 2) of
+    models/transformer.py:188 is folded into the output addressing."""
+    E = hs.shape[-1]
+    N = wt.shape[0]
+    out = torch.empty((L, B, Q, N), dtype=torch.float32, device=hs.device)
+    K.gemm(GEMM_FWD, K.t4(hs, (E, B, Q, L), (1, E, B * E, Q * B * E)), K.t4(wt, (E, N, 1, 1), (1, E, 0, 0)), out,
+           ext=(B, Q, L), tile=K.pick_tile(B, Q, L), n_cols=N, out_strides=(Q * N, N, B * Q * N), k_per_tap=E,
+           col_shift=bias, act=act)
+    return out
+
+
+def heads_linear_bwd(g: G, req: Set[str], wname: str, bname: str, dout16, hs, wt, L: int, Q: int, B: int,
+                     res=None, mask=None):
+    """dout16 bf16 [L, B, Q, ldn] (ldn >= N, zero padded to a multiple of 8) -> d_hs bf16 [L, Q*B, E]
+    ((+ res) * (mask > 0)), parameter grads into g."""
+    E = hs.shape[-1]
+    N = wt.shape[0]
+    ldn = dout16.shape[-1]
+    a = K.t4(dout16, (ldn, B, Q, L), (1, Q * ldn, ldn, B * Q * ldn))
+    if wname in req:
+        dw = _zeros((N, E), hs.device)
+        tile = K.pick_tile(B, Q, L, 64, 64)
+        ptiles = -(-B // tile[0]) * -(-Q // tile[1]) * -(-L // tile[2])
+        K.gemm(GEMM_WGRAD, a, K.t4(hs, (E, B, Q, L), (1, E, B * E, Q * B * E)), dw, ext=(B, Q, L), tile=tile,
+               n_cols=E, m_rows=N, out_strides=(E, 0, 0), splits=K._wgrad_splits(N, E, 1, ptiles), accumulate=True)
+        g[wname] = dw
+    if bname in req:
+        db = _zeros((N,), hs.device)
+        K.colsum(dout16.view(-1, ldn)[:, :N], db)
+        g[bname] = db
+    dhs = torch.empty((L, Q * B, E), dtype=BF, device=hs.device)
+    K.gemm(GEMM_DGRAD, a, K.t4(wt, (E, N, 1, 1), (1, E, 0, 0)), dhs, ext=(B, Q, L), tile=K.pick_tile(B, Q, L),
+           n_cols=E, out_strides=(E, B * E, Q * B * E), k_per_tap=ldn, res=res, mask=mask)
+    return dhs

@@ -13,6 +13,8 @@ struct PrepItem {
   const float* row_scale;  // may be null
   int rows, cols, ldd;
   int first_block;  // prefix of blocks (each block handles 2048 elements)
+  int taps;         // > 1: src is [rows][cols / taps][taps] (conv OIHW) and dst gets [rows][taps][cols / taps] (OHWI)
+  int pad_;
 };
 
 __global__ void weight_prep_kernel(const PrepItem* __restrict__ items, int n_items) {
@@ -25,7 +27,7 @@ __global__ void weight_prep_kernel(const PrepItem* __restrict__ items, int n_ite
   const PrepItem it = items[lo];
   const long long total = (long long)it.rows * it.cols;
   const long long base = (long long)(blockIdx.x - it.first_block) * 2048;
-  if (it.ldd == it.cols && it.row_scale == nullptr && (it.cols % 8 == 0)) {
+  if (it.ldd == it.cols && it.row_scale == nullptr && (it.cols % 8 == 0) && it.taps <= 1) {
     const long long i = base + (long long)threadIdx.x * 8;
     if (i + 8 <= total) {
       const float4 a = *reinterpret_cast<const float4*>(it.src + i);
@@ -39,9 +41,15 @@ __global__ void weight_prep_kernel(const PrepItem* __restrict__ items, int n_ite
   for (int k = 0; k < 8; ++k) {
     const long long i = base + (long long)threadIdx.x * 8 + k;
     if (i >= total) break;
-    const int r = (int)(i / it.cols), c = (int)(i % it.cols);
+    const int r = (int)(i / it.cols), c = (int)(i % it.cols);  // c indexes the destination row
     const float s = it.row_scale ? it.row_scale[r] : 1.f;
-    it.dst[(long long)r * it.ldd + c] = __float2bfloat16_rn(it.src[i] * s);
+    long long si = i;
+    if (it.taps > 1) {
+      const int cin = it.cols / it.taps;
+      const int t = c / cin, ci = c % cin;
+      si = (long long)r * it.cols + (long long)ci * it.taps + t;
+    }
+    it.dst[(long long)r * it.ldd + c] = __float2bfloat16_rn(it.src[si] * s);
   }
 }
 
@@ -257,6 +265,52 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
   y[i] = __bfloat162float(x[((long long)n * HW + hw) * C + c]);
 }
 
+// dst[r, 0:ld] = bf16(src[r, 0:n]) zero-padded to ld columns (TMA needs 16-byte rows: e.g. the 4-wide box head)
+__global__ void cast_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int n,
+                                int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  const long long r = i / ld;
+  const int c = (int)(i % ld);
+  dst[i] = __float2bfloat16_rn(c < n ? src[r * n + c] : 0.f);
+}
+
+// dst[a, c, b] = src[a, b, c]  (fp32) — conv weight gradients come out of the WGRAD engine as [Cout][taps][Cin]
+__global__ void permute_021_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int B, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)A * B * C) return;
+  const int b = (int)(i % B);
+  const long long p = i / B;
+  const int c = (int)(p % C);
+  const int a = (int)(p / C);
+  dst[i] = src[((long long)a * B + b) * C + c];
+}
+
+// Nearest-neighbour resize of the padding mask (models/backbone.py:78 -> F.interpolate default mode) and assembly
+// of the encoder key-padding mask [B, h*w + L] (models/transformer.py:102,134,146).
+__global__ void key_mask_kernel(const uint8_t* __restrict__ pad, const long long* __restrict__ text_attn,
+                                uint8_t* __restrict__ small, uint8_t* __restrict__ key, int B, int H, int W, int h,
+                                int w, int L) {
+  const int S = h * w + L;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * S) return;
+  const int b = (int)(i / S), s = (int)(i % S);
+  uint8_t v;
+  if (s < h * w) {
+    const int y = s / w, x = s % w;
+    // torch nearest: src = floor(dst * (in / out)) computed in float
+    int sy = (int)floorf((float)y * ((float)H / (float)h));
+    int sx = (int)floorf((float)x * ((float)W / (float)w));
+    sy = sy < H - 1 ? sy : H - 1;
+    sx = sx < W - 1 ? sx : W - 1;
+    v = pad[((long long)b * H + sy) * W + sx] ? 1 : 0;
+    if (small) small[((long long)b * h + y) * w + x] = v;
+  } else {
+    v = text_attn ? (text_attn[(long long)b * L + (s - h * w)] != 1 ? 1 : 0) : 0;
+  }
+  if (key) key[i] = v;
+}
+
 }  // namespace toist
 
 using namespace toist;
@@ -397,6 +451,37 @@ int toist_nhwc_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw
   const long long t = (long long)n * c * hw;
   if (t == 0) return TOIST_OK;
   nhwc_to_nchw_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n, c, hw);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_cast_pad_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n, int32_t ld, void* stream) {
+  TOIST_REQUIRE(src && dst && ld >= n, "toist_cast_pad_f32_bf16: bad arguments");
+  if (rows * ld == 0) return TOIST_OK;
+  cast_pad_kernel<<<nblk(rows * ld, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, n, ld);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_permute_021(const float* src, float* dst, int32_t a, int32_t b, int32_t c, void* stream) {
+  TOIST_REQUIRE(src && dst, "toist_permute_021: null pointer");
+  const long long t = (long long)a * b * c;
+  if (t == 0) return TOIST_OK;
+  permute_021_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, a, b, c);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_key_mask(const uint8_t* pad_mask, const int64_t* text_attention, uint8_t* small_mask, uint8_t* key_mask,
+                   int32_t batch, int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w, int32_t n_text,
+                   void* stream) {
+  TOIST_REQUIRE(pad_mask && (small_mask || key_mask), "toist_key_mask: null pointer");
+  TOIST_REQUIRE(n_text == 0 || text_attention != nullptr || key_mask == nullptr, "toist_key_mask: text mask missing");
+  const long long t = (long long)batch * (out_h * out_w + n_text);
+  if (t == 0) return TOIST_OK;
+  key_mask_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>(pad_mask, (const long long*)text_attention,
+                                                                  small_mask, key_mask, batch, in_h, in_w, out_h,
+                                                                  out_w, n_text);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

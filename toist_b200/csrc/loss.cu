@@ -296,8 +296,8 @@ __global__ void contrastive_kernel(const float* __restrict__ pq, const float* __
 __global__ void criterion_reduce_kernel(const float* __restrict__ row_loss, const float* __restrict__ pair_l1,
                                         const float* __restrict__ pair_giou, const int* __restrict__ card,
                                         const float* __restrict__ img_loss, const int* __restrict__ tgt_count,
-                                        const float* __restrict__ num_boxes, float* __restrict__ out, int L, int B, int Q,
-                                        int Tmax) {
+                                        const float* __restrict__ num_boxes, const int* __restrict__ flags,
+                                        float* __restrict__ out, int L, int B, int Q, int Tmax) {
   __shared__ float red[32];
   const int l = blockIdx.x;
   const float inv_nb = 1.f / num_boxes[0];
@@ -319,6 +319,9 @@ __global__ void criterion_reduce_kernel(const float* __restrict__ row_loss, cons
   ce = block_sum(ce, red);
   ca = block_sum(ca, red);
   if (threadIdx.x == 0) {
+    // an invalid matching cost (scipy's ValueError in the reference) poisons every term: the caller's
+    // non-finite-loss guard (engine.py:82-85) then aborts without a device synchronisation here
+    if (flags != nullptr && flags[0] != 0) a = __int_as_float(0x7fc00000);
     out[0 * L + l] = a * inv_nb;
     out[1 * L + l] = l1 * inv_nb;
     out[2 * L + l] = gi * inv_nb;
@@ -340,6 +343,15 @@ __global__ void scale_layers_kernel(const float* __restrict__ x, const float* __
   } else {
     for (int l = 0; l < L; ++l) y[(size_t)l * n + i] = x[(size_t)l * n + i] * g[l];
   }
+}
+
+// y[l, i] = x1[l, i] * g1[l] + x2[l, i] * g2[l]
+__global__ void scale_layers2_kernel(const float* __restrict__ x1, const float* __restrict__ g1,
+                                     const float* __restrict__ x2, const float* __restrict__ g2, float* __restrict__ y,
+                                     int L, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int l = 0; l < L; ++l) y[(size_t)l * n + i] = x1[(size_t)l * n + i] * g1[l] + x2[(size_t)l * n + i] * g2[l];
 }
 
 }  // namespace toist
@@ -403,13 +415,23 @@ int toist_contrastive_align(const float* proj_queries, const float* proj_tokens,
 }
 
 int toist_criterion_reduce(const float* row_loss, const float* pair_l1, const float* pair_giou, const int32_t* card,
-                           const float* img_loss, const int32_t* tgt_count, const float* num_boxes, float* out,
-                           int32_t n_layers, int32_t batch, int32_t n_queries, int32_t t_max, void* stream) {
+                           const float* img_loss, const int32_t* tgt_count, const float* num_boxes,
+                           const int32_t* flags, float* out, int32_t n_layers, int32_t batch, int32_t n_queries,
+                           int32_t t_max, void* stream) {
   TOIST_REQUIRE(row_loss && pair_l1 && pair_giou && card && tgt_count && num_boxes && out,
                 "toist_criterion_reduce: null pointer");
   criterion_reduce_kernel<<<n_layers, 256, 0, (cudaStream_t)stream>>>(row_loss, pair_l1, pair_giou, card, img_loss,
-                                                                      tgt_count, num_boxes, out, n_layers, batch,
-                                                                      n_queries, t_max);
+                                                                      tgt_count, num_boxes, flags, out, n_layers,
+                                                                      batch, n_queries, t_max);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_scale_layers2(const float* x1, const float* g1, const float* x2, const float* g2, float* y, int32_t n_layers,
+                        int64_t n, void* stream) {
+  TOIST_REQUIRE(x1 && g1 && x2 && g2 && y, "toist_scale_layers2: null pointer");
+  if (n == 0) return TOIST_OK;
+  scale_layers2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x1, g1, x2, g2, y, n_layers, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

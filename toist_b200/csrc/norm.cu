@@ -238,10 +238,11 @@ __global__ void pos_sine_kernel(const uint8_t* __restrict__ mask, float* __restr
 // x[b*L + l, :] = word[id] + pos[pos_id] + type[0];  pos_id = cumsum(id != pad)[l] * (id != pad) + pad
 __global__ void embed_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
                                     const float* __restrict__ posw, const float* __restrict__ type0,
-                                    float* __restrict__ out, int* __restrict__ pos_ids, int L, int E, int pad_id) {
-  const int row = blockIdx.x;
-  const int b = row / L, l = row % L;
-  const long long id = ids[row];
+                                    float* __restrict__ out, int* __restrict__ pos_ids, int B, int L, int E, int pad_id,
+                                    int seq_first) {
+  const int b = blockIdx.x / L, l = blockIdx.x % L;
+  const long long id = ids[blockIdx.x];
+  const int row = seq_first ? l * B + b : blockIdx.x;  // output row (ids are always [B, L])
   int cnt = 0;
   for (int k = 0; k <= l; ++k) cnt += ids[(long long)b * L + k] != pad_id;
   const int pid = (id != pad_id ? cnt : 0) + pad_id;
@@ -253,9 +254,11 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const flo
 template <typename T>
 __global__ void embed_scatter_kernel(const T* __restrict__ dx, const long long* __restrict__ ids,
                                      const int* __restrict__ pos_ids, float* __restrict__ dword,
-                                     float* __restrict__ dpos, float* __restrict__ dtype0, int E) {
-  const int row = blockIdx.x;
-  const long long id = ids[row];
+                                     float* __restrict__ dpos, float* __restrict__ dtype0, int B, int L, int E,
+                                     int seq_first) {
+  const int b = blockIdx.x / L, l = blockIdx.x % L;
+  const int row = seq_first ? l * B + b : blockIdx.x;
+  const long long id = ids[blockIdx.x];
   const int pid = pos_ids[row];
   for (int c = threadIdx.x; c < E; c += blockDim.x) {
     const float g = ld_as_float(dx, (long long)row * E + c);
@@ -373,23 +376,26 @@ int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t 
 }
 
 int toist_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out,
-                       int32_t* pos_ids, int32_t batch, int32_t len, int32_t dim, int32_t pad_id, void* stream) {
+                       int32_t* pos_ids, int32_t batch, int32_t len, int32_t dim, int32_t pad_id, int32_t seq_first,
+                       void* stream) {
   TOIST_REQUIRE(ids && word && pos && type0 && out, "toist_embed_gather: null pointer");
   if (batch * len == 0) return TOIST_OK;
   embed_gather_kernel<<<batch * len, 256, 0, (cudaStream_t)stream>>>((const long long*)ids, word, pos, type0, out,
-                                                                     pos_ids, len, dim, pad_id);
+                                                                     pos_ids, batch, len, dim, pad_id, seq_first);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
 
 int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, const int32_t* pos_ids, float* dword,
-                        float* dpos, float* dtype0, int32_t rows, int32_t dim, void* stream) {
+                        float* dpos, float* dtype0, int32_t batch, int32_t len, int32_t dim, int32_t seq_first,
+                        void* stream) {
   TOIST_REQUIRE(dx && ids && pos_ids, "toist_embed_scatter: null pointer");
+  const int rows = batch * len;
   if (rows == 0) return TOIST_OK;
   if (dx_dtype == TOIST_BF16)
-    embed_scatter_kernel<__nv_bfloat16><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, dim);
+    embed_scatter_kernel<__nv_bfloat16><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
   else
-    embed_scatter_kernel<float><<<rows, 256, 0, (cudaStream_t)stream>>>((const float*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, dim);
+    embed_scatter_kernel<float><<<rows, 256, 0, (cudaStream_t)stream>>>((const float*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

@@ -266,18 +266,29 @@ def _ck(rc: int, n: int = 1) -> None:
     _count(n)
 
 
-def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 -> bf16 copy (contiguous)."""
     assert x.dtype == torch.float32 and x.is_contiguous()
-    y = torch.empty_like(x, dtype=torch.bfloat16)
+    y = out if out is not None else torch.empty_like(x, dtype=torch.bfloat16)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.numel() == x.numel()
     _ck(_L().toist_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
     return y
 
 
-def cast_f32(x: torch.Tensor) -> torch.Tensor:
+def cast_f32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
-    y = torch.empty_like(x, dtype=torch.float32)
+    y = out if out is not None else torch.empty_like(x, dtype=torch.float32)
+    assert y.dtype == torch.float32 and y.is_contiguous() and y.numel() == x.numel()
     _ck(_L().toist_cast_bf16_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+def cast_pad_bf16(x: torch.Tensor, ld: int) -> torch.Tensor:
+    """fp32 [..., n] -> bf16 [..., ld] zero padded (ld >= n)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n = x.shape[-1]
+    y = torch.empty((*x.shape[:-1], ld), dtype=torch.bfloat16, device=x.device)
+    _ck(_L().toist_cast_pad_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel() // n, n, ld, _stream()))
     return y
 
 
@@ -300,9 +311,11 @@ class WeightPrep:
         self._keep = []
 
     def add(self, src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, ldd: Optional[int] = None,
-            row_scale: Optional[torch.Tensor] = None) -> None:
-        assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16
-        self.items.append((src, dst, row_scale, rows, cols, ldd or cols))
+            row_scale: Optional[torch.Tensor] = None, taps: int = 1) -> None:
+        """`taps` > 1: src is a conv weight [rows, cols // taps, taps] (OIHW) written as [rows, taps, cols // taps]."""
+        assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.is_contiguous()
+        assert src.numel() == rows * cols and cols % taps == 0
+        self.items.append((src, dst, row_scale, rows, cols, ldd or cols, taps))
         self._table = None
 
     def _build(self) -> None:
@@ -310,9 +323,9 @@ class WeightPrep:
 
         buf = bytearray()
         blocks = 0
-        for src, dst, sc, rows, cols, ldd in self.items:
-            buf += struct.pack("<QQQiiii", src.data_ptr(), dst.data_ptr(), 0 if sc is None else sc.data_ptr(), rows,
-                               cols, ldd, blocks)
+        for src, dst, sc, rows, cols, ldd, taps in self.items:
+            buf += struct.pack("<QQQiiiiii", src.data_ptr(), dst.data_ptr(), 0 if sc is None else sc.data_ptr(), rows,
+                               cols, ldd, blocks, taps, 0)
             blocks += -(-(rows * cols) // 2048)
         host = torch.frombuffer(buf, dtype=torch.uint8).clone()
         self._table = host.to(self.device)
@@ -397,12 +410,18 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------ norms / softmax
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, want_f32: bool = False,
-                  want_bf16: bool = True, save_stats: bool = True):
-    """x [rows, N] (fp32 or bf16) -> (y_bf16 | None, y_f32 | None, mean, rstd)."""
+                  want_bf16: bool = True, save_stats: bool = True, out16: Optional[torch.Tensor] = None,
+                  out32: Optional[torch.Tensor] = None):
+    """x [rows, N] (fp32 or bf16) -> (y_bf16 | None, y_f32 | None, mean, rstd).  out16 / out32: preallocated
+    contiguous [rows, N] destinations (e.g. a row slice of a larger buffer)."""
     rows, n = x.shape
     assert x.is_contiguous()
-    y16 = torch.empty((rows, n), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    y32 = torch.empty((rows, n), dtype=torch.float32, device=x.device) if want_f32 else None
+    y16 = out16 if out16 is not None else (
+        torch.empty((rows, n), dtype=torch.bfloat16, device=x.device) if want_bf16 else None)
+    y32 = out32 if out32 is not None else (
+        torch.empty((rows, n), dtype=torch.float32, device=x.device) if want_f32 else None)
+    for t in (y16, y32):
+        assert t is None or (t.is_contiguous() and t.shape == (rows, n))
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     _ck(_L().toist_layernorm_fwd(x.data_ptr(), _dt(x), gamma.data_ptr(), beta.data_ptr(), _ptr(y16), _ptr(y32),
@@ -437,33 +456,64 @@ def l2norm_bwd(dy: torch.Tensor, y: torch.Tensor, nrm: torch.Tensor) -> torch.Te
     return dx
 
 
-def pos_sine(mask_u8: torch.Tensor, num_pos_feats: int, temperature: float = 10000.0):
-    """mask [B,H,W] uint8 -> (pos_f32, pos_bf16) each [H*W, B, 2*num_pos_feats]."""
+def pos_sine(mask_u8: torch.Tensor, num_pos_feats: int, temperature: float = 10000.0, extra_rows: int = 0):
+    """mask [B,H,W] uint8 -> (pos_f32, pos_bf16) each [H*W + extra_rows, B, 2*num_pos_feats]; the extra (text) rows
+    are zero (models/transformer.py:148)."""
     b, h, w = mask_u8.shape
     assert mask_u8.dtype == torch.uint8 and mask_u8.is_contiguous()
-    p32 = torch.empty((h * w, b, 2 * num_pos_feats), dtype=torch.float32, device=mask_u8.device)
-    p16 = torch.empty((h * w, b, 2 * num_pos_feats), dtype=torch.bfloat16, device=mask_u8.device)
+    alloc = torch.zeros if extra_rows else torch.empty
+    p32 = alloc((h * w + extra_rows, b, 2 * num_pos_feats), dtype=torch.float32, device=mask_u8.device)
+    p16 = alloc((h * w + extra_rows, b, 2 * num_pos_feats), dtype=torch.bfloat16, device=mask_u8.device)
     _ck(_L().toist_pos_sine(mask_u8.data_ptr(), p32.data_ptr(), p16.data_ptr(), b, h, w, num_pos_feats, temperature,
                             _stream()))
     return p32, p16
 
 
-def embed_gather(ids: torch.Tensor, word: torch.Tensor, pos: torch.Tensor, type_w: torch.Tensor, pad_id: int = 1):
+def embed_gather(ids: torch.Tensor, word: torch.Tensor, pos: torch.Tensor, type_w: torch.Tensor, pad_id: int = 1,
+                 seq_first: bool = False):
+    """RoBERTa embedding sum; ids [B, L] -> rows b*L + l (or l*B + b when seq_first)."""
     b, l = ids.shape
     e = word.shape[1]
     assert ids.dtype == torch.int64 and ids.is_contiguous()
     out = torch.empty((b * l, e), dtype=torch.float32, device=ids.device)
     pos_ids = torch.empty(b * l, dtype=torch.int32, device=ids.device)
     _ck(_L().toist_embed_gather(ids.data_ptr(), word.data_ptr(), pos.data_ptr(), type_w.data_ptr(), out.data_ptr(),
-                                pos_ids.data_ptr(), b, l, e, pad_id, _stream()))
+                                pos_ids.data_ptr(), b, l, e, pad_id, 1 if seq_first else 0, _stream()))
     return out, pos_ids
 
 
 def embed_scatter(dx: torch.Tensor, ids: torch.Tensor, pos_ids: torch.Tensor, dword: Optional[torch.Tensor],
-                  dpos: Optional[torch.Tensor], dtype0: Optional[torch.Tensor]) -> None:
+                  dpos: Optional[torch.Tensor], dtype0: Optional[torch.Tensor], seq_first: bool = False) -> None:
+    b, l = ids.shape
     rows, e = dx.shape
+    assert rows == b * l and dx.is_contiguous()
     _ck(_L().toist_embed_scatter(dx.data_ptr(), _dt(dx), ids.data_ptr(), pos_ids.data_ptr(), _ptr(dword), _ptr(dpos),
-                                 _ptr(dtype0), rows, e, _stream()))
+                                 _ptr(dtype0), b, l, e, 1 if seq_first else 0, _stream()))
+
+
+def permute_021(src: torch.Tensor) -> torch.Tensor:
+    """fp32 [A, B, C] -> [A, C, B] (conv weight gradient OHWI -> OIHW)."""
+    a, b, c = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    dst = torch.empty((a, c, b), dtype=torch.float32, device=src.device)
+    _ck(_L().toist_permute_021(src.data_ptr(), dst.data_ptr(), a, b, c, _stream()))
+    return dst
+
+
+def key_mask(pad_mask_u8: torch.Tensor, out_hw: Tuple[int, int], text_attention: Optional[torch.Tensor] = None):
+    """pad mask [B,H,W] uint8 -> (small [B,h,w] uint8, key [B, h*w + L] uint8); text_attention int64 [B, L]."""
+    b, hh, ww = pad_mask_u8.shape
+    h, w = out_hw
+    assert pad_mask_u8.dtype == torch.uint8 and pad_mask_u8.is_contiguous()
+    n_text = 0
+    if text_attention is not None:
+        assert text_attention.dtype == torch.int64 and text_attention.is_contiguous()
+        n_text = text_attention.shape[1]
+    small = torch.empty((b, h, w), dtype=torch.uint8, device=pad_mask_u8.device)
+    key = torch.empty((b, h * w + n_text), dtype=torch.uint8, device=pad_mask_u8.device)
+    _ck(_L().toist_key_mask(pad_mask_u8.data_ptr(), _ptr(text_attention), small.data_ptr(), key.data_ptr(), b, hh, ww,
+                            h, w, n_text, _stream()))
+    return small, key
 
 
 # ------------------------------------------------------------------------------------------------ attention (unfused)
@@ -472,7 +522,7 @@ def _ld8(n: int) -> int:
 
 
 def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8: Optional[torch.Tensor], nhead: int,
-                  need_probs: bool = True):
+                  need_probs: bool = True, ctx: Optional[torch.Tensor] = None):
     """Multi-head attention core on packed projections.
 
     q [Sq, B, E], k [Sk, B, E], v [Sk, B, E]: bf16 views whose last dim is contiguous (they may be column slices of a
@@ -491,10 +541,12 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8
     probs = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=dev)
     _ck(_L().toist_attn_softmax_fwd(scores.data_ptr(), _ptr(key_mask_u8), probs.data_ptr(), b * nhead * sq, sk, ld, ld,
                                     nhead * sq, _stream()))
-    ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=dev)
+    if ctx is None:
+        ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=dev)
+    assert ctx.shape == (sq, b, e) and ctx.stride(2) == 1
     gemm(GEMM_DGRAD, t4(probs, (sk, sq, nhead, b), (1, ld, sq * ld, nhead * sq * ld)),
          t4(v, (d, sk, nhead, b), (1, v.stride(0), d, v.stride(1))), ctx, ext=(sq, nhead, b), tile=(128, 1, 1),
-         n_cols=d, out_strides=(b * e, d, e), k_per_tap=sk, b_batched=True)
+         n_cols=d, out_strides=(ctx.stride(0), d, ctx.stride(1)), k_per_tap=sk, b_batched=True)
     return ctx, (probs if need_probs else None)
 
 
@@ -576,3 +628,77 @@ def relu_bwd(dy: torch.Tensor, y: torch.Tensor, dy2: Optional[torch.Tensor] = No
     out = torch.empty_like(dy)
     _ck(_L().toist_relu_bwd(dy.data_ptr(), _ptr(dy2), y.data_ptr(), out.data_ptr(), dy.numel(), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ criterion
+def token_ce(logits, match_q, tgt_count, posmap, num_boxes, eos_coef: float, want_grad: bool):
+    L, B, Q, Cc = logits.shape
+    tmax = match_q.shape[-1]
+    row_loss = torch.empty((L, B, Q), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    _ck(_L().toist_token_ce(logits.data_ptr(), match_q.data_ptr(), tgt_count.data_ptr(), posmap.data_ptr(),
+                            num_boxes.data_ptr(), row_loss.data_ptr(), _ptr(dlogits), L, B, Q, Cc, tmax, eos_coef,
+                            _stream()))
+    return row_loss, dlogits
+
+
+def box_loss(boxes, match_q, tgt_count, tgt_boxes, num_boxes, want_grad: bool):
+    L, B, Q, _ = boxes.shape
+    tmax = match_q.shape[-1]
+    dev = boxes.device
+    pl1 = torch.empty((L, B, tmax), dtype=torch.float32, device=dev)
+    pgi = torch.empty((L, B, tmax), dtype=torch.float32, device=dev)
+    d1 = torch.empty_like(boxes) if want_grad else None
+    d2 = torch.empty_like(boxes) if want_grad else None
+    _ck(_L().toist_box_loss(boxes.data_ptr(), match_q.data_ptr(), tgt_count.data_ptr(), tgt_boxes.data_ptr(),
+                            num_boxes.data_ptr(), pl1.data_ptr(), pgi.data_ptr(), _ptr(d1), _ptr(d2), L, B, Q, tmax,
+                            _stream()))
+    return pl1, pgi, d1, d2
+
+
+def cardinality(logits) -> torch.Tensor:
+    L, B, Q, Cc = logits.shape
+    card = torch.empty((L, B), dtype=torch.int32, device=logits.device)
+    _ck(_L().toist_cardinality(logits.data_ptr(), card.data_ptr(), L, B, Q, Cc, _stream()))
+    return card
+
+
+def contrastive_align(pq, pt, match_q, tgt_count, tok_pos, num_boxes, temperature: float, want_grad: bool = False):
+    L, B, Q, D = pq.shape
+    Kt = pt.shape[1]
+    tmax = match_q.shape[-1]
+    img_loss = torch.empty((L, B), dtype=torch.float32, device=pq.device)
+    dpq = torch.empty_like(pq) if want_grad else None
+    dpt = torch.empty((L, B, Kt, D), dtype=torch.float32, device=pq.device) if want_grad else None
+    _ck(_L().toist_contrastive_align(pq.data_ptr(), pt.data_ptr(), match_q.data_ptr(), tgt_count.data_ptr(),
+                                     tok_pos.data_ptr(), num_boxes.data_ptr(), img_loss.data_ptr(), _ptr(dpq),
+                                     _ptr(dpt), L, B, Q, Kt, D, tmax, temperature, _stream()))
+    return img_loss, dpq, dpt
+
+
+def criterion_reduce(row_loss, pl1, pgi, card, img_loss, tgt_count, num_boxes, flags) -> torch.Tensor:
+    L, B, Q = row_loss.shape
+    tmax = pl1.shape[-1]
+    out = torch.zeros((5, L), dtype=torch.float32, device=row_loss.device)
+    _ck(_L().toist_criterion_reduce(row_loss.data_ptr(), pl1.data_ptr(), pgi.data_ptr(), card.data_ptr(),
+                                    _ptr(img_loss), tgt_count.data_ptr(), num_boxes.data_ptr(), _ptr(flags),
+                                    out.data_ptr(), L, B, Q, tmax, _stream()))
+    return out
+
+
+def scale_layers(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """y[l] = x[l] * g[l] for x [L, ...] fp32, g [L] fp32."""
+    L = x.shape[0]
+    assert x.is_contiguous() and g.is_contiguous() and g.numel() == L
+    y = torch.empty_like(x)
+    _ck(_L().toist_scale_layers(x.data_ptr(), g.data_ptr(), y.data_ptr(), L, x.numel() // L, 0, _stream()))
+    return y
+
+
+def scale_layers2(x1, g1, x2, g2) -> torch.Tensor:
+    L = x1.shape[0]
+    assert x1.is_contiguous() and x2.is_contiguous() and g1.is_contiguous() and g2.is_contiguous()
+    y = torch.empty_like(x1)
+    _ck(_L().toist_scale_layers2(x1.data_ptr(), g1.data_ptr(), x2.data_ptr(), g2.data_ptr(), y.data_ptr(), L,
+                                 x1.numel() // L, _stream()))
+    return y

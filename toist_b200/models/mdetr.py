@@ -1,0 +1,442 @@
+"""MDETR / TOIST detector and its set criterion behind the reference's API (reference models/mdetr.py:315-1141).
+
+`MDETR.forward(samples, captions, encode_and_save, memory_cache)` keeps the two-phase protocol of engine.py:63-66 and
+the `memory_cache` / output dictionaries of models/transformer.py:155-166 and models/mdetr.py:422-462; parameters keep
+the reference's names so state dicts are interchangeable.  Everything numerical runs in hand-written sm_100a kernels
+(runtime.py); there is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from .. import kernels as K
+from ..runtime import (BackboneFn, Call, DecoderFn, EncoderFn, HeadsFn, ShadowBank, Stage, TextFn)
+from ..util import dist
+from ..util.misc import NestedTensor
+from .backbone import build_backbone
+from .matcher import PackedTargets, build_matcher, indices_from_match, match_layers, pack_targets
+from .transformer import build_transformer
+
+
+class MLP(nn.Module):
+    """Parameter container of the box head: Linear(256,256) - ReLU - Linear(256,256) - ReLU - Linear(256,4)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+
+class ModelRuntime:
+    """Lazily built per-model state: bf16 shadow weights and the static description of each autograd stage."""
+
+    def __init__(self):
+        self.bank = ShadowBank()
+        self.stages: Optional[Dict[str, Stage]] = None
+
+    def __deepcopy__(self, memo):  # the EMA copy (main.py:322) rebuilds its own
+        return ModelRuntime()
+
+    def build(self, m: "MDETR") -> None:
+        names = [n for n, _ in m.named_parameters()]
+        tr = m.transformer
+        tcfg = tr.text_encoder.config
+        body = m.backbone[0].body
+
+        def pick(*prefixes, exclude=()):
+            return [n for n in names if n.startswith(prefixes) and not any(e in n for e in exclude)]
+
+        heads = ("class_embed.", "bbox_embed.", "contrastive_align_projection_")
+        self.stages = {
+            "backbone": Stage(m, pick("backbone.0.body."), prefix="backbone.0.body.", blocks=body.blocks,
+                              first_trainable=2 if m.backbone[0].train_backbone else 5,
+                              return_interm=m.backbone[0].return_interm_layers),
+            "text": Stage(m, pick("transformer.text_encoder.", "transformer.resizer.", exclude=("pooler.",)),
+                          prefix="transformer.text_encoder.", resizer_prefix="transformer.resizer.",
+                          num_layers=tcfg.num_hidden_layers, num_heads=tcfg.num_attention_heads,
+                          eps=float(tcfg.layer_norm_eps), pad_id=int(tcfg.pad_token_id)),
+            "encoder": Stage(m, pick("input_proj.", "transformer.encoder."), prefix="transformer.encoder.",
+                             input_proj_prefix="input_proj.", num_layers=tr.encoder.num_layers, nhead=tr.nhead,
+                             want_src_proj=False),
+            "decoder": Stage(m, pick("transformer.decoder."), prefix="transformer.decoder.",
+                             num_layers=tr.decoder.num_layers, nhead=tr.nhead),
+            "heads": Stage(m, pick(*heads), prefix="", contrastive=m.contrastive_align_loss),
+        }
+
+    def refresh(self, m: "MDETR") -> None:
+        if self.stages is None:
+            self.build(m)
+        self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body)
+
+    def call(self, name: str, save: bool, **kw) -> Call:
+        return Call(self.stages[name], self.bank.w, save, **kw)
+
+
+class MDETR(nn.Module):
+    """Modulated detection model: ResNet trunk + RoBERTa -> 6+6 layer cross-modal transformer -> box / token heads."""
+
+    def __init__(self, backbone, transformer, num_classes, num_queries, aux_loss=False, contrastive_hdim=64,
+                 contrastive_align_loss=False, cluster_num=16, args=None):
+        super().__init__()
+        self.args = args
+        self.num_queries = num_queries
+        self.transformer = transformer
+        hidden_dim = transformer.d_model
+        self.class_embed = nn.Linear(hidden_dim, num_classes + 1)
+        self.bbox_embed = MLP(hidden_dim, hidden_dim, 4, 3)
+        self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.input_proj = nn.Conv2d(backbone.num_channels, hidden_dim, kernel_size=1)
+        self.backbone = backbone
+        self.aux_loss = aux_loss
+        self.contrastive_align_loss = contrastive_align_loss
+        if contrastive_align_loss:
+            self.contrastive_align_projection_image = nn.Linear(hidden_dim, contrastive_hdim)
+            self.contrastive_align_projection_text = nn.Linear(hidden_dim, contrastive_hdim)
+        self._rt = ModelRuntime()
+
+    # ------------------------------------------------------------------ helpers
+    def _check_mode(self) -> None:
+        p = float(getattr(self.transformer, "dropout_p", 0.0))
+        if self.training and p > 0:
+            raise NotImplementedError(
+                "toist_b200 round 1 implements the deterministic path (model.eval() or --dropout 0); training-mode "
+                f"dropout (p={p}) is not wired into the kernels yet")
+
+    def _grad_wanted(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    # ------------------------------------------------------------------ phase A (engine.py:63)
+    def encode(self, samples: NestedTensor, captions, want_features: bool = False) -> dict:
+        self._check_mode()
+        rt = self._rt
+        rt.refresh(self)
+        save = self._grad_wanted()
+        images = samples.tensors
+        if images.dtype != torch.float32 or not images.is_cuda:
+            raise RuntimeError("toist_b200 expects fp32 CUDA images (sm_100a); there is no CPU path")
+        images = images.contiguous()
+        bb = rt.call("backbone", save)
+        feats = BackboneFn.apply(bb, images, *bb.stage.params)
+        c5 = feats[-1]
+        B, h, w, _ = c5.shape
+        E = self.transformer.d_model
+        dev = images.device
+
+        if isinstance(captions[0], str):
+            tokenized = self.transformer.tokenizer.batch_encode_plus(captions, padding="longest",
+                                                                     return_tensors="pt").to(dev)
+            ids = tokenized["input_ids"].contiguous()
+            attn = tokenized["attention_mask"].to(torch.int64).contiguous()
+            text_attention_mask = attn.ne(1)
+            tx = rt.call("text", save)
+            text_resized = TextFn.apply(tx, ids, text_attention_mask.view(torch.uint8), *tx.stage.params)
+        else:  # already encoded (models/transformer.py:139-141)
+            text_attention_mask, text_resized, tokenized = captions
+            attn = (~text_attention_mask).to(torch.int64).contiguous()
+        L = text_resized.shape[0]
+
+        pad_u8 = samples.mask.contiguous().view(torch.uint8)
+        small, key = K.key_mask(pad_u8, (h, w), attn)
+        npf = self.backbone[1].num_pos_feats
+        pos32, pos16 = K.pos_sine(small, npf, float(self.backbone[1].temperature), extra_rows=L)
+        S = h * w + L
+        en = rt.call("encoder", save)
+        en.stage.want_src_proj = want_features
+        enc_out = EncoderFn.apply(en, c5, text_resized, pos16.view(S * B, E), key, *en.stage.params)
+        img_memory = enc_out[0] if want_features else enc_out
+        query_embed = self.query_embed.weight.unsqueeze(1).repeat(1, B, 1)
+        memory_cache = {
+            "text_memory_resized": text_resized,
+            "text_memory": img_memory[-L:],
+            "img_memory": img_memory,
+            "text_pooled_op": None,
+            "img_pooled_op": None,
+            "mask": key.view(torch.bool),
+            "text_attention_mask": text_attention_mask,
+            "pos_embed": pos32,
+            "query_embed": query_embed,
+            "tokenized": tokenized,
+        }
+        if want_features:
+            memory_cache["_b200_feats"] = feats
+            memory_cache["_b200_src_proj"] = enc_out[1]
+            memory_cache["_b200_small_mask"] = small
+        return memory_cache
+
+    # ------------------------------------------------------------------ phase B (engine.py:66)
+    def decode(self, memory_cache: dict, want_hs: bool = False) -> dict:
+        self._check_mode()
+        rt = self._rt
+        if rt.stages is None:
+            rt.refresh(self)
+        save = self._grad_wanted()
+        cluster = bool(getattr(self.args, "cluster", False))
+        mem = memory_cache["img_memory_mod"] if cluster else memory_cache["img_memory"]
+        S, B, E = mem.shape
+        pos16 = K.cast_bf16(memory_cache["pos_embed"].contiguous()).view(S * B, E)
+        key = memory_cache["mask"].contiguous().view(torch.uint8)
+        de = rt.call("decoder", save)
+        hs = DecoderFn.apply(de, mem, memory_cache["query_embed"], pos16, key, *de.stage.params)
+        hd = rt.call("heads", save, B=B)
+        res = HeadsFn.apply(hd, hs, memory_cache["text_memory"], *hd.stage.params)
+        logits, boxes = res[0], res[1]
+        out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
+        stacked = {"pred_logits": logits, "pred_boxes": boxes}
+        if self.contrastive_align_loss:
+            pq, ptok = res[2], res[3]
+            out.update({"proj_queries": pq[-1], "proj_tokens": ptok, "tokenized": memory_cache["tokenized"]})
+            stacked.update({"proj_queries": pq, "proj_tokens": ptok})
+        if self.aux_loss:
+            aux = []
+            for l in range(logits.shape[0] - 1):
+                a = {"pred_logits": logits[l], "pred_boxes": boxes[l]}
+                if self.contrastive_align_loss:
+                    a.update({"proj_queries": stacked["proj_queries"][l], "proj_tokens": stacked["proj_tokens"],
+                              "tokenized": memory_cache["tokenized"]})
+                aux.append(a)
+            out["aux_outputs"] = aux
+        out["_b200_stacked"] = stacked  # all decoder layers in one tensor each: the criterion consumes these
+        if want_hs:
+            out["_b200_hs"] = hs
+        return out
+
+    def forward(self, samples: NestedTensor, captions, encode_and_save=True, memory_cache=None):
+        if not isinstance(samples, NestedTensor):
+            samples = NestedTensor.from_tensor_list(samples)
+        if encode_and_save:
+            assert memory_cache is None
+            return self.encode(samples, captions)
+        assert memory_cache is not None
+        return self.decode(memory_cache)
+
+
+# ====================================================================================================== criterion
+class _CriterionFn(torch.autograd.Function):
+    """Matching + every detection loss term of every decoder layer; returns out [5, L] (see toist_criterion_reduce)
+    and the assignments.  Gradients w.r.t. logits and boxes only (the alignment loss is evaluated without gradient
+    in the reference, models/mdetr.py:601)."""
+
+    @staticmethod
+    def forward(ctx, cfg, logits, boxes, pq, ptok, tgt_boxes, tgt_count, posmap, tok_pos, num_boxes):
+        logits = logits.contiguous()
+        boxes = boxes.contiguous()
+        pt = PackedTargets(tgt_boxes, tgt_count, posmap, (), tgt_boxes.shape[1])
+        match_q, flags, _ = match_layers(logits, boxes, pt, cfg["w_class"], cfg["w_bbox"], cfg["w_giou"])
+        want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        row_loss, dlogits = K.token_ce(logits, match_q, tgt_count, posmap, num_boxes, cfg["eos_coef"], want)
+        pl1, pgi, d1, d2 = K.box_loss(boxes, match_q, tgt_count, tgt_boxes, num_boxes, want)
+        card = K.cardinality(logits)
+        img_loss = None
+        if pq is not None:
+            img_loss, _, _ = K.contrastive_align(pq.contiguous(), ptok.contiguous(), match_q, tgt_count, tok_pos,
+                                                 num_boxes, cfg["temperature"], False)
+        out = K.criterion_reduce(row_loss, pl1, pgi, card, img_loss, tgt_count, num_boxes, flags)
+        if want:
+            ctx.save_for_backward(dlogits, d1, d2)
+        ctx.mark_non_differentiable(match_q, flags)
+        return out, match_q, flags
+
+    @staticmethod
+    def backward(ctx, gout, _gm, _gf):
+        dlogits, d1, d2 = ctx.saved_tensors
+        gout = gout.contiguous()
+        gl = K.scale_layers(dlogits, gout[0]) if ctx.needs_input_grad[1] else None
+        gb = K.scale_layers2(d1, gout[1], d2, gout[2]) if ctx.needs_input_grad[2] else None
+        return (None, gl, gb) + (None,) * 7
+
+
+def _token_spans(tokenized, i: int, spans):
+    """char span -> token span with the reference's fallbacks (models/mdetr.py:622-643)."""
+    res = []
+    for (beg, end) in spans:
+        beg_pos = tokenized.char_to_token(i, beg)
+        end_pos = tokenized.char_to_token(i, end - 1)
+        if beg_pos is None:
+            try:
+                beg_pos = tokenized.char_to_token(beg + 1)
+                if beg_pos is None:
+                    beg_pos = tokenized.char_to_token(beg + 2)
+            except Exception:
+                beg_pos = None
+        if end_pos is None:
+            try:
+                end_pos = tokenized.char_to_token(end - 2)
+                if end_pos is None:
+                    end_pos = tokenized.char_to_token(end - 3)
+            except Exception:
+                end_pos = None
+        if beg_pos is None or end_pos is None:
+            continue
+        res.append((beg_pos, end_pos))
+    return res
+
+
+def build_token_positive(tokenized, targets, t_max: int, n_tokens: int) -> torch.Tensor:
+    """uint8 [B, t_max, n_tokens]: token j belongs to a positive span of target t of image b.  Built once per batch on
+    the host (the reference rebuilds it per decoder layer inside the loss, models/mdetr.py:614-645)."""
+    B = len(targets)
+    tp = torch.zeros((B, t_max, n_tokens), dtype=torch.uint8)
+    for i, tgt in enumerate(targets):
+        spans_all = tgt["tokens_positive"] if "tokens_positive" in tgt else tgt["tokens"]
+        for t in range(min(len(spans_all), t_max)):
+            for (b, e) in _token_spans(tokenized, i, spans_all[t]):
+                tp[i, t, b: e + 1] = 1
+    return tp
+
+
+class SetCriterion(nn.Module):
+    """Hungarian matching + soft-token CE, L1 / GIoU box losses, cardinality error and contrastive alignment for the
+    last decoder layer and every auxiliary layer, evaluated in a handful of launches without host synchronisation."""
+
+    _TERMS = ("loss_ce", "loss_bbox", "loss_giou", "cardinality_error", "loss_contrastive_align")
+
+    def __init__(self, args, num_classes, matcher, eos_coef, losses, temperature, contrastive_hdim, task_count=14):
+        super().__init__()
+        self.args = args
+        self.num_classes = num_classes
+        self.matcher = matcher
+        self.eos_coef = eos_coef
+        self.losses = losses
+        self.temperature = temperature
+        unsupported = [l for l in losses if l not in ("labels", "boxes", "cardinality", "contrastive_align")]
+        self._unsupported = unsupported
+
+    def _stack(self, outputs: dict) -> Dict[str, torch.Tensor]:
+        st = outputs.get("_b200_stacked")
+        if st is not None:
+            return st
+        layers = list(outputs.get("aux_outputs", [])) + [outputs]
+        res = {k: torch.stack([o[k] for o in layers]) for k in ("pred_logits", "pred_boxes")}
+        if "proj_queries" in outputs:
+            res["proj_queries"] = torch.stack([o["proj_queries"] for o in layers])
+            res["proj_tokens"] = outputs["proj_tokens"]
+        return res
+
+    def num_boxes_tensor(self, targets, device) -> torch.Tensor:
+        """Global mean number of target boxes, clamped to >= 1, kept on the device (models/mdetr.py:997-1001 does an
+        all-reduce followed by a blocking .item())."""
+        n = sum(len(t["labels"]) for t in targets)
+        nb = torch.as_tensor([n], dtype=torch.float, device=device)
+        if dist.is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(nb)
+        return torch.clamp(nb / dist.get_world_size(), min=1)
+
+    def forward(self, memory_cache, outputs, targets, positive_map, example_rel=None):
+        if isinstance(outputs, list):
+            raise NotImplementedError("the distillation branch (models/mdetr.py:887-989) is not built yet")
+        if self._unsupported:
+            raise NotImplementedError(f"losses {self._unsupported} are not built yet")
+        st = self._stack(outputs)
+        logits, boxes = st["pred_logits"], st["pred_boxes"]
+        if logits.dtype != torch.float32 or not logits.is_cuda:
+            raise RuntimeError("toist_b200 criterion expects fp32 CUDA predictions; there is no CPU path")
+        L = logits.shape[0]
+        dev = logits.device
+        use_aux = "aux_outputs" in outputs
+        packed = pack_targets(targets, positive_map, dev)
+        nb = self.num_boxes_tensor(targets, dev)
+        pq = ptok = tok_pos = None
+        if "contrastive_align" in self.losses:
+            pq, ptok = st["proj_queries"], st["proj_tokens"]
+            tok_pos = build_token_positive(outputs["tokenized"], targets, packed.t_max, ptok.shape[1]).to(
+                dev, non_blocking=True)
+        cfg = {"w_class": float(self.matcher.cost_class), "w_bbox": float(self.matcher.cost_bbox),
+               "w_giou": float(self.matcher.cost_giou), "eos_coef": float(self.eos_coef),
+               "temperature": float(self.temperature)}
+        out, match_q, flags = _CriterionFn.apply(cfg, logits, boxes, pq, ptok, packed.boxes, packed.count,
+                                                 packed.posmap, tok_pos, nb)
+        self.last_match = (match_q, packed.counts, flags)
+        terms = [("loss_ce", 0), ("loss_bbox", 1), ("loss_giou", 2), ("cardinality_error", 3)]
+        if pq is not None:
+            terms.append(("loss_contrastive_align", 4))
+        losses = {}
+        for name, row in terms:
+            v = out[row, L - 1]
+            losses[name] = v.detach() if row >= 3 else v
+        if use_aux:
+            for i in range(L - 1):
+                for name, row in terms:
+                    v = out[row, i]
+                    losses[f"{name}_{i}"] = v.detach() if row >= 3 else v
+        return losses
+
+    def last_indices(self) -> List[List[tuple]]:
+        """Assignments of the most recent forward as the reference's index pairs, one list per decoder layer
+        (synchronises; for tests and debugging)."""
+        match_q, counts, flags = self.last_match
+        if int(flags.item()) != 0:
+            raise ValueError("matrix contains invalid numeric entries")
+        mq = match_q.cpu()
+        return [indices_from_match(mq[l], counts) for l in range(mq.shape[0])]
+
+
+def build(args):
+    num_classes = 255
+    device = torch.device(args.device)
+    assert not args.masks or args.mask_model != "none"
+    backbone = build_backbone(args)
+    transformer = build_transformer(args)
+    model = MDETR(backbone, transformer, num_classes=num_classes, num_queries=args.num_queries, aux_loss=args.aux_loss,
+                  contrastive_hdim=args.contrastive_loss_hdim, contrastive_align_loss=args.contrastive_align_loss,
+                  cluster_num=args.cluster_num, args=args)
+    if args.mask_model != "none":
+        from .segmentation import DETRsegm
+
+        model = DETRsegm(model, mask_head=args.mask_model, freeze_detr=(args.frozen_weights is not None))
+    matcher = build_matcher(args)
+    weight_dict = {"loss_ce": args.ce_loss_coef, "loss_bbox": args.bbox_loss_coef}
+    if args.contrastive_align_loss:
+        weight_dict["loss_contrastive_align"] = args.contrastive_align_loss_coef
+    if args.nsthl2_loss:
+        weight_dict["loss_nsthl2"] = args.nsthl2_coef
+    if args.softkd_loss:
+        weight_dict["loss_softkd"] = args.softkd_coef
+    if args.cluster and args.distillation:
+        weight_dict["loss_cluster_choice"] = args.cluster_choice_loss
+        weight_dict["loss_cluster_feature"] = args.cluster_feature_loss
+    weight_dict["loss_giou"] = args.giou_loss_coef
+    if args.masks:
+        weight_dict["loss_mask"] = args.mask_loss_coef
+        weight_dict["loss_dice"] = args.dice_loss_coef
+
+    def with_aux(d):
+        if args.aux_loss:
+            extra = {}
+            for i in range(args.dec_layers - 1):
+                extra.update({k + f"_{i}": v for k, v in d.items()})
+            d.update(extra)
+        return d
+
+    if args.distillation:
+        cross = ("loss_nsthl2", "loss_softkd", "loss_cluster_choice", "loss_cluster_feature")
+        prefixed = {}
+        for k, v in weight_dict.items():
+            if k in cross:
+                prefixed[k] = v
+            else:
+                prefixed["noun_" + k] = v
+                prefixed["sth_" + k] = v
+        weight_dict = with_aux(prefixed)
+    else:
+        weight_dict = with_aux(weight_dict)
+
+    losses = ["labels", "boxes", "cardinality"]
+    if args.masks:
+        losses += ["masks"]
+    if args.contrastive_align_loss:
+        losses += ["contrastive_align"]
+    if args.nsthl2_loss:
+        losses += ["nsthl2"]
+    if args.softkd_loss:
+        losses += ["softkd"]
+    criterion = SetCriterion(args, num_classes, matcher=matcher, eos_coef=args.eos_coef, losses=losses,
+                             temperature=args.temperature_NCE, contrastive_hdim=args.contrastive_loss_hdim,
+                             task_count=14)
+    criterion.to(device)
+    if args.cluster:
+        raise NotImplementedError("ClusterCriterion (models/mdetr.py:29-312, config 5) is not built yet")
+    return model, criterion, None, weight_dict

@@ -1,0 +1,546 @@
+"""Glue between torch.autograd / nn.Module parameters and the kernel-level blocks.
+
+* `ShadowBank` keeps a bf16 copy of every GEMM / convolution weight (FrozenBatchNorm scale folded per output
+  channel, conv weights re-laid out OIHW -> OHWI) and refreshes all of them with one `toist_weight_prep` launch.
+* Five `torch.autograd.Function`s wrap the stages of the hot path; their backward passes are hand written on top of
+  blocks.py, so torch only moves gradients between stages and accumulates them into `Parameter.grad` (which keeps
+  DistributedDataParallel's reducer hooks working, reference main.py:336).
+
+  BackboneFn  images -> NHWC features            (models/backbone.py:74-80, torchvision resnet)
+  TextFn      token ids -> resized text features (models/transformer.py:129-138,487-492)
+  EncoderFn   features + text -> img_memory      (models/mdetr.py:383 input_proj, models/transformer.py:144-152)
+  DecoderFn   img_memory -> hs                   (models/transformer.py:170-188)
+  HeadsFn     hs -> logits / boxes / projections (models/mdetr.py:420-433)
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence, Set, Tuple
+
+import torch
+
+from . import blocks as Bk
+from . import kernels as K
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
+
+BF = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ prefix views
+class WView:
+    """Read-only view of the flat weight dict under a name prefix."""
+
+    __slots__ = ("d", "p")
+
+    def __init__(self, d, p: str):
+        self.d, self.p = d, p
+
+    def __getitem__(self, k: str):
+        return self.d[self.p + k]
+
+    def sub(self, p: str) -> "WView":
+        return WView(self.d, self.p + p)
+
+
+class GView:
+    """Gradient sink under a name prefix (dict-like: in / get / set)."""
+
+    __slots__ = ("d", "p")
+
+    def __init__(self, d, p: str):
+        self.d, self.p = d, p
+
+    def __contains__(self, k: str) -> bool:
+        return (self.p + k) in self.d
+
+    def __getitem__(self, k: str):
+        return self.d[self.p + k]
+
+    def __setitem__(self, k: str, v) -> None:
+        self.d[self.p + k] = v
+
+
+class RView:
+    __slots__ = ("s", "p")
+
+    def __init__(self, s: Set[str], p: str):
+        self.s, self.p = s, p
+
+    def __contains__(self, k: str) -> bool:
+        return (self.p + k) in self.s
+
+
+# ------------------------------------------------------------------------------------------------ saved-tensor packing
+def _pack(obj, flat: List[torch.Tensor]):
+    if isinstance(obj, torch.Tensor):
+        flat.append(obj)
+        return ("t", len(flat) - 1)
+    if isinstance(obj, (tuple, list)):
+        return ("l", [_pack(o, flat) for o in obj])
+    return ("c", obj)
+
+
+def _unpack(spec, flat: Sequence[torch.Tensor]):
+    kind, val = spec
+    if kind == "t":
+        return flat[val]
+    if kind == "l":
+        return tuple(_unpack(s, flat) for s in val)
+    return val
+
+
+def _save(ctx, obj) -> None:
+    flat: List[torch.Tensor] = []
+    ctx.spec = _pack(obj, flat)
+    ctx.save_for_backward(*flat)
+
+
+def _load(ctx):
+    return _unpack(ctx.spec, ctx.saved_tensors)
+
+
+# ------------------------------------------------------------------------------------------------ shadow weights
+_EMBEDDING_KEYS = ("word_embeddings", "position_embeddings", "token_type_embeddings", "query_embed")
+RESNET_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
+STEM_LDK = 192  # 7*7*3 = 147 patch columns padded to a multiple of 64
+
+
+class ShadowBank:
+    """bf16 working copies of a model's weights + derived FrozenBatchNorm scale / shift vectors."""
+
+    def __init__(self):
+        self.w: Dict[str, torch.Tensor] = {}
+        self.prep: Optional[K.WeightPrep] = None
+        self._sig = None
+
+    def __deepcopy__(self, memo):  # EMA deep-copies the model (util/optim.py, main.py:322); rebuild lazily there
+        return ShadowBank()
+
+    @staticmethod
+    def _signature(model) -> tuple:
+        ps = tuple(p.data_ptr() for p in model.parameters())
+        bs = tuple((b.data_ptr(), b._version) for b in model.buffers())
+        return ps + bs
+
+    def ensure(self, model, backbone_prefix: str, body) -> None:
+        """(Re)builds the bank when parameters moved (device change, load of a new module) or BN buffers changed,
+        then refreshes every shadow from its fp32 master."""
+        sig = self._signature(model)
+        if sig != self._sig:
+            self._build(model, backbone_prefix, body)
+            self._sig = sig
+        self.prep.run()
+
+    def _build(self, model, backbone_prefix: str, body) -> None:
+        params = dict(model.named_parameters())
+        dev = next(iter(params.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("toist_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        prep = K.WeightPrep(dev)
+        w: Dict[str, torch.Tensor] = {}
+        conv_names = set()
+        # ---- backbone: conv + FrozenBatchNorm pairs
+        for conv_name, bn_name in body.conv_bn_pairs():
+            conv_w = params[backbone_prefix + conv_name + ".weight"]
+            bn = body.get_submodule(bn_name)
+            scale = (bn.weight * (bn.running_var + 1e-5).rsqrt()).float().contiguous()  # models/backbone.py:54-57
+            shift = (bn.bias - bn.running_mean * scale).float().contiguous()
+            cout, cin, kh, kw = conv_w.shape
+            if conv_name == "conv1":  # 7x7 stem, consumed as an im2col GEMM
+                sh = torch.zeros((cout, STEM_LDK), dtype=BF, device=dev)
+                prep.add(conv_w.detach(), sh, cout, cin * kh * kw, STEM_LDK, scale, taps=kh * kw)
+            else:
+                sh = torch.empty((cout, kh, kw, cin), dtype=BF, device=dev)
+                prep.add(conv_w.detach(), sh, cout, cin * kh * kw, None, scale, taps=kh * kw)
+            w[backbone_prefix + conv_name + ".weight"] = sh
+            w[backbone_prefix + bn_name + ".scale"] = scale
+            w[backbone_prefix + bn_name + ".shift"] = shift
+            conv_names.add(backbone_prefix + conv_name + ".weight")
+        # ---- everything else
+        for name, p in params.items():
+            if name in conv_names:
+                continue
+            qkv_part = ".attention.self." in name and name.endswith(("query.weight", "key.weight", "value.weight"))
+            if p.dim() >= 2 and not qkv_part and not any(k in name for k in _EMBEDDING_KEYS):
+                rows = p.shape[0]
+                cols = p.numel() // rows
+                sh = torch.empty((rows, cols), dtype=BF, device=dev)
+                prep.add(p.detach(), sh, rows, cols)
+                w[name] = sh
+            else:
+                w[name] = p.detach()
+        # ---- RoBERTa: q | k | v stacked so that the data gradient is one GEMM
+        for name in list(params):
+            if name.endswith("attention.self.query.weight"):
+                base = name[: -len("query.weight")]
+                E = params[name].shape[0]
+                qkv = torch.empty((3 * E, E), dtype=BF, device=dev)
+                for i, nm in enumerate(("query", "key", "value")):
+                    prep.add(params[base + nm + ".weight"].detach(), qkv[i * E:(i + 1) * E], E, E)
+                w[base + "qkv"] = qkv
+        self.w, self.prep = w, prep
+
+
+def requires(names: Iterable[str], params: Sequence[torch.Tensor], enabled: bool) -> Set[str]:
+    return {n for n, p in zip(names, params) if enabled and p.requires_grad}
+
+
+def _grads_for(names: Sequence[str], g: Dict[str, torch.Tensor], params_shapes) -> tuple:
+    out = []
+    for n, shp in zip(names, params_shapes):
+        t = g.get(n)
+        out.append(None if t is None else t.view(shp))
+    return tuple(out)
+
+
+class Stage:
+    """Static description of one autograd stage: which parameters it owns (ordered) and configuration."""
+
+    def __init__(self, model, names: Sequence[str], **cfg):
+        lookup = dict(model.named_parameters())
+        self.names = list(names)
+        self.params = [lookup[n] for n in self.names]
+        self.shapes = [tuple(p.shape) for p in self.params]
+        self.__dict__.update(cfg)
+
+    def req(self) -> Set[str]:
+        return requires(self.names, self.params, torch.is_grad_enabled())
+
+
+class Call:
+    """Per-invocation context handed to a Function (non-tensor argument)."""
+
+    def __init__(self, stage: Stage, w: Dict[str, torch.Tensor], save: bool, **kw):
+        self.stage, self.w = stage, w
+        self.req = stage.req() if save else set()
+        self.save = save  # keep activations for a backward pass (some tensor upstream or here wants a gradient)
+        self.__dict__.update(kw)
+
+
+# ------------------------------------------------------------------------------------------------ backbone
+def backbone_fwd(c: Call, images: torch.Tensor):
+    st = c.stage
+    w = WView(c.w, st.prefix)
+    n, _, hh, ww = images.shape
+    patches = K.stem_im2col(images, STEM_LDK)
+    ho, wo = K.conv_out_size(hh, 7, 2, 3), K.conv_out_size(ww, 7, 2, 3)
+    y = K.linear_fwd(patches, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU).view(n, ho, wo, 64)
+    del patches
+    x = K.maxpool3x3s2(y)
+    del y
+    feats, saved = [], {}
+    for li, nblocks in enumerate(st.blocks, start=1):
+        for bi in range(nblocks):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            x, sv = Bk.bottleneck_fwd(w.sub(f"layer{li}.{bi}."), x, stride, bi == 0)
+            if c.save and li >= st.first_trainable:
+                saved[(li, bi)] = sv
+        feats.append(x)
+    return feats, saved
+
+
+def backbone_bwd(c: Call, gfeats: Dict[int, torch.Tensor], feats: Sequence[torch.Tensor], saved) -> Dict[str, torch.Tensor]:
+    """gfeats: layer index (1..4) -> gradient of that layer's output (NHWC bf16)."""
+    st = c.stage
+    grads: Dict[str, torch.Tensor] = {}
+    w = WView(c.w, st.prefix)
+    gz = None
+    for li in range(4, st.first_trainable - 1, -1):
+        nblocks = st.blocks[li - 1]
+        ext = gfeats.get(li)
+        if ext is not None:
+            ext = K.relu_bwd(ext.contiguous(), feats[li - 1])
+            gz = ext if gz is None else K.add_bf16(gz, ext)
+        if gz is None:
+            continue
+        for bi in range(nblocks - 1, -1, -1):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            pre = f"layer{li}.{bi}."
+            need_dx = not (li == st.first_trainable and bi == 0)
+            gz = Bk.bottleneck_bwd(w.sub(pre), GView(grads, st.prefix + pre), RView(c.req, st.prefix + pre), gz,
+                                   saved[(li, bi)], stride, bi == 0, need_dx)
+    return grads
+
+
+class BackboneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c: Call, images, *params):
+        feats, saved = backbone_fwd(c, images)
+        ctx.c = c
+        keys = sorted(saved)
+        ctx.keys = keys
+        if c.save:
+            _save(ctx, (tuple(feats), tuple(saved[k] for k in keys)))
+        return tuple(feats) if c.stage.return_interm else (feats[-1],)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        c = ctx.c
+        feats, saved_list = _load(ctx)
+        saved = dict(zip(ctx.keys, saved_list))
+        if c.stage.return_interm:
+            gfeats = {i + 1: g for i, g in enumerate(gouts) if g is not None}
+        else:
+            gfeats = {4: gouts[0]} if gouts[0] is not None else {}
+        grads = backbone_bwd(c, gfeats, feats, saved) if c.req else {}
+        return (None, None) + _grads_for(c.stage.names, grads, c.stage.shapes)
+
+
+# ------------------------------------------------------------------------------------------------ text encoder
+def text_fwd(c: Call, input_ids: torch.Tensor, text_mask_u8: torch.Tensor):
+    """RobertaModel.forward + FeatureResizer (eval semantics: no dropout).  Returns fp32 [L, B, d_model]."""
+    st = c.stage
+    w = WView(c.w, st.prefix)
+    B, L = input_ids.shape
+    e = w.sub("embeddings.")
+    x32, pos_ids = K.embed_gather(input_ids, e["word_embeddings.weight"], e["position_embeddings.weight"],
+                                  e["token_type_embeddings.weight"], st.pad_id, seq_first=True)
+    x, _, m0, r0 = Bk.ln_fwd(e, "LayerNorm.", x32, st.eps)
+    saved_layers = []
+    for i in range(st.num_layers):
+        x, sv = Bk.roberta_layer_fwd(w.sub(f"encoder.layer.{i}."), x, text_mask_u8, st.num_heads, B, st.eps)
+        saved_layers.append(sv if c.save else None)
+    r = WView(c.w, st.resizer_prefix)
+    y = K.linear_fwd(x, r["fc.weight"], r["fc.bias"], out_dtype=torch.float32)
+    _, out, m1, r1 = Bk.ln_fwd(r, "layer_norm.", y, 1e-12, want_bf16=False, want_f32=True)
+    saved = (pos_ids, x32, m0, r0, tuple(saved_layers), x, y, m1, r1) if c.save else None
+    return out.view(L, B, -1), saved
+
+
+def text_bwd(c: Call, dout: torch.Tensor, input_ids, saved) -> Dict[str, torch.Tensor]:
+    st = c.stage
+    grads: Dict[str, torch.Tensor] = {}
+    w = WView(c.w, st.prefix)
+    pos_ids, x32, m0, r0, saved_layers, x_last, y, m1, r1 = saved
+    B, L = input_ids.shape
+    rp = st.resizer_prefix
+    r = WView(c.w, rp)
+    d = dout.contiguous().view(L * B, -1)
+    dy = Bk.ln_bwd(r, GView(grads, rp), RView(c.req, rp), "layer_norm.", d, y, m1, r1)
+    Bk.lin_param_grads(GView(grads, rp), RView(c.req, rp), "fc.weight", "fc.bias", dy, x_last, r["fc.weight"].shape)
+    body_req = any(n.startswith(st.prefix) for n in c.req)
+    if not body_req:
+        return grads
+    dx = K.linear_dgrad(dy, r["fc.weight"])
+    for i in range(st.num_layers - 1, -1, -1):
+        pre = st.prefix + f"encoder.layer.{i}."
+        dx = Bk.roberta_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dx, saved_layers[i],
+                                  st.num_heads, B)
+    pre = st.prefix + "embeddings."
+    e = WView(c.w, pre)
+    dx32 = Bk.ln_bwd(e, GView(grads, pre), RView(c.req, pre), "LayerNorm.", dx, x32, m0, r0, dx_dtype=torch.float32)
+    names = ("word_embeddings.weight", "position_embeddings.weight", "token_type_embeddings.weight")
+    bufs = []
+    for nm in names:
+        if (pre + nm) in c.req:
+            t = torch.zeros_like(e[nm], dtype=torch.float32)
+            grads[pre + nm] = t
+            bufs.append(t)
+        else:
+            bufs.append(None)
+    if any(b is not None for b in bufs):
+        K.embed_scatter(dx32, input_ids, pos_ids, bufs[0], bufs[1], bufs[2], seq_first=True)
+    return grads
+
+
+class TextFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c: Call, input_ids, text_mask_u8, *params):
+        out, saved = text_fwd(c, input_ids, text_mask_u8)
+        ctx.c = c
+        if c.save:
+            _save(ctx, (input_ids, saved))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        c = ctx.c
+        input_ids, saved = _load(ctx)
+        grads = text_bwd(c, dout, input_ids, saved)
+        return (None, None, None) + _grads_for(c.stage.names, grads, c.stage.shapes)
+
+
+# ------------------------------------------------------------------------------------------------ encoder
+def encoder_fwd(c: Call, feat: torch.Tensor, text: torch.Tensor, pos16: torch.Tensor, key_mask: torch.Tensor):
+    """feat NHWC bf16 [B,h,w,C]; text fp32 [L,B,E]; pos16 bf16 [S*B,E]; key_mask uint8 [B,S]."""
+    st = c.stage
+    B, h, wd, _ = feat.shape
+    L, _, E = text.shape
+    hw = h * wd
+    S = hw + L
+    src = torch.empty((S * B, E), dtype=BF, device=feat.device)
+    ip = WView(c.w, st.input_proj_prefix)
+    Bk.seq_from_nhwc_fwd(feat, ip["weight"], ip["bias"], src[: hw * B], B)
+    K.cast_bf16(text.contiguous().view(L * B, E), out=src[hw * B:])
+    x = src
+    saved_layers = []
+    for i in range(st.num_layers):
+        x, sv = Bk.encoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), x, pos16, key_mask, st.nhead, B)
+        saved_layers.append(sv if c.save else None)
+    mem = K.cast_f32(x).view(S, B, E)
+    return mem, (src, tuple(saved_layers), x)
+
+
+class EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c: Call, feat, text, pos16, key_mask, *params):
+        mem, saved = encoder_fwd(c, feat, text, pos16, key_mask)
+        ctx.c = c
+        ctx.text_shape = tuple(text.shape)
+        if c.save:
+            _save(ctx, (feat, pos16, key_mask, saved))
+        if c.stage.want_src_proj:
+            B, h, wd, _ = feat.shape
+            E = text.shape[-1]
+            return mem, saved[0][: h * wd * B].view(h * wd, B, E)
+        return mem
+
+    @staticmethod
+    def backward(ctx, dmem, dsrc_proj=None):
+        c = ctx.c
+        st = c.stage
+        feat, pos16, key_mask, (src, saved_layers, x_last) = _load(ctx)
+        B, h, wd, _ = feat.shape
+        L, _, E = ctx.text_shape
+        hw = h * wd
+        grads: Dict[str, torch.Tensor] = {}
+        d = K.cast_bf16(dmem.contiguous().view(-1, E))
+        for i in range(st.num_layers - 1, -1, -1):
+            pre = st.prefix + f"layers.{i}."
+            d = Bk.encoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), d, saved_layers[i],
+                                     st.nhead, B)
+        d_img = d[: hw * B]
+        if dsrc_proj is not None:  # mask head reads src_proj (models/segmentation.py:77-78)
+            d_img = K.add_bf16(d_img, K.cast_bf16(dsrc_proj.contiguous().view(-1, E)))
+        dtext = K.cast_f32(d[hw * B:]).view(L, B, E) if ctx.needs_input_grad[2] else None
+        ipp = st.input_proj_prefix
+        dfeat = Bk.seq_from_nhwc_bwd(GView(grads, ipp), RView(c.req, ipp), "weight", "bias", d_img, feat,
+                                     c.w[ipp + "weight"], ctx.needs_input_grad[1])
+        return (None, dfeat, dtext, None, None) + _grads_for(st.names, grads, st.shapes)
+
+
+# ------------------------------------------------------------------------------------------------ decoder
+def decoder_fwd(c: Call, mem32: torch.Tensor, qpos32: torch.Tensor, pos16: torch.Tensor, key_mask: torch.Tensor):
+    """mem32 fp32 [S,B,E], qpos32 fp32 [Q,B,E] -> hs bf16 [layers, Q*B, E] (final LayerNorm applied per layer)."""
+    st = c.stage
+    S, B, E = mem32.shape
+    Q = qpos32.shape[0]
+    mem = K.cast_bf16(mem32.contiguous().view(S * B, E))
+    mem_pos = K.add_bf16(mem, pos16)
+    qpos = K.cast_bf16(qpos32.contiguous().view(Q * B, E))
+    tgt = torch.zeros((Q * B, E), dtype=BF, device=mem.device)
+    hs = torch.empty((st.num_layers, Q * B, E), dtype=BF, device=mem.device)
+    nw = WView(c.w, st.prefix + "norm.")
+    saved_layers = []
+    for i in range(st.num_layers):
+        tgt, sv = Bk.decoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), tgt, qpos, mem, mem_pos, key_mask,
+                                       st.nhead, B)
+        _, _, m, r = K.layernorm_fwd(tgt, nw["weight"], nw["bias"], 1e-5, out16=hs[i])
+        saved_layers.append((sv, tgt, m, r) if c.save else None)
+    return hs, tuple(saved_layers)
+
+
+class DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c: Call, mem32, qpos32, pos16, key_mask, *params):
+        hs, saved = decoder_fwd(c, mem32, qpos32, pos16, key_mask)
+        ctx.c = c
+        ctx.shapes = (tuple(mem32.shape), tuple(qpos32.shape))
+        if c.save:
+            _save(ctx, saved)
+        return hs
+
+    @staticmethod
+    def backward(ctx, dhs):
+        c = ctx.c
+        st = c.stage
+        saved_layers = _load(ctx)
+        (S, B, E), (Q, _, _) = ctx.shapes
+        grads: Dict[str, torch.Tensor] = {}
+        dhs = dhs.contiguous()
+        np_ = st.prefix + "norm."
+        d_next = None
+        d_qpos = d_mem = None
+        for i in range(st.num_layers - 1, -1, -1):
+            sv, t3, m, r = saved_layers[i]
+            dy = Bk.ln_bwd(WView(c.w, np_), GView(grads, np_), RView(c.req, np_), "", dhs[i], t3, m, r)
+            pre = st.prefix + f"layers.{i}."
+            d_tgt, dq, dmp, dm = Bk.decoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dy,
+                                                      d_next, sv, st.nhead, B, need_tgt=i > 0)
+            d_next = d_tgt
+            d_qpos = dq if d_qpos is None else K.add_bf16(d_qpos, dq)
+            d_mem = K.add_bf16(dmp, dm) if d_mem is None else K.add_bf16(d_mem, dmp, dm)
+        dmem32 = K.cast_f32(d_mem).view(S, B, E) if ctx.needs_input_grad[1] else None
+        dqpos32 = K.cast_f32(d_qpos).view(Q, B, E) if ctx.needs_input_grad[2] else None
+        return (None, dmem32, dqpos32, None, None) + _grads_for(st.names, grads, st.shapes)
+
+
+# ------------------------------------------------------------------------------------------------ heads
+def heads_fwd(c: Call, hs: torch.Tensor, text_mem32: Optional[torch.Tensor], B: int):
+    """hs bf16 [L, Q*B, E] -> logits [L,B,Q,C], boxes [L,B,Q,4] (sigmoid), proj_queries [L,B,Q,D], proj_tokens [B,T,D]."""
+    st = c.stage
+    w = WView(c.w, st.prefix)
+    L, QB, E = hs.shape
+    Q = QB // B
+    logits = Bk.heads_linear_fwd(hs, w["class_embed.weight"], w["class_embed.bias"], L, Q, B)
+    hs2 = hs.view(L * QB, E)
+    h1 = K.linear_fwd(hs2, w["bbox_embed.layers.0.weight"], w["bbox_embed.layers.0.bias"], act=ACT_RELU)
+    h2 = K.linear_fwd(h1, w["bbox_embed.layers.1.weight"], w["bbox_embed.layers.1.bias"], act=ACT_RELU)
+    boxes = Bk.heads_linear_fwd(h2.view(L, QB, E), w["bbox_embed.layers.2.weight"], w["bbox_embed.layers.2.bias"], L, Q,
+                                B, act=ACT_SIGMOID)
+    pq = pt = None
+    if st.contrastive:
+        raw = Bk.heads_linear_fwd(hs, w["contrastive_align_projection_image.weight"],
+                                  w["contrastive_align_projection_image.bias"], L, Q, B)
+        D = raw.shape[-1]
+        pq, _ = K.l2norm_fwd(raw.view(-1, D))
+        pq = pq.view(L, B, Q, D)
+        T = text_mem32.shape[0]
+        tm = K.cast_bf16(text_mem32.contiguous().view(1, T * B, E))
+        rawt = Bk.heads_linear_fwd(tm, w["contrastive_align_projection_text.weight"],
+                                   w["contrastive_align_projection_text.bias"], 1, T, B)
+        pt, _ = K.l2norm_fwd(rawt.view(-1, D))
+        pt = pt.view(B, T, D)
+    return logits, boxes, pq, pt, (h1, h2)
+
+
+class HeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c: Call, hs, text_mem32, *params):
+        logits, boxes, pq, pt, (h1, h2) = heads_fwd(c, hs, text_mem32, c.B)
+        ctx.c = c
+        if c.save:
+            ctx.save_for_backward(hs, h1, h2, boxes)
+        if pq is None:
+            return logits, boxes
+        # the reference evaluates the contrastive-alignment loss under torch.no_grad (models/mdetr.py:601), so the
+        # projections never receive a gradient; they are emitted as constants
+        ctx.mark_non_differentiable(pq, pt)
+        return logits, boxes, pq, pt
+
+    @staticmethod
+    def backward(ctx, dlogits, dboxes, *unused):
+        c = ctx.c
+        st = c.stage
+        hs, h1, h2, boxes = ctx.saved_tensors
+        L, QB, E = hs.shape
+        B = c.B
+        Q = QB // B
+        grads: Dict[str, torch.Tensor] = {}
+        g, rq, w = GView(grads, st.prefix), RView(c.req, st.prefix), WView(c.w, st.prefix)
+        dhs = None
+        if dboxes is not None:
+            dpre = K.sigmoid_bwd(dboxes.contiguous(), boxes)
+            d16 = K.cast_pad_bf16(dpre, 8)
+            dh2 = Bk.heads_linear_bwd(g, rq, "bbox_embed.layers.2.weight", "bbox_embed.layers.2.bias", d16,
+                                      h2.view(L, QB, E), w["bbox_embed.layers.2.weight"], L, Q, B,
+                                      mask=h2.view(L, QB, E)).view(L * QB, E)
+            Bk.lin_param_grads(g, rq, "bbox_embed.layers.1.weight", "bbox_embed.layers.1.bias", dh2, h1, (E, E))
+            dh1 = K.linear_dgrad(dh2, w["bbox_embed.layers.1.weight"], mask=h1)
+            Bk.lin_param_grads(g, rq, "bbox_embed.layers.0.weight", "bbox_embed.layers.0.bias", dh1, hs.view(L * QB, E),
+                               (E, E))
+            dhs = K.linear_dgrad(dh1, w["bbox_embed.layers.0.weight"]).view(L, QB, E)
+        if dlogits is not None:
+            d16 = K.cast_bf16(dlogits.contiguous())
+            dhs = Bk.heads_linear_bwd(g, rq, "class_embed.weight", "class_embed.bias", d16, hs,
+                                      w["class_embed.weight"], L, Q, B, res=dhs)
+        return (None, dhs, None) + _grads_for(st.names, grads, st.shapes)

@@ -1,0 +1,46 @@
+"""Batch container used at the model boundary (mirrors the reference's util/misc.py:171-212 interface)."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+
+class NestedTensor(object):
+    """A padded image batch `tensors` [B, C, H, W] with its boolean padding mask `mask` [B, H, W] (True = padding)."""
+
+    def __init__(self, tensors: Tensor, mask: Optional[Tensor]):
+        self.tensors = tensors
+        self.mask = mask
+
+    def to(self, *args, **kwargs) -> "NestedTensor":
+        t = self.tensors.to(*args, **kwargs)
+        m = self.mask.to(*args, **kwargs) if self.mask is not None else None
+        return type(self)(t, m)
+
+    def decompose(self):
+        return self.tensors, self.mask
+
+    @classmethod
+    def from_tensor_list(cls, tensor_list: List[Tensor], do_round: bool = False) -> "NestedTensor":
+        """Pads every [C, h, w] image to the largest h / w of the list (optionally rounded up to a multiple of 128)."""
+        if tensor_list[0].ndim != 3:
+            raise ValueError("not supported")
+        c = tensor_list[0].shape[0]
+        h = max(int(t.shape[1]) for t in tensor_list)
+        w = max(int(t.shape[2]) for t in tensor_list)
+        if do_round:
+            h = (h + 127) // 128 * 128
+            w = (w + 127) // 128 * 128
+        b = len(tensor_list)
+        dtype, device = tensor_list[0].dtype, tensor_list[0].device
+        tensor = torch.zeros((b, c, h, w), dtype=dtype, device=device)
+        mask = torch.ones((b, h, w), dtype=torch.bool, device=device)
+        for i, img in enumerate(tensor_list):
+            tensor[i, :, : img.shape[1], : img.shape[2]].copy_(img)
+            mask[i, : img.shape[1], : img.shape[2]] = False
+        return cls(tensor, mask)
+
+    def __repr__(self) -> str:
+        return repr(self.tensors)
