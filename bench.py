@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of one TOIST training step (phase A + phase B + criterion + backward, + gradient
+all-reduce when N > 1) on synthetic 3x640x640 images with 16-token captions, bs = 8 per GPU, ResNet-101.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # our sm_100a path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # the reference algorithm on the host CPU cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "images/sec (640^2, bs=8/GPU) training step"
+UNIT = "images/s"
+WORKLOAD = ("ResNet-101 TOIST detection, bs=8/GPU, 3x640x640 synthetic + 16-token captions, "
+            "phase A + phase B + SetCriterion(6 layers) + backward")
+BATCH, SIZE, TOKENS = 8, 640, 16
+# algorithmic FLOPs of the attention core per step at B=8 (fwd 11.04 GF, fwd+bwd 38.6 GF)
+STEP_FLOPS_PER_IMAGE = (141.1 + 256.5) * 1e9
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML every 100 ms while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            }
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = get(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ kernel profiler
+class GemmProfiler:
+    """CUDA-event pair around every tensor-core launch of one instrumented step (after the timed region)."""
+
+    def __init__(self):
+        self.rec = []
+
+    @contextlib.contextmanager
+    def record(self, tag, flops):
+        import torch
+
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.rec.append((tag, flops, a, b))
+
+    def summary(self):
+        agg = {}
+        for tag, flops, a, b in self.rec:
+            t = agg.setdefault(tag, [0.0, 0.0, 0])
+            t[0] += flops
+            t[1] += a.elapsed_time(b) * 1e-3
+            t[2] += 1
+        return agg
+
+
+# ------------------------------------------------------------------------------------------------ oracle on the CPU
+def cpu_training_step_rate(batch: int, steps: int, warmup: int, threads: int):
+    """The reference algorithm (oracle/model.py, the fp32 torch restatement validated against the unmodified
+    reference) timed on the host: forward, criterion, weighted sum, backward.  Returns (images/s, seconds/step)."""
+    import torch
+
+    from oracle import model as O
+    from toist_b200.models import build_model
+    from toist_b200.synth import make_args, make_batch
+
+    torch.set_num_threads(threads)
+    args = make_args("resnet101", device="cpu")
+    torch.manual_seed(0)
+    model, _, _, weight_dict = build_model(args)  # parameter containers only: construction is plain torch on the CPU
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            sd[n] = p.detach().clone().requires_grad_(True)
+    images, mask, captions, targets, pm = make_batch(batch, SIZE, TOKENS, seed=1234)
+    tokd = model.transformer.tokenizer(captions)
+    cfg = O.Config(backbone="resnet101")
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        mc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+        out = O.decode(sd, cfg, mc)
+        losses, _ = O.criterion(cfg, out, tokd, targets, pm)
+        total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+        total.backward()
+        for v in sd.values():
+            v.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_batch = 2
+    rate, sec = cpu_training_step_rate(sample_batch, a.steps, a.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample_batch} of the 8 images per step"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{a.steps} steps of {sample_batch} images (R101, 640^2, 16 tokens), fp32 torch CPU"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from toist_b200 import kernels as K
+    from toist_b200.models import build_model
+    from toist_b200.synth import make_args, make_batch, targets_to
+    from toist_b200.util.misc import NestedTensor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args = make_args("resnet101", device="cuda", dropout=0.0)
+    torch.manual_seed(0)
+    model, criterion, _, weight_dict = build_model(args)
+    model.to(dev).train()
+    ddp = None
+    if world > 1:
+        # the reference wraps the model exactly like this (main.py:336); gradients are all-reduced in buckets over NCCL
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    net = ddp if ddp is not None else model
+
+    images, mask, captions, targets, pm = make_batch(BATCH, SIZE, TOKENS, seed=1234 + rank)
+    h_images = images.pin_memory()
+    h_mask = mask.pin_memory()
+    h_pm = pm.pin_memory()
+    d_samples = NestedTensor(images.to(dev), mask.to(dev))
+    d_targets = targets_to(targets, dev)
+    d_pm = pm.to(dev)
+    flush = torch.empty(80 * 1024 * 1024, dtype=torch.float32, device=dev)  # 320 MB > 126 MB L2
+
+    def step(samples, tg, pmap):
+        model.zero_grad(set_to_none=True)
+        mc = net(samples, captions, encode_and_save=True)
+        out = net(samples, captions, encode_and_save=False, memory_cache=mc)
+        losses = criterion(mc, out, tg, pmap, None)
+        total = sum(losses[k] * weight_dict[k] for k in losses.keys() if k in weight_dict)
+        total.backward()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            flush.zero_()
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident inputs
+    for _ in range(a.warmup):
+        step(d_samples, d_targets, d_pm)
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = K.launches()
+    ms = timed(lambda: step(d_samples, d_targets, d_pm), a.steps)
+    launches = (K.launches() - n0) // a.steps
+    clocks = sampler.stop()
+    value = world * BATCH * a.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers in, loss scalar out, every step
+    def e2e_step():
+        s = NestedTensor(h_images.to(dev, non_blocking=True), h_mask.to(dev, non_blocking=True))
+        tg = targets_to(targets, dev)
+        total = step(s, tg, h_pm.to(dev, non_blocking=True))
+        return float(total.item())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    h2d = h_images.numel() * 4 + h_mask.numel() + h_pm.numel() * 4 + sum(t["boxes"].numel() * 4 + t["labels"].numel() * 8
+                                                                            for t in targets)
+    e2e = {"value": world * BATCH * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": 4}
+
+    # ---- one instrumented step: CUDA events around every tensor-core launch (gemm_kernel family)
+    peaks = _peaks()
+    roof = attn = None
+    if rank == 0:
+        prof = GemmProfiler()
+        K.set_gemm_profiler(prof)
+        step(d_samples, d_targets, d_pm)
+        torch.cuda.synchronize()
+        K.set_gemm_profiler(None)
+        agg = prof.summary()
+        fl = sum(v[0] for v in agg.values())
+        tm = sum(v[1] for v in agg.values())
+        nl = sum(v[2] for v in agg.values())
+        roof = {"bound": "tensor", "kernel": "toist::gemm_kernel (all modes, all layers)", "achieved": fl / tm / 1e12,
+                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": fl / tm / 1e12 / peaks["tf_sustained"],
+                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)", "launches": nl,
+                "flops_per_step": fl, "kernel_seconds_per_step": tm, "share_of_step": tm / (ms * 1e-3 / a.steps)}
+        if "attn_core" in agg:
+            f, t, n = agg["attn_core"]
+            attn = {"kernels": "QK^T / softmax / PV and their backward (enc-self, dec-self, dec-cross, RoBERTa)",
+                    "achieved": f / t / 1e12, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": f / t / 1e12 / peaks["tf_sustained"], "flops_per_step": f, "seconds_per_step": t,
+                    "launches": n}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sec = cpu_training_step_rate(2, 2, 1, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "2 timed steps (+1 warm-up) of 2 images (R101, 640^2, 16 tokens), fp32 torch CPU, "
+                         f"{sec:.2f} s/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": 0.0,
+                       "l2": "320 MB buffer rewritten between steps (> 126 MB L2)",
+                       "parallelism": f"dp{world}" + (" (DDP bucketed NCCL all-reduce)" if world > 1 else "")},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * a.steps,
+            "gpu_launches_per_step": int(launches), "roofline": roof, "attention_roofline": attn,
+            "step_tensor_frac": STEP_FLOPS_PER_IMAGE * BATCH / (ms * 1e-3 / a.steps) / 1e12 / peaks["tf_sustained"],
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

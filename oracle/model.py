@@ -568,11 +568,15 @@ def loss_masks(pred_masks: Tensor, targets, indices, num_boxes: float) -> Tuple[
 
 
 def criterion(cfg: Config, out: dict, tokenized, targets, positive_map: Tensor, world_size: int = 1,
-              num_boxes: Optional[float] = None, masks: bool = False) -> Tuple[Dict[str, Tensor], list]:
-    """models/mdetr.py:990-1021 (single-model branch). Returns (losses, indices of every decoder layer)."""
-    def one(o, suffix, with_masks):
-        idx = hungarian_match(o["pred_logits"], o["pred_boxes"], targets, positive_map, cfg.set_cost_class,
-                              cfg.set_cost_bbox, cfg.set_cost_giou)
+              num_boxes: Optional[float] = None, masks: bool = False,
+              forced_indices: Optional[list] = None) -> Tuple[Dict[str, Tensor], list]:
+    """models/mdetr.py:990-1021 (single-model branch). Returns (losses, indices of every decoder layer), ordered
+    [main, aux_0, aux_1, ...].  `forced_indices` (same order) replaces the matcher: used by gradient-parity tests so
+    that both implementations differentiate the same assignment when near-tie costs would otherwise flip it."""
+    def one(o, suffix, with_masks, forced=None):
+        idx = forced if forced is not None else hungarian_match(
+            o["pred_logits"], o["pred_boxes"], targets, positive_map, cfg.set_cost_class, cfg.set_cost_bbox,
+            cfg.set_cost_giou)
         res = {"loss_ce" + suffix: loss_labels(o["pred_logits"], targets, positive_map, idx, nb, cfg.eos_coef)}
         l1, gi = loss_boxes(o["pred_boxes"], targets, idx, nb)
         res["loss_bbox" + suffix], res["loss_giou" + suffix] = l1, gi
@@ -588,10 +592,10 @@ def criterion(cfg: Config, out: dict, tokenized, targets, positive_map: Tensor, 
     nb = num_boxes
     if nb is None:
         nb = max(float(sum(len(t["labels"]) for t in targets)) / world_size, 1.0)
-    losses, idx = one(out, "", masks)
+    losses, idx = one(out, "", masks, forced_indices[0] if forced_indices else None)
     all_idx = [idx]
     for i, aux in enumerate(out.get("aux_outputs", [])):
-        l, idx_i = one(aux, f"_{i}", False)
+        l, idx_i = one(aux, f"_{i}", False, forced_indices[i + 1] if forced_indices else None)
         losses.update(l)
         all_idx.append(idx_i)
     return losses, all_idx

@@ -1,0 +1,158 @@
+"""CPU suite: pins the oracle to the golden vectors frozen from the unmodified reference (tools/make_golden.py),
+checks the host-side logic, and that libtoist_b200.so loads and exports the whole C ABI (no GPU compute here)."""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import max_err, rel_err
+from oracle import model as O
+from toist_b200.synth import make_args, make_batch
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def matcher_gold():
+    return torch.load(GOLD / "matcher_cases.pt", weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def config1_gold():
+    return torch.load(GOLD / "config1_r50.pt", weights_only=False)
+
+
+def test_oracle_matcher_reproduces_reference_goldens(matcher_gold):
+    for c in matcher_gold["cases"]:
+        targets = [{"boxes": b} for b in c["tgt_boxes"]]
+        tgt = torch.cat(c["tgt_boxes"])
+        cost = O.matcher_cost(c["logits"], c["boxes"], tgt, c["positive_map"], 1.0, 5.0, 2.0)
+        assert max_err(cost, c["cost"]) < 1e-6
+        idx = O.hungarian_match(c["logits"], c["boxes"], targets, c["positive_map"], 1.0, 5.0, 2.0)
+        for (r0, c0), (r1, c1) in zip(idx, c["indices"]):
+            assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist()
+
+
+def test_oracle_model_reproduces_reference_golden(config1_gold):
+    """Our parameter containers initialise bit-identically to the reference under the same seed, and the oracle run on
+    those weights reproduces the reference's forward, losses and assignments (BASELINE config 1)."""
+    from toist_b200.models import build_model
+
+    g = config1_gold
+    torch.set_num_threads(max(torch.get_num_threads(), 4))
+    torch.manual_seed(0)
+    model, _, _, weight_dict = build_model(make_args("resnet50", device="cpu"))
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    assert set(sd) == set(g["state_checksum"])
+    for k, v in g["state_checksum"].items():
+        assert abs(float(sd[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), k
+    assert dict(weight_dict) == g["weight_dict"]
+    b = g["batch"]
+    images, mask, captions, targets, pm = make_batch(b["batch"], b["size"], b["tokens"], seed=b["seed"], pad=b["pad"])
+    tokd = model.transformer.tokenizer(captions)
+    cfg = O.Config(backbone="resnet50")
+    with torch.no_grad():
+        mc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+        out = O.decode(sd, cfg, mc)
+        losses, idx = O.criterion(cfg, out, tokd, targets, pm)
+    assert torch.equal(mc["mask"], g["mask"])
+    assert rel_err(mc["img_memory"], g["img_memory"].float()) < 1e-3  # golden stored in fp16
+    assert rel_err(mc["pos_embed"][:, 0], g["pos_embed_row0"]) < 1e-6
+    layers = list(out["aux_outputs"]) + [out]
+    for k in ("pred_logits", "pred_boxes", "proj_queries"):
+        assert rel_err(torch.stack([o[k] for o in layers]), g[k]) < 1e-4, k
+    assert rel_err(out["proj_tokens"], g["proj_tokens"]) < 1e-4
+    assert set(losses) == set(g["losses"])
+    for k, v in g["losses"].items():
+        assert abs(float(losses[k]) - v) <= 2e-4 * max(1.0, abs(v)), k
+    oidx = idx[1:] + idx[:1]
+    for l, layer in enumerate(g["indices"]):
+        for (r0, c0), (r1, c1) in zip(oidx[l], layer):
+            assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist(), l
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    from toist_b200 import _lib
+
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    lib = _lib.load()
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert lib.toist_abi_version() == 1
+    assert lib.toist_sizeof_gemm_desc() == ctypes.sizeof(_lib.GemmDesc)
+    assert isinstance(lib.toist_last_error(), bytes)
+
+
+def test_host_lsap_matches_scipy_and_oracle():
+    """toist_lsap_f64 is host code (C++), so it runs here: identical to scipy (the reference's solver) and the oracle."""
+    from scipy.optimize import linear_sum_assignment
+
+    from toist_b200 import kernels as K
+
+    rng = np.random.RandomState(0)
+    for nr, nc in [(100, 4), (4, 100), (97, 97), (1, 1), (5, 0), (0, 5), (30, 1024), (100, 1), (3, 3)]:
+        for trial in range(3):
+            c = rng.rand(nr, nc)
+            if trial == 1 and c.size:
+                c = np.round(c * 4) / 4
+            if trial == 2 and c.size:
+                c = np.zeros((nr, nc))
+            r0, c0 = linear_sum_assignment(c)
+            r1, c1 = K.lsap_host(c)
+            assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist(), (nr, nc, trial)
+            if nr * nc <= 400:
+                r2, c2 = O.lsap(c)
+                assert r0.tolist() == r2.tolist() and c0.tolist() == c2.tolist()
+    with pytest.raises(ValueError):
+        K.lsap_host(np.array([[np.nan, 1.0], [1.0, 2.0]]))
+    with pytest.raises(ValueError):
+        K.lsap_host(np.array([[np.inf, np.inf], [np.inf, np.inf]]))
+    with pytest.raises(ValueError):
+        K.lsap_host(np.array([[-np.inf, 1.0]]))
+
+
+def test_target_packing_and_token_spans_host_logic():
+    from toist_b200.models.matcher import indices_from_match, pack_targets
+    from toist_b200.models.mdetr import build_token_positive
+    from toist_b200.tokenizer import CharTokenizer
+
+    _, _, captions, targets, pm = make_batch(5, 32, 8, seed=3)
+    p = pack_targets(targets, pm, "cpu")
+    assert p.counts == (1, 2, 3, 4, 1) and p.t_max == 4
+    off = 0
+    for b, n in enumerate(p.counts):
+        assert torch.equal(p.boxes[b, :n], targets[b]["boxes"])
+        assert torch.equal(p.posmap[b, :n], pm[off:off + n])
+        assert bool((p.boxes[b, n:] == 0).all()) and bool((p.posmap[b, n:] == 0).all())
+        off += n
+    assert p.count.tolist() == list(p.counts)
+    tok = CharTokenizer()(captions)
+    tp = build_token_positive(tok, targets, p.t_max, 8)
+    for b, n in enumerate(p.counts):
+        assert bool((tp[b, :n, 1:7] == 1).all()) and bool((tp[b, :n, 0] == 0).all()) and bool((tp[b, :n, 7] == 0).all())
+        assert bool((tp[b, n:] == 0).all())
+    mq = torch.tensor([[5, -1, -1, -1], [9, 2, -1, -1]], dtype=torch.int32)
+    idx = indices_from_match(mq, (1, 2))
+    assert idx[0][0].tolist() == [5] and idx[0][1].tolist() == [0]
+    assert idx[1][0].tolist() == [2, 9] and idx[1][1].tolist() == [1, 0]
+
+
+def test_no_cpu_fallback_in_product_path():
+    """The product path must fail loudly without a CUDA device instead of silently computing on the CPU."""
+    from toist_b200.models import build_model
+    from toist_b200.util.misc import NestedTensor
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    model, criterion, _, _ = build_model(make_args("resnet50", device="cpu"))
+    model.eval()
+    images, mask, captions, targets, pm = make_batch(1, 64, 8)
+    with pytest.raises(RuntimeError):
+        model(NestedTensor(images, mask), captions, encode_and_save=True)
+    with pytest.raises(RuntimeError):
+        criterion({}, {"pred_logits": torch.zeros(1, 100, 256), "pred_boxes": torch.zeros(1, 100, 4)}, targets, pm, None)

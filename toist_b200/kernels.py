@@ -19,6 +19,40 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32, GEMM_DG
                    Tap, Tensor4)
 
 _launch_count = 0
+_gemm_profiler = None  # bench.py installs an object with .record(tag, flops) -> context manager around the launch
+_gemm_tag = "gemm"
+
+
+def set_gemm_profiler(p) -> None:
+    global _gemm_profiler
+    _gemm_profiler = p
+
+
+class _NoProf:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _prof(tag: str, flops: float = 0.0):
+    return _NoProf() if _gemm_profiler is None else _gemm_profiler.record(tag, flops)
+
+
+class gemm_tag:
+    """`with gemm_tag("attn_core"):` labels the GEMM launches issued inside (used for the per-family roofline)."""
+
+    def __init__(self, tag: str):
+        self.tag = tag
+
+    def __enter__(self):
+        global _gemm_tag
+        self.prev, _gemm_tag = _gemm_tag, self.tag
+
+    def __exit__(self, *exc):
+        global _gemm_tag
+        _gemm_tag = self.prev
 
 
 def launches() -> int:
@@ -125,7 +159,16 @@ def gemm(mode: int, a: Tensor4, b: Tensor4, out: torch.Tensor, *, ext: Tuple[int
         d.aux = aux.data_ptr() + 2 * out_offset
     d.act = act
     d.accumulate = 1 if accumulate else 0
-    _lib.check(_lib.load().toist_gemm(C.byref(d), _stream()))
+    if _gemm_profiler is None:
+        _lib.check(_lib.load().toist_gemm(C.byref(d), _stream()))
+    else:
+        pix = ext[0] * ext[1] * ext[2]
+        if mode == GEMM_WGRAD:
+            flops = 2.0 * m_rows * n_cols * len(taps) * pix * batch[0] * batch[1]
+        else:
+            flops = 2.0 * pix * n_cols * k_per_tap * len(taps)
+        with _gemm_profiler.record(_gemm_tag, flops):
+            _lib.check(_lib.load().toist_gemm(C.byref(d), _stream()))
     _count()
 
 
@@ -535,12 +578,18 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8
     ld = _ld8(sk)
     dev = q.device
     scores = torch.empty((b, nhead, sq, ld), dtype=torch.float32, device=dev)
+    with gemm_tag("attn_core"):
+        return _attention_fwd(q, k, v, key_mask_u8, nhead, need_probs, ctx, scores, sq, sk, b, e, d, ld, dev)
+
+
+def _attention_fwd(q, k, v, key_mask_u8, nhead, need_probs, ctx, scores, sq, sk, b, e, d, ld, dev):
     gemm(GEMM_FWD, t4(q, (d, sq, nhead, b), (1, q.stride(0), d, q.stride(1))),
          t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), scores, ext=(sq, nhead, b), tile=(128, 1, 1),
          n_cols=sk, out_strides=(ld, sq * ld, nhead * sq * ld), k_per_tap=d, b_batched=True, alpha=float(d) ** -0.5)
     probs = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=dev)
-    _ck(_L().toist_attn_softmax_fwd(scores.data_ptr(), _ptr(key_mask_u8), probs.data_ptr(), b * nhead * sq, sk, ld, ld,
-                                    nhead * sq, _stream()))
+    with _prof("attn_core"):
+        _ck(_L().toist_attn_softmax_fwd(scores.data_ptr(), _ptr(key_mask_u8), probs.data_ptr(), b * nhead * sq, sk, ld,
+                                        ld, nhead * sq, _stream()))
     if ctx is None:
         ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=dev)
     assert ctx.shape == (sq, b, e) and ctx.stride(2) == 1
@@ -554,6 +603,11 @@ def attention_bwd(dctx: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch
                   nhead: int, dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor) -> None:
     """Backward of attention_fwd.  dq/dk/dv are bf16 outputs with the same [S, B, E] indexing as q/k/v (they may be
     column slices of one packed gradient buffer)."""
+    with gemm_tag("attn_core"):
+        _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv)
+
+
+def _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv) -> None:
     sq, b, e = q.shape
     sk = k.shape[0]
     d = e // nhead
@@ -570,8 +624,9 @@ def attention_bwd(dctx: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch
          t4(v, (d, sk, nhead, b), (1, v.stride(0), d, v.stride(1))), dp, ext=(sq, nhead, b), tile=(128, 1, 1),
          n_cols=sk, out_strides=(ld, sq * ld, nhead * sq * ld), k_per_tap=d, b_batched=True)
     ds = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=dev)
-    _ck(_L().toist_attn_softmax_bwd(dp.data_ptr(), probs.data_ptr(), ds.data_ptr(), b * nhead * sq, sk, ld, ld,
-                                    float(d) ** -0.5, _stream()))
+    with _prof("attn_core"):
+        _ck(_L().toist_attn_softmax_bwd(dp.data_ptr(), probs.data_ptr(), ds.data_ptr(), b * nhead * sq, sk, ld, ld,
+                                        float(d) ** -0.5, _stream()))
     # dQ = dS K   (DGRAD mode: B = K is MN-major, reduction over keys)
     gemm(GEMM_DGRAD, t4(ds, (sk, sq, nhead, b), sP), t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), dq,
          ext=(sq, nhead, b), tile=(128, 1, 1), n_cols=d, out_strides=(dq.stride(0), d, dq.stride(1)), k_per_tap=sk,

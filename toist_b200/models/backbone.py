@@ -43,6 +43,8 @@ class ConvWeight(nn.Module):
         super().__init__()
         self.stride = stride
         self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+
+    def reset_parameters(self) -> None:
         nn.init.kaiming_normal_(self.weight, mode="fan_out", nonlinearity="relu")
 
 
@@ -83,6 +85,22 @@ class ResNetBody(nn.Module):
             layer += [Bottleneck(inplanes, planes, 1, False) for _ in range(1, n)]
             setattr(self, f"layer{li}", nn.Sequential(*layer))
 
+    def reset_parameters(self) -> None:
+        """Same random stream as the reference's `torchvision.models.resnetNN(norm_layer=FrozenBatchNorm2d)`
+        (models/backbone.py:87): torchvision draws the default Conv2d / fc initialisations first and then re-draws every
+        convolution with kaiming-normal, so the simplest way to consume the generator identically is to let
+        torchvision construct a throw-away copy and take its values.  Falls back to plain kaiming-normal."""
+        try:
+            import torchvision
+
+            tv = getattr(torchvision.models, self.arch)(weights=None, norm_layer=FrozenBatchNorm2d)
+            sd = {k: v for k, v in tv.state_dict().items() if not k.startswith("fc.")}
+            self.load_state_dict(sd, strict=True)
+        except ImportError:  # pragma: no cover
+            for m in self.modules():
+                if isinstance(m, ConvWeight):
+                    m.reset_parameters()
+
     def conv_bn_pairs(self) -> List[Tuple[str, str]]:
         pairs = [("conv1", "bn1")]
         for li, n in enumerate(self.blocks, start=1):
@@ -102,6 +120,7 @@ class Backbone(nn.Module):
         if dilation:
             raise NotImplementedError("dilation (DC5) is outside the TOIST hot path (main.py:99-103 default False)")
         self.body = ResNetBody(name)
+        self.body.reset_parameters()
         for pname, p in self.body.named_parameters():
             if not train_backbone or ("layer2" not in pname and "layer3" not in pname and "layer4" not in pname):
                 p.requires_grad_(False)
