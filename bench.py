@@ -189,6 +189,9 @@ def run_ours(a):
     torch.manual_seed(0)
     model, criterion, _, weight_dict = build_model(args)
     model.to(dev).train()
+    if not a.no_graphs:  # replay each stage's launch sequence as a CUDA graph (same public API, fixed shapes)
+        model.enable_cuda_graphs(True)
+        criterion.enable_cuda_graphs(True)
     ddp = None
     if world > 1:
         # the reference wraps the model exactly like this (main.py:336); gradients are all-reduced in buckets over NCCL
@@ -261,6 +264,8 @@ def run_ours(a):
     peaks = _peaks()
     roof = attn = None
     if rank == 0:
+        model.enable_cuda_graphs(False)  # per-launch events need the eager launch sequence
+        criterion.enable_cuda_graphs(False)
         prof = GemmProfiler()
         K.set_gemm_profiler(prof)
         step(d_samples, d_targets, d_pm)
@@ -295,6 +300,7 @@ def run_ours(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": 0.0,
+                       "cuda_graphs": not a.no_graphs,
                        "l2": "320 MB buffer rewritten between steps (> 126 MB L2)",
                        "parallelism": f"dp{world}" + (" (DDP bucketed NCCL all-reduce)" if world > 1 else "")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * a.steps,
@@ -314,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="issue every kernel launch from Python (no CUDA graphs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
     if a.impl == "reference":

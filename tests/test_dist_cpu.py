@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU) of the host-side multi-rank logic: the global num_boxes normalisation of the
+criterion (reference models/mdetr.py:997-1001), per-rank synthetic shards, and the bench reference arm on rank != 0."""
+from __future__ import annotations
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank: int, world: int, port: int, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from toist_b200.models.matcher import HungarianMatcher
+    from toist_b200.models.mdetr import SetCriterion
+    from toist_b200.synth import make_args, make_batch
+
+    crit = SetCriterion(make_args(), 255, HungarianMatcher(1, 5, 2), 0.1, ["labels", "boxes", "cardinality"], 0.07, 64)
+    # rank 0 has 3 images (1 + 2 + 3 boxes), rank 1 has 1 image (1 box): global mean (6 + 1) / 2 = 3.5
+    _, _, _, targets, _ = make_batch(3 if rank == 0 else 1, 32, 8, seed=1234 + rank)
+    nb = crit.num_boxes_tensor(targets, "cpu")
+    # an all-empty step clamps to 1 (models/mdetr.py:1001)
+    nb0 = crit.num_boxes_tensor([{"labels": torch.zeros(0)}], "cpu")
+    # different ranks draw different synthetic shards
+    img = make_batch(1, 8, 8, seed=1234 + rank)[0]
+    gathered = [torch.zeros_like(img) for _ in range(world)]
+    dist.all_gather(gathered, img)
+    import argparse
+
+    import bench
+
+    out = bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=1)) if rank != 0 else "skipped-on-rank0"
+    q.put((rank, float(nb), float(nb0), bool(torch.equal(gathered[0], gathered[1])), out))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_host_logic():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, nb, nb0, same_shard, ref in res:
+        assert nb == 3.5
+        assert nb0 == 1.0
+        assert not same_shard
+    assert res[1][4] is None  # the reference arm does no work on rank != 0

@@ -25,7 +25,10 @@ def test_forward_within_bf16_budget(rows):
 
 def test_losses_close(rows):
     for k, v in rows.items():
-        if k.startswith("loss:"):
+        if k.startswith("loss:cardinality"):
+            # an argmax count over 100 queries: at random init the logits are near-ties, a handful flip under bf16
+            assert v < 0.1, (k, v)
+        elif k.startswith("loss:"):
             assert v < 2e-2, (k, v)
 
 
@@ -91,3 +94,41 @@ def test_training_mode_dropout_is_reported_not_silently_skipped():
     images, mask, captions, _, _ = make_batch(1, 64, 8)
     with pytest.raises(NotImplementedError):
         model(NestedTensor(images.cuda(), mask.cuda()), captions, encode_and_save=True)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The graph-captured stages reproduce the eager launch sequence bit for bit, step after step."""
+    from toist_b200.models import build_model
+    from toist_b200.synth import make_args, make_batch, targets_to
+    from toist_b200.util.misc import NestedTensor
+
+    torch.manual_seed(0)
+    model, criterion, _, wd = build_model(make_args("resnet50"))
+    model.cuda().train()
+    batches = [make_batch(2, 160, 8, seed=s) for s in (5, 6, 7)]
+
+    def step(b):
+        images, mask, captions, targets, pm = b
+        s = NestedTensor(images.cuda(), mask.cuda())
+        model.zero_grad(set_to_none=True)
+        mc = model(s, captions, encode_and_save=True)
+        out = model(s, captions, encode_and_save=False, memory_cache=mc)
+        losses = criterion(mc, out, targets_to(targets, "cuda"), pm.cuda(), None)
+        total = sum(losses[k] * wd[k] for k in losses if k in wd)
+        total.backward()
+        grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        return float(total), out["pred_logits"].clone(), grads
+
+    eager = [step(b) for b in batches]
+    model.enable_cuda_graphs(True)
+    criterion.enable_cuda_graphs(True)
+    graphed = [step(b) for b in batches]  # first call captures, later calls replay
+    graphed2 = [step(b) for b in batches]
+    for (t0, l0, g0), (t1, l1, g1), (t2, l2, g2) in zip(eager, graphed, graphed2):
+        assert t0 == t1 == t2
+        assert torch.equal(l0, l1) and torch.equal(l0, l2)
+        assert set(g0) == set(g1) == set(g2)
+        for k in g0:
+            # split-K weight gradients accumulate with fp32 atomics: order may differ between runs
+            assert torch.allclose(g0[k], g1[k], rtol=1e-3, atol=1e-6 * float(g0[k].abs().max() + 1e-30)), k
+            assert torch.allclose(g0[k], g2[k], rtol=1e-3, atol=1e-6 * float(g0[k].abs().max() + 1e-30)), k

@@ -178,6 +178,38 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
   if (threadIdx.y == 0 && c < C) atomicAdd(out + c, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
+// Vectorised variant for bf16 with 16-byte aligned rows: a warp covers 256 consecutive columns (8 per lane, one 16-byte
+// load each), the 8 warps of a block take interleaved rows, partial sums meet in shared memory.
+__global__ void colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long R, int C,
+                                       long long ld, int rows_per_block) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (c0 < C) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ld + c0));
+      const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+      acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y;
+      acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+    }
+  }
+  __shared__ float red[8][256 + 8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[warp][lane * 8 + k] = acc[k];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ activation grads
 // dpre = dy * gelu'(pre)   (erf GELU), bf16
 __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
@@ -377,6 +409,18 @@ int toist_maxpool3x3s2(const void* x, void* y, int32_t n, int32_t h, int32_t w, 
 int toist_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t cols, int64_t ld, void* stream) {
   TOIST_REQUIRE(x && out, "toist_colsum: null pointer");
   if (rows == 0) return TOIST_OK;
+  if (dtype == TOIST_BF16 && cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int col_blocks = (cols + 255) / 256;
+    int chunks = (int)((rows + 63) / 64);               // at least 64 rows per block
+    const int want = (592 + col_blocks - 1) / col_blocks;  // ~4 blocks per SM in total
+    if (chunks > want) chunks = want;
+    if (chunks < 1) chunks = 1;
+    const int rpb = (int)((rows + chunks - 1) / chunks);
+    dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb));
+    colsum_bf16_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
+    TOIST_CHECK_CUDA(cudaGetLastError());
+    return TOIST_OK;
+  }
   int chunks = (int)((rows + 511) / 512);
   if (chunks > 256) chunks = 256;
   const int rpb = (int)((rows + chunks - 1) / chunks);

@@ -40,7 +40,9 @@ struct GemmKParams {
   void* aux;
   int act;
   int accumulate;
-  int vec_ok;  // 1: every row base and column tile is 16-byte aligned for all epilogue pointers
+  int vec_ok;   // 1: every row base and column tile is 16-byte aligned for all epilogue pointers
+  int stages;   // depth of the TMA -> MMA shared-memory ring
+  int tma_epi;  // 1: bf16 epilogue through shared memory: res / mask tiles by TMA load, output by TMA store
   toist_tap taps[TOIST_MAX_TAPS];
 };
 
@@ -51,10 +53,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BN, int STAGES, int MODE>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ GemmKParams p) {
+            const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
+            const __grid_constant__ CUtensorMap tma_mask, const __grid_constant__ GemmKParams p) {
+  const int STAGES = p.stages;
   constexpr int kBBytes = BN * 128;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr bool kAMN = (MODE == TOIST_GEMM_WGRAD);
@@ -66,7 +70,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* epi_bar = accum_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,6 +119,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
+    mbar_init(epi_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -225,6 +231,107 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (n_iters > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
+    }
+    if constexpr (MODE != TOIST_GEMM_WGRAD) {
+      if (p.tma_epi) {
+        // ---- bf16 epilogue staged through shared memory.  The accumulator barrier implies that every MMA has
+        // retired, so the operand ring is idle and is reused: [out | res | mask], each BN/64 slabs of 128 rows x 128 B
+        // in the SWIZZLE_128B layout (16-byte chunk index XOR row % 8), which makes the per-row accesses of the 128
+        // epilogue threads bank-conflict free and lets TMA move whole tiles with full-line transactions.
+        const bool has_res = p.res != nullptr, has_mask = p.mask != nullptr;
+        uint8_t* st_out = smem;
+        uint8_t* st_res = smem + BN * 256;
+        uint8_t* st_mask = st_res + (has_res ? BN * 256 : 0);
+        const bool leader = (warp == 2 && lane == 0);
+        if (has_res || has_mask) {
+          if (leader) {
+            mbar_expect_tx(epi_bar, (uint32_t)((has_res ? 1 : 0) + (has_mask ? 1 : 0)) * BN * 256);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              if (has_res) tma_load_4d(st_res + j * 16384, &tma_res, epi_bar, n0 + j * 64, x0, y0, i0);
+              if (has_mask) tma_load_4d(st_mask + j * 16384, &tma_mask, epi_bar, n0 + j * 64, x0, y0, i0);
+            }
+          }
+          mbar_wait(epi_bar, 0);
+        }
+        const uint32_t rx = (uint32_t)(r & 7);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.n_cols) break;  // warp-uniform
+          uint32_t raw[32];
+          if (n_iters > 0) {
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = 0u;
+          }
+          const int ncol = n0 + c0;
+          const int nvalid = min(32, p.n_cols - ncol);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+          if (p.col_scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) v[i] *= __ldg(p.col_scale + ncol + i);
+          }
+          if (p.col_shift != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) v[i] += __ldg(p.col_shift + ncol + i);
+          }
+          const uint32_t row_base = (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
+          const uint32_t cb = (uint32_t)(c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group (0 or 4)
+          if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 u = *reinterpret_cast<const uint4*>(st_res + row_base + (((cb + g) ^ rx) << 4));
+              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+              v[g * 8 + 0] += f0.x; v[g * 8 + 1] += f0.y; v[g * 8 + 2] += f1.x; v[g * 8 + 3] += f1.y;
+              v[g * 8 + 4] += f2.x; v[g * 8 + 5] += f2.y; v[g * 8 + 6] += f3.x; v[g * 8 + 7] += f3.y;
+            }
+          }
+          if (has_mask) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 u = *reinterpret_cast<const uint4*>(st_mask + row_base + (((cb + g) ^ rx) << 4));
+              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+              if (!(f0.x > 0.f)) v[g * 8 + 0] = 0.f;
+              if (!(f0.y > 0.f)) v[g * 8 + 1] = 0.f;
+              if (!(f1.x > 0.f)) v[g * 8 + 2] = 0.f;
+              if (!(f1.y > 0.f)) v[g * 8 + 3] = 0.f;
+              if (!(f2.x > 0.f)) v[g * 8 + 4] = 0.f;
+              if (!(f2.y > 0.f)) v[g * 8 + 5] = 0.f;
+              if (!(f3.x > 0.f)) v[g * 8 + 6] = 0.f;
+              if (!(f3.y > 0.f)) v[g * 8 + 7] = 0.f;
+            }
+          }
+          if (p.act != TOIST_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+            u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+            u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(st_out + row_base + (((cb + g) ^ rx) << 4)) = u;
+          }
+        }
+        fence_proxy_async();          // generic-proxy writes above -> visible to the TMA (async proxy) reads below
+        named_barrier_sync(1, 128);   // the four epilogue warps
+        if (leader) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            if (n0 + j * 64 < p.n_cols) tma_store_4d(&tma_out, st_out + j * 16384, n0 + j * 64, x0, y0, i0);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        goto epilogue_done;
+      }
     }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -370,6 +477,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   }
 
+epilogue_done:
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
@@ -379,28 +487,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
 }
 
-template <int BN, int STAGES, int MODE>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKParams& kp, dim3 grid,
-                       cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+template <int BN, int MODE>
+static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
+  constexpr int kMaxStages = (BN == 128) ? 3 : 4;
+  constexpr int max_smem = kMaxStages * (kABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int smem = kp.stages * (kABytes + BN * 128) + 1024 + 256;
   static bool configured = false;
-  auto kfn = gemm_kernel<BN, STAGES, MODE>;
+  auto kfn = gemm_kernel<BN, MODE>;
   if (!configured) {
-    TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
-  kfn<<<grid, kThreads, smem, stream>>>(ma, mb, kp);
+  kfn<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
 
 template <int MODE>
-static int dispatch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmKParams& kp, dim3 grid,
-                       cudaStream_t stream) {
+static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 grid, cudaStream_t stream) {
+  // ring depth: 2 CTAs per SM for BN <= 128 (one tile's epilogue overlaps the other's main loop)
   switch (bn) {
-    case 256: return launch_gemm<256, 4, MODE>(ma, mb, kp, grid, stream);
-    case 128: return launch_gemm<128, 3, MODE>(ma, mb, kp, grid, stream);
-    default:  return launch_gemm<64, 4, MODE>(ma, mb, kp, grid, stream);
+    case 256: kp.stages = 4; return launch_gemm<256, MODE>(maps, kp, grid, stream);
+    case 128: kp.stages = 3; return launch_gemm<128, MODE>(maps, kp, grid, stream);
+    default:  kp.stages = 4; return launch_gemm<64, MODE>(maps, kp, grid, stream);
   }
 }
 
@@ -460,9 +569,12 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   const int64_t z_mult = (d->mode == TOIST_GEMM_WGRAD) ? (int64_t)kp.batch_y * kp.batch_n * kp.splits * d->n_taps : 1;
   int bn = 64;
   const int cands[3] = {256, 128, 64};
+  // short reductions are epilogue bound: keep two CTAs per SM (BN <= 128) so epilogues overlap main loops
+  const int64_t k_iters = (d->mode == TOIST_GEMM_WGRAD) ? 1 << 20 : (int64_t)ceil_div(d->k_per_tap, kBK) * d->n_taps;
   for (int c = 0; c < 3; ++c) {
     const int cand = cands[c];
     if (cand > 64 && d->n_cols <= cand / 2) continue;  // more than half the tile would be padding
+    if (cand == 256 && k_iters < 8) continue;
     const int64_t ctas = m_tiles * ceil_div(d->n_cols, cand) * z_mult;
     if (ctas >= 132 || cand == 64) {
       bn = cand;
@@ -472,10 +584,24 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   const int n_tiles = (int)ceil_div(d->n_cols, bn);
   kp.n_tiles = n_tiles;
 
-  CUtensorMap ma, mb;
+  CUtensorMap maps[5];
+  memset(maps, 0, sizeof(maps));
+  CUtensorMap& ma = maps[0];
+  CUtensorMap& mb = maps[1];
   uint32_t ones[4] = {1, 1, 1, 1};
   int rc;
   if (d->mode != TOIST_GEMM_WGRAD) {
+    // bf16 outputs go through the shared-memory / TMA epilogue (full-line stores, res / mask tiles by TMA load)
+    if (vec && d->out_dtype == TOIST_BF16 && (d->res == nullptr || d->res_dtype == TOIST_BF16) && d->aux == nullptr &&
+        !d->accumulate) {
+      const int64_t odim[4] = {d->n_cols, d->ext_x, d->ext_y, d->ext_n};
+      const int64_t ostr[4] = {1, d->out_sx, d->out_sy, d->out_sn};
+      const uint32_t obox[4] = {64, (uint32_t)d->tile_x, (uint32_t)d->tile_y, (uint32_t)d->tile_n};
+      if ((rc = encode_tmap_bf16_4d(&maps[2], d->out, odim, ostr, obox, ones)) != TOIST_OK) return rc;
+      if (d->res && (rc = encode_tmap_bf16_4d(&maps[3], d->res, odim, ostr, obox, ones)) != TOIST_OK) return rc;
+      if (d->mask && (rc = encode_tmap_bf16_4d(&maps[4], d->mask, odim, ostr, obox, ones)) != TOIST_OK) return rc;
+      kp.tma_epi = 1;
+    }
     TOIST_REQUIRE(tile_rows == kBM, "toist_gemm: FWD/DGRAD pixel tile must hold 128 rows (got %d)", tile_rows);
     TOIST_REQUIRE(d->k_per_tap >= 1, "toist_gemm: k_per_tap must be positive");
     kp.kblocks = (int)ceil_div(d->k_per_tap, kBK);
@@ -489,8 +615,8 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
                                   d->mode == TOIST_GEMM_FWD ? bbox_fwd : bbox_dg, ones)) != TOIST_OK)
       return rc;
     dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, 1);
-    if (d->mode == TOIST_GEMM_FWD) return dispatch_bn<TOIST_GEMM_FWD>(bn, ma, mb, kp, grid, stream);
-    return dispatch_bn<TOIST_GEMM_DGRAD>(bn, ma, mb, kp, grid, stream);
+    if (d->mode == TOIST_GEMM_FWD) return dispatch_bn<TOIST_GEMM_FWD>(bn, maps, kp, grid, stream);
+    return dispatch_bn<TOIST_GEMM_DGRAD>(bn, maps, kp, grid, stream);
   }
   TOIST_REQUIRE(tile_rows == kBK, "toist_gemm: WGRAD pixel tile must hold 64 rows (got %d)", tile_rows);
   TOIST_REQUIRE(d->m_rows >= 1, "toist_gemm: WGRAD needs m_rows");
@@ -506,5 +632,5 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   uint32_t bes[4] = {1, (uint32_t)d->stride_x, (uint32_t)d->stride_y, 1};
   if ((rc = encode_tmap_bf16_4d(&mb, d->b.ptr, d->b.dim, d->b.stride, bbox, bes)) != TOIST_OK) return rc;
   dim3 grid((unsigned)m_tiles, (unsigned)(n_tiles * d->n_taps), (unsigned)(kp.batch_y * kp.batch_n * kp.splits));
-  return dispatch_bn<TOIST_GEMM_WGRAD>(bn, ma, mb, kp, grid, stream);
+  return dispatch_bn<TOIST_GEMM_WGRAD>(bn, maps, kp, grid, stream);
 }

@@ -2,7 +2,7 @@
 
 The modules below are *parameter containers* whose names reproduce the reference's state-dict layout
 (`backbone.0.body.layer3.5.conv2.weight`, `...bn2.running_var`, `...downsample.0.weight`); the arithmetic runs in
-runtime.BackboneFn on NHWC bf16 implicit-GEMM kernels with the BatchNorm affine folded into the epilogue.
+runtime.BACKBONE on NHWC bf16 implicit-GEMM kernels with the BatchNorm affine folded into the epilogue.
 """
 from __future__ import annotations
 
@@ -133,24 +133,10 @@ class Backbone(nn.Module):
             sd = {k: v for k, v in sd.items() if not k.startswith("fc.")}
             self.body.load_state_dict(sd, strict=True)
 
-    @torch.no_grad()
     def forward(self, tensor_list: NestedTensor):
-        """Inference-only convenience with the reference's return type (OrderedDict of NCHW fp32 NestedTensors).
-        The training path goes through MDETR.forward -> runtime.BackboneFn."""
-        from ..runtime import backbone_fwd
-
-        rt = getattr(self, "_owner_runtime", None)
-        if rt is None:
-            raise RuntimeError("Backbone.forward needs the owning MDETR's runtime; call it through MDETR")
-        call = rt().call("backbone", False)
-        feats, _ = backbone_fwd(call, tensor_list.tensors.contiguous())
-        out = OrderedDict()
-        names = ["0", "1", "2", "3"] if self.return_interm_layers else [0]
-        for name, f in zip(names, feats if self.return_interm_layers else feats[-1:]):
-            n, h, w, c = f.shape
-            small, _ = K.key_mask(tensor_list.mask.contiguous().view(torch.uint8), (h, w))
-            out[name] = NestedTensor(K.nhwc_to_nchw(f), small.view(torch.bool))
-        return out
+        raise NotImplementedError(
+            "the trunk has no standalone forward in toist_b200: it runs inside MDETR.forward (runtime.BACKBONE), which "
+            "keeps activations NHWC bf16 end to end; call the model, not its backbone")
 
 
 class Joiner(nn.Sequential):

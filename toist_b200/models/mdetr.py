@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from .. import kernels as K
-from ..runtime import (BackboneFn, Call, DecoderFn, EncoderFn, HeadsFn, ShadowBank, Stage, TextFn)
+from ..runtime import (BACKBONE, DECODER, ENCODER, HEADS, TEXT, Call, GraphCache, ShadowBank, Spec, Stage, run_stage)
 from ..util import dist
 from ..util.misc import NestedTensor
 from .backbone import build_backbone
@@ -37,6 +37,7 @@ class ModelRuntime:
     def __init__(self):
         self.bank = ShadowBank()
         self.stages: Optional[Dict[str, Stage]] = None
+        self.graphs: Optional[GraphCache] = None
 
     def __deepcopy__(self, memo):  # the EMA copy (main.py:322) rebuilds its own
         return ModelRuntime()
@@ -52,28 +53,30 @@ class ModelRuntime:
 
         heads = ("class_embed.", "bbox_embed.", "contrastive_align_projection_")
         self.stages = {
-            "backbone": Stage(m, pick("backbone.0.body."), prefix="backbone.0.body.", blocks=body.blocks,
+            "backbone": Stage(m, "backbone", pick("backbone.0.body."), prefix="backbone.0.body.", blocks=body.blocks,
                               first_trainable=2 if m.backbone[0].train_backbone else 5,
                               return_interm=m.backbone[0].return_interm_layers),
-            "text": Stage(m, pick("transformer.text_encoder.", "transformer.resizer.", exclude=("pooler.",)),
+            "text": Stage(m, "text", pick("transformer.text_encoder.", "transformer.resizer.", exclude=("pooler.",)),
                           prefix="transformer.text_encoder.", resizer_prefix="transformer.resizer.",
                           num_layers=tcfg.num_hidden_layers, num_heads=tcfg.num_attention_heads,
                           eps=float(tcfg.layer_norm_eps), pad_id=int(tcfg.pad_token_id)),
-            "encoder": Stage(m, pick("input_proj.", "transformer.encoder."), prefix="transformer.encoder.",
-                             input_proj_prefix="input_proj.", num_layers=tr.encoder.num_layers, nhead=tr.nhead,
-                             want_src_proj=False),
-            "decoder": Stage(m, pick("transformer.decoder."), prefix="transformer.decoder.",
+            "encoder": Stage(m, "encoder", pick("input_proj.", "transformer.encoder."), prefix="transformer.encoder.",
+                             input_proj_prefix="input_proj.", num_layers=tr.encoder.num_layers, nhead=tr.nhead),
+            "decoder": Stage(m, "decoder", pick("transformer.decoder."), prefix="transformer.decoder.",
                              num_layers=tr.decoder.num_layers, nhead=tr.nhead),
-            "heads": Stage(m, pick(*heads), prefix="", contrastive=m.contrastive_align_loss),
+            "heads": Stage(m, "heads", pick(*heads), prefix="", contrastive=m.contrastive_align_loss),
         }
 
     def refresh(self, m: "MDETR") -> None:
         if self.stages is None:
             self.build(m)
+        sig = self.bank._sig
         self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body)
+        if self.graphs is not None and sig is not None and sig != self.bank._sig:
+            self.graphs.clear()  # shadow buffers moved: captured pointers are stale
 
     def call(self, name: str, save: bool, **kw) -> Call:
-        return Call(self.stages[name], self.bank.w, save, **kw)
+        return Call(self.stages[name], self.bank.w, save, graphs=self.graphs, **kw)
 
 
 class MDETR(nn.Module):
@@ -106,6 +109,13 @@ class MDETR(nn.Module):
                 "toist_b200 round 1 implements the deterministic path (model.eval() or --dropout 0); training-mode "
                 f"dropout (p={p}) is not wired into the kernels yet")
 
+    def enable_cuda_graphs(self, on: bool = True) -> "MDETR":
+        """Capture each stage's forward / backward launch sequence into CUDA graphs (one per input-shape signature)
+        and replay them on later steps.  For fixed-shape training / benchmarking; tensors returned by a step are
+        overwritten by the next step with the same shapes."""
+        self._rt.graphs = GraphCache() if on else None
+        return self
+
     def _grad_wanted(self) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
@@ -119,8 +129,7 @@ class MDETR(nn.Module):
         if images.dtype != torch.float32 or not images.is_cuda:
             raise RuntimeError("toist_b200 expects fp32 CUDA images (sm_100a); there is no CPU path")
         images = images.contiguous()
-        bb = rt.call("backbone", save)
-        feats = BackboneFn.apply(bb, images, *bb.stage.params)
+        feats = run_stage(BACKBONE, rt.call("backbone", save), images)
         c5 = feats[-1]
         B, h, w, _ = c5.shape
         E = self.transformer.d_model
@@ -132,8 +141,7 @@ class MDETR(nn.Module):
             ids = tokenized["input_ids"].contiguous()
             attn = tokenized["attention_mask"].to(torch.int64).contiguous()
             text_attention_mask = attn.ne(1)
-            tx = rt.call("text", save)
-            text_resized = TextFn.apply(tx, ids, text_attention_mask.view(torch.uint8), *tx.stage.params)
+            text_resized = run_stage(TEXT, rt.call("text", save), ids, text_attention_mask.view(torch.uint8))[0]
         else:  # already encoded (models/transformer.py:139-141)
             text_attention_mask, text_resized, tokenized = captions
             attn = (~text_attention_mask).to(torch.int64).contiguous()
@@ -144,10 +152,8 @@ class MDETR(nn.Module):
         npf = self.backbone[1].num_pos_feats
         pos32, pos16 = K.pos_sine(small, npf, float(self.backbone[1].temperature), extra_rows=L)
         S = h * w + L
-        en = rt.call("encoder", save)
-        en.stage.want_src_proj = want_features
-        enc_out = EncoderFn.apply(en, c5, text_resized, pos16.view(S * B, E), key, *en.stage.params)
-        img_memory = enc_out[0] if want_features else enc_out
+        enc_out = run_stage(ENCODER, rt.call("encoder", save), c5, text_resized, pos16.view(S * B, E), key)
+        img_memory = enc_out[0]
         query_embed = self.query_embed.weight.unsqueeze(1).repeat(1, B, 1)
         memory_cache = {
             "text_memory_resized": text_resized,
@@ -179,10 +185,8 @@ class MDETR(nn.Module):
         S, B, E = mem.shape
         pos16 = K.cast_bf16(memory_cache["pos_embed"].contiguous()).view(S * B, E)
         key = memory_cache["mask"].contiguous().view(torch.uint8)
-        de = rt.call("decoder", save)
-        hs = DecoderFn.apply(de, mem, memory_cache["query_embed"], pos16, key, *de.stage.params)
-        hd = rt.call("heads", save, B=B)
-        res = HeadsFn.apply(hd, hs, memory_cache["text_memory"], *hd.stage.params)
+        hs = run_stage(DECODER, rt.call("decoder", save), mem, memory_cache["query_embed"], pos16, key)[0]
+        res = run_stage(HEADS, rt.call("heads", save, B=B), hs, memory_cache["text_memory"])
         logits, boxes = res[0], res[1]
         out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
         stacked = {"pred_logits": logits, "pred_boxes": boxes}
@@ -215,38 +219,30 @@ class MDETR(nn.Module):
 
 
 # ====================================================================================================== criterion
-class _CriterionFn(torch.autograd.Function):
-    """Matching + every detection loss term of every decoder layer; returns out [5, L] (see toist_criterion_reduce)
-    and the assignments.  Gradients w.r.t. logits and boxes only (the alignment loss is evaluated without gradient
-    in the reference, models/mdetr.py:601)."""
+def _criterion_fwd(c: Call, logits, boxes, pq, ptok, tgt_boxes, tgt_count, posmap, tok_pos, num_boxes):
+    """Matching + every detection loss term of every decoder layer in a handful of launches; returns out [5, L] (see
+    toist_criterion_reduce), the assignments and the error flag.  Gradients exist w.r.t. logits and boxes only (the
+    alignment loss is evaluated without gradient in the reference, models/mdetr.py:600)."""
+    pt = PackedTargets(tgt_boxes, tgt_count, posmap, (), tgt_boxes.shape[1])
+    match_q, flags, _ = match_layers(logits, boxes, pt, c.w_class, c.w_bbox, c.w_giou)
+    row_loss, dlogits = K.token_ce(logits, match_q, tgt_count, posmap, num_boxes, c.eos_coef, c.save)
+    pl1, pgi, d1, d2 = K.box_loss(boxes, match_q, tgt_count, tgt_boxes, num_boxes, c.save)
+    card = K.cardinality(logits)
+    img_loss = None
+    if pq is not None:
+        img_loss, _, _ = K.contrastive_align(pq, ptok, match_q, tgt_count, tok_pos, num_boxes, c.temperature, False)
+    out = K.criterion_reduce(row_loss, pl1, pgi, card, img_loss, tgt_count, num_boxes, flags)
+    return (out, match_q, flags), ((dlogits, d1, d2) if c.save else None)
 
-    @staticmethod
-    def forward(ctx, cfg, logits, boxes, pq, ptok, tgt_boxes, tgt_count, posmap, tok_pos, num_boxes):
-        logits = logits.contiguous()
-        boxes = boxes.contiguous()
-        pt = PackedTargets(tgt_boxes, tgt_count, posmap, (), tgt_boxes.shape[1])
-        match_q, flags, _ = match_layers(logits, boxes, pt, cfg["w_class"], cfg["w_bbox"], cfg["w_giou"])
-        want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        row_loss, dlogits = K.token_ce(logits, match_q, tgt_count, posmap, num_boxes, cfg["eos_coef"], want)
-        pl1, pgi, d1, d2 = K.box_loss(boxes, match_q, tgt_count, tgt_boxes, num_boxes, want)
-        card = K.cardinality(logits)
-        img_loss = None
-        if pq is not None:
-            img_loss, _, _ = K.contrastive_align(pq.contiguous(), ptok.contiguous(), match_q, tgt_count, tok_pos,
-                                                 num_boxes, cfg["temperature"], False)
-        out = K.criterion_reduce(row_loss, pl1, pgi, card, img_loss, tgt_count, num_boxes, flags)
-        if want:
-            ctx.save_for_backward(dlogits, d1, d2)
-        ctx.mark_non_differentiable(match_q, flags)
-        return out, match_q, flags
 
-    @staticmethod
-    def backward(ctx, gout, _gm, _gf):
-        dlogits, d1, d2 = ctx.saved_tensors
-        gout = gout.contiguous()
-        gl = K.scale_layers(dlogits, gout[0]) if ctx.needs_input_grad[1] else None
-        gb = K.scale_layers2(d1, gout[1], d2, gout[2]) if ctx.needs_input_grad[2] else None
-        return (None, gl, gb) + (None,) * 7
+def _criterion_bwd(c: Call, saved, needs, gout, *unused):
+    dlogits, d1, d2 = saved
+    gl = K.scale_layers(dlogits, gout[0]) if needs[0] else None
+    gb = K.scale_layers2(d1, gout[1], d2, gout[2]) if needs[1] else None
+    return (gl, gb) + (None,) * 7, {}
+
+
+CRITERION = Spec("criterion", 9, _criterion_fwd, _criterion_bwd, nondiff=(1, 2))
 
 
 def _token_spans(tokenized, i: int, spans):
@@ -304,6 +300,22 @@ class SetCriterion(nn.Module):
         self.temperature = temperature
         unsupported = [l for l in losses if l not in ("labels", "boxes", "cardinality", "contrastive_align")]
         self._unsupported = unsupported
+        self._stage = Stage.empty("criterion")
+        self._graphs: Optional[GraphCache] = None
+
+    def enable_cuda_graphs(self, on: bool = True) -> "SetCriterion":
+        """Replay the criterion's launch sequence as a CUDA graph (fixed shapes; see MDETR.enable_cuda_graphs)."""
+        self._graphs = GraphCache() if on else None
+        return self
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, None if k == "_graphs" else copy.deepcopy(v, memo))
+        return new
 
     def _stack(self, outputs: dict) -> Dict[str, torch.Tensor]:
         st = outputs.get("_b200_stacked")
@@ -344,11 +356,12 @@ class SetCriterion(nn.Module):
             pq, ptok = st["proj_queries"], st["proj_tokens"]
             tok_pos = build_token_positive(outputs["tokenized"], targets, packed.t_max, ptok.shape[1]).to(
                 dev, non_blocking=True)
-        cfg = {"w_class": float(self.matcher.cost_class), "w_bbox": float(self.matcher.cost_bbox),
-               "w_giou": float(self.matcher.cost_giou), "eos_coef": float(self.eos_coef),
-               "temperature": float(self.temperature)}
-        out, match_q, flags = _CriterionFn.apply(cfg, logits, boxes, pq, ptok, packed.boxes, packed.count,
-                                                 packed.posmap, tok_pos, nb)
+        save = torch.is_grad_enabled() and (logits.requires_grad or boxes.requires_grad)
+        call = Call(self._stage, {}, save, graphs=self._graphs, w_class=float(self.matcher.cost_class),
+                    w_bbox=float(self.matcher.cost_bbox), w_giou=float(self.matcher.cost_giou),
+                    eos_coef=float(self.eos_coef), temperature=float(self.temperature))
+        out, match_q, flags = run_stage(CRITERION, call, logits, boxes, pq, ptok, packed.boxes, packed.count,
+                                        packed.posmap, tok_pos, nb)
         self.last_match = (match_q, packed.counts, flags)
         terms = [("loss_ce", 0), ("loss_bbox", 1), ("loss_giou", 2), ("cardinality_error", 3)]
         if pq is not None:

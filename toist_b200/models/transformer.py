@@ -1,6 +1,6 @@
 """Cross-modal transformer: parameter containers with the reference's module / state-dict names
-(reference models/transformer.py:22-96,270-349,473-525).  The arithmetic lives in runtime.TextFn / EncoderFn /
-DecoderFn (tcgen05 GEMMs, fused epilogues); these classes only own parameters, the tokenizer and hyper-parameters.
+(reference models/transformer.py:22-96,270-349,473-525).  The arithmetic lives in runtime.TEXT / ENCODER /
+DECODER (tcgen05 GEMMs, fused epilogues); these classes only own parameters, the tokenizer and hyper-parameters.
 """
 from __future__ import annotations
 

@@ -2,15 +2,18 @@
 
 * `ShadowBank` keeps a bf16 copy of every GEMM / convolution weight (FrozenBatchNorm scale folded per output
   channel, conv weights re-laid out OIHW -> OHWI) and refreshes all of them with one `toist_weight_prep` launch.
-* Five `torch.autograd.Function`s wrap the stages of the hot path; their backward passes are hand written on top of
+* Five autograd stages wrap the parts of the hot path; their backward passes are hand written on top of
   blocks.py, so torch only moves gradients between stages and accumulates them into `Parameter.grad` (which keeps
   DistributedDataParallel's reducer hooks working, reference main.py:336).
 
-  BackboneFn  images -> NHWC features            (models/backbone.py:74-80, torchvision resnet)
-  TextFn      token ids -> resized text features (models/transformer.py:129-138,487-492)
-  EncoderFn   features + text -> img_memory      (models/mdetr.py:383 input_proj, models/transformer.py:144-152)
-  DecoderFn   img_memory -> hs                   (models/transformer.py:170-188)
-  HeadsFn     hs -> logits / boxes / projections (models/mdetr.py:420-433)
+  BACKBONE  images -> NHWC features            (models/backbone.py:74-80, torchvision resnet)
+  TEXT      token ids -> resized text features (models/transformer.py:129-138,487-492)
+  ENCODER   features + text -> img_memory      (models/mdetr.py:383 input_proj, models/transformer.py:144-152)
+  DECODER   img_memory -> hs                   (models/transformer.py:170-188)
+  HEADS     hs -> logits / boxes / projections (models/mdetr.py:420-433)
+
+  Each is a `Spec` (forward / backward launch sequence) run by the generic `StageFn`; with CUDA graphs enabled the
+  sequences are captured once per shape signature and replayed (`GraphCache`).
 """
 from __future__ import annotations
 
@@ -90,12 +93,12 @@ def _unpack(spec, flat: Sequence[torch.Tensor]):
 
 def _save(ctx, obj) -> None:
     flat: List[torch.Tensor] = []
-    ctx.spec = _pack(obj, flat)
+    ctx.pack_spec = _pack(obj, flat)
     ctx.save_for_backward(*flat)
 
 
 def _load(ctx):
-    return _unpack(ctx.spec, ctx.saved_tensors)
+    return _unpack(ctx.pack_spec, ctx.saved_tensors)
 
 
 # ------------------------------------------------------------------------------------------------ shadow weights
@@ -195,12 +198,21 @@ def _grads_for(names: Sequence[str], g: Dict[str, torch.Tensor], params_shapes) 
 class Stage:
     """Static description of one autograd stage: which parameters it owns (ordered) and configuration."""
 
-    def __init__(self, model, names: Sequence[str], **cfg):
+    def __init__(self, model, name: str, names: Sequence[str], **cfg):
         lookup = dict(model.named_parameters())
+        self.name = name
         self.names = list(names)
         self.params = [lookup[n] for n in self.names]
         self.shapes = [tuple(p.shape) for p in self.params]
         self.__dict__.update(cfg)
+
+    @classmethod
+    def empty(cls, name: str, **cfg) -> "Stage":
+        """A stage without parameters (the criterion)."""
+        st = cls.__new__(cls)
+        st.name, st.names, st.params, st.shapes = name, [], [], []
+        st.__dict__.update(cfg)
+        return st
 
     def req(self) -> Set[str]:
         return requires(self.names, self.params, torch.is_grad_enabled())
@@ -209,11 +221,124 @@ class Stage:
 class Call:
     """Per-invocation context handed to a Function (non-tensor argument)."""
 
-    def __init__(self, stage: Stage, w: Dict[str, torch.Tensor], save: bool, **kw):
+    def __init__(self, stage: Stage, w: Dict[str, torch.Tensor], save: bool, graphs: "Optional[GraphCache]" = None,
+                 **kw):
         self.stage, self.w = stage, w
         self.req = stage.req() if save else set()
         self.save = save  # keep activations for a backward pass (some tensor upstream or here wants a gradient)
+        self.graphs = graphs
+        self.extra = tuple(sorted(kw.items()))
         self.__dict__.update(kw)
+
+    def signature(self) -> tuple:
+        return (self.stage.name, self.save, frozenset(self.req), self.extra)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA graphs
+class _GraphEntry:
+    __slots__ = ("graph", "static_in", "outputs", "launches")
+
+
+class GraphCache:
+    """Captures the launch sequence of a stage body into a CUDA graph the first time a (stage, shapes, flags) key is
+    seen and replays it afterwards, so a training step costs a handful of graph launches instead of ~1400 kernel
+    launches issued from Python.  Inputs are copied into static buffers; outputs (including everything saved for
+    the backward graph) live in the graph's private memory pool and are overwritten by the next replay."""
+
+    def __init__(self):
+        self.entries: Dict[tuple, _GraphEntry] = {}
+        self.pool = None
+
+    def __deepcopy__(self, memo):
+        return GraphCache()
+
+    def clear(self) -> None:
+        self.entries.clear()
+        self.pool = None
+
+    def run(self, key: tuple, fn, inputs: Sequence[Optional[torch.Tensor]]):
+        e = self.entries.get(key)
+        if e is not None:
+            for s_, t in zip(e.static_in, inputs):
+                if s_ is not None:
+                    s_.copy_(t)
+            e.graph.replay()
+            K._count(e.launches)
+            return e.outputs
+        static_in = [None if t is None else t.detach().clone() for t in inputs]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up outside the capture: lazy kernel attributes, allocator, tile caches
+            fn(*static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = K.launches()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self.pool):
+            outputs = fn(*static_in)
+        if self.pool is None:
+            self.pool = g.pool()
+        e = _GraphEntry()
+        e.graph, e.static_in, e.outputs, e.launches = g, static_in, outputs, K.launches() - n0
+        self.entries[key] = e
+        g.replay()
+        return outputs
+
+
+def _sig(tensors) -> tuple:
+    return tuple(None if t is None else (tuple(t.shape), t.dtype, tuple(t.stride())) for t in tensors)
+
+
+class StageFn(torch.autograd.Function):
+    """Generic autograd node of one stage.  `spec.fwd(c, *inputs) -> (outputs, saved)` and
+    `spec.bwd(c, saved, needs, *grad_outputs) -> (input_grads, param_grads)` are plain launch sequences (blocks.py);
+    with `c.graphs` set they are captured once per shape signature and replayed."""
+
+    @staticmethod
+    def forward(ctx, spec, c: Call, *args):
+        n_in = spec.n_inputs
+        inputs = [a.contiguous() if isinstance(a, torch.Tensor) and spec.contiguous_inputs else a for a in args[:n_in]]
+        ctx.spec, ctx.c = spec, c
+        ctx.n_in = n_in
+        if c.graphs is None:
+            outs, saved = spec.fwd(c, *inputs)
+            ctx.fkey = None
+        else:
+            ctx.fkey = ("fwd", c.signature(), _sig(inputs))
+            outs, saved = c.graphs.run(ctx.fkey, lambda *t: spec.fwd(c, *t), inputs)
+            outs = tuple(None if o is None else o.detach() for o in outs)  # fresh aliases of the static buffers
+        if c.save:
+            _save(ctx, saved)
+        nd = [outs[i] for i in spec.nondiff if i < len(outs) and outs[i] is not None]
+        if nd:
+            ctx.mark_non_differentiable(*nd)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        spec, c = ctx.spec, ctx.c
+        saved = _load(ctx)
+        needs = tuple(ctx.needs_input_grad[2: 2 + ctx.n_in])
+        gouts = [None if g is None else g.contiguous() for g in gouts]
+        if c.graphs is None:
+            gin, grads = spec.bwd(c, saved, needs, *gouts)
+        else:
+            key = ("bwd", ctx.fkey, needs, _sig(gouts))
+            gin, grads = c.graphs.run(key, lambda *g: spec.bwd(c, saved, needs, *g), gouts)
+        return (None, None) + tuple(gin) + _grads_for(c.stage.names, grads, c.stage.shapes)
+
+
+class Spec:
+    def __init__(self, name, n_inputs, fwd, bwd, nondiff=(), contiguous_inputs=True):
+        self.name, self.n_inputs, self.fwd, self.bwd = name, n_inputs, fwd, bwd
+        self.nondiff, self.contiguous_inputs = tuple(nondiff), contiguous_inputs
+
+
+def run_stage(spec: Spec, c: Call, *inputs):
+    return StageFn.apply(spec, c, *inputs, *c.stage.params)
+
+
 
 
 # ------------------------------------------------------------------------------------------------ backbone
@@ -261,28 +386,25 @@ def backbone_bwd(c: Call, gfeats: Dict[int, torch.Tensor], feats: Sequence[torch
     return grads
 
 
-class BackboneFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, c: Call, images, *params):
-        feats, saved = backbone_fwd(c, images)
-        ctx.c = c
-        keys = sorted(saved)
-        ctx.keys = keys
-        if c.save:
-            _save(ctx, (tuple(feats), tuple(saved[k] for k in keys)))
-        return tuple(feats) if c.stage.return_interm else (feats[-1],)
+def _bb_fwd(c: Call, images):
+    feats, saved = backbone_fwd(c, images)
+    keys = sorted(saved)
+    outs = tuple(feats) if c.stage.return_interm else (feats[-1],)
+    return outs, (tuple(feats), tuple(keys), tuple(saved[k] for k in keys))
 
-    @staticmethod
-    def backward(ctx, *gouts):
-        c = ctx.c
-        feats, saved_list = _load(ctx)
-        saved = dict(zip(ctx.keys, saved_list))
-        if c.stage.return_interm:
-            gfeats = {i + 1: g for i, g in enumerate(gouts) if g is not None}
-        else:
-            gfeats = {4: gouts[0]} if gouts[0] is not None else {}
-        grads = backbone_bwd(c, gfeats, feats, saved) if c.req else {}
-        return (None, None) + _grads_for(c.stage.names, grads, c.stage.shapes)
+
+def _bb_bwd(c: Call, saved, needs, *gouts):
+    feats, keys, saved_list = saved
+    sv = dict(zip(keys, saved_list))
+    if c.stage.return_interm:
+        gfeats = {i + 1: g for i, g in enumerate(gouts) if g is not None}
+    else:
+        gfeats = {4: gouts[0]} if gouts[0] is not None else {}
+    grads = backbone_bwd(c, gfeats, feats, sv) if c.req else {}
+    return (None,), grads
+
+
+BACKBONE = Spec("backbone", 1, _bb_fwd, _bb_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ text encoder
@@ -302,15 +424,15 @@ def text_fwd(c: Call, input_ids: torch.Tensor, text_mask_u8: torch.Tensor):
     r = WView(c.w, st.resizer_prefix)
     y = K.linear_fwd(x, r["fc.weight"], r["fc.bias"], out_dtype=torch.float32)
     _, out, m1, r1 = Bk.ln_fwd(r, "layer_norm.", y, 1e-12, want_bf16=False, want_f32=True)
-    saved = (pos_ids, x32, m0, r0, tuple(saved_layers), x, y, m1, r1) if c.save else None
-    return out.view(L, B, -1), saved
+    saved = (input_ids, pos_ids, x32, m0, r0, tuple(saved_layers), x, y, m1, r1) if c.save else None
+    return (out.view(L, B, -1),), saved
 
 
-def text_bwd(c: Call, dout: torch.Tensor, input_ids, saved) -> Dict[str, torch.Tensor]:
+def text_bwd(c: Call, saved, needs, dout: torch.Tensor):
     st = c.stage
     grads: Dict[str, torch.Tensor] = {}
     w = WView(c.w, st.prefix)
-    pos_ids, x32, m0, r0, saved_layers, x_last, y, m1, r1 = saved
+    input_ids, pos_ids, x32, m0, r0, saved_layers, x_last, y, m1, r1 = saved
     B, L = input_ids.shape
     rp = st.resizer_prefix
     r = WView(c.w, rp)
@@ -319,7 +441,7 @@ def text_bwd(c: Call, dout: torch.Tensor, input_ids, saved) -> Dict[str, torch.T
     Bk.lin_param_grads(GView(grads, rp), RView(c.req, rp), "fc.weight", "fc.bias", dy, x_last, r["fc.weight"].shape)
     body_req = any(n.startswith(st.prefix) for n in c.req)
     if not body_req:
-        return grads
+        return (None, None), grads
     dx = K.linear_dgrad(dy, r["fc.weight"])
     for i in range(st.num_layers - 1, -1, -1):
         pre = st.prefix + f"encoder.layer.{i}."
@@ -339,29 +461,16 @@ def text_bwd(c: Call, dout: torch.Tensor, input_ids, saved) -> Dict[str, torch.T
             bufs.append(None)
     if any(b is not None for b in bufs):
         K.embed_scatter(dx32, input_ids, pos_ids, bufs[0], bufs[1], bufs[2], seq_first=True)
-    return grads
+    return (None, None), grads
 
 
-class TextFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, c: Call, input_ids, text_mask_u8, *params):
-        out, saved = text_fwd(c, input_ids, text_mask_u8)
-        ctx.c = c
-        if c.save:
-            _save(ctx, (input_ids, saved))
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        c = ctx.c
-        input_ids, saved = _load(ctx)
-        grads = text_bwd(c, dout, input_ids, saved)
-        return (None, None, None) + _grads_for(c.stage.names, grads, c.stage.shapes)
+TEXT = Spec("text", 2, text_fwd, text_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ encoder
 def encoder_fwd(c: Call, feat: torch.Tensor, text: torch.Tensor, pos16: torch.Tensor, key_mask: torch.Tensor):
-    """feat NHWC bf16 [B,h,w,C]; text fp32 [L,B,E]; pos16 bf16 [S*B,E]; key_mask uint8 [B,S]."""
+    """feat NHWC bf16 [B,h,w,C]; text fp32 [L,B,E]; pos16 bf16 [S*B,E]; key_mask uint8 [B,S].
+    Outputs: img_memory fp32 [S,B,E] and the projected image rows src_proj bf16 [h*w, B, E] (mask head input)."""
     st = c.stage
     B, h, wd, _ = feat.shape
     L, _, E = text.shape
@@ -377,45 +486,31 @@ def encoder_fwd(c: Call, feat: torch.Tensor, text: torch.Tensor, pos16: torch.Te
         x, sv = Bk.encoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), x, pos16, key_mask, st.nhead, B)
         saved_layers.append(sv if c.save else None)
     mem = K.cast_f32(x).view(S, B, E)
-    return mem, (src, tuple(saved_layers), x)
+    saved = (feat, (L, B, E), tuple(saved_layers)) if c.save else None
+    return (mem, src[: hw * B].view(hw, B, E)), saved
 
 
-class EncoderFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, c: Call, feat, text, pos16, key_mask, *params):
-        mem, saved = encoder_fwd(c, feat, text, pos16, key_mask)
-        ctx.c = c
-        ctx.text_shape = tuple(text.shape)
-        if c.save:
-            _save(ctx, (feat, pos16, key_mask, saved))
-        if c.stage.want_src_proj:
-            B, h, wd, _ = feat.shape
-            E = text.shape[-1]
-            return mem, saved[0][: h * wd * B].view(h * wd, B, E)
-        return mem
+def encoder_bwd(c: Call, saved, needs, dmem, dsrc_proj=None):
+    st = c.stage
+    feat, (L, B, E), saved_layers = saved
+    _, h, wd, _ = feat.shape
+    hw = h * wd
+    grads: Dict[str, torch.Tensor] = {}
+    d = K.cast_bf16(dmem.contiguous().view(-1, E))
+    for i in range(st.num_layers - 1, -1, -1):
+        pre = st.prefix + f"layers.{i}."
+        d = Bk.encoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), d, saved_layers[i], st.nhead, B)
+    d_img = d[: hw * B]
+    if dsrc_proj is not None:  # the mask head reads src_proj (models/segmentation.py:77-78)
+        d_img = K.add_bf16(d_img, dsrc_proj.contiguous().view(-1, E))
+    dtext = K.cast_f32(d[hw * B:]).view(L, B, E) if needs[1] else None
+    ipp = st.input_proj_prefix
+    dfeat = Bk.seq_from_nhwc_bwd(GView(grads, ipp), RView(c.req, ipp), "weight", "bias", d_img, feat,
+                                 c.w[ipp + "weight"], needs[0])
+    return (dfeat, dtext, None, None), grads
 
-    @staticmethod
-    def backward(ctx, dmem, dsrc_proj=None):
-        c = ctx.c
-        st = c.stage
-        feat, pos16, key_mask, (src, saved_layers, x_last) = _load(ctx)
-        B, h, wd, _ = feat.shape
-        L, _, E = ctx.text_shape
-        hw = h * wd
-        grads: Dict[str, torch.Tensor] = {}
-        d = K.cast_bf16(dmem.contiguous().view(-1, E))
-        for i in range(st.num_layers - 1, -1, -1):
-            pre = st.prefix + f"layers.{i}."
-            d = Bk.encoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), d, saved_layers[i],
-                                     st.nhead, B)
-        d_img = d[: hw * B]
-        if dsrc_proj is not None:  # mask head reads src_proj (models/segmentation.py:77-78)
-            d_img = K.add_bf16(d_img, K.cast_bf16(dsrc_proj.contiguous().view(-1, E)))
-        dtext = K.cast_f32(d[hw * B:]).view(L, B, E) if ctx.needs_input_grad[2] else None
-        ipp = st.input_proj_prefix
-        dfeat = Bk.seq_from_nhwc_bwd(GView(grads, ipp), RView(c.req, ipp), "weight", "bias", d_img, feat,
-                                     c.w[ipp + "weight"], ctx.needs_input_grad[1])
-        return (None, dfeat, dtext, None, None) + _grads_for(st.names, grads, st.shapes)
+
+ENCODER = Spec("encoder", 4, encoder_fwd, encoder_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ decoder
@@ -436,48 +531,41 @@ def decoder_fwd(c: Call, mem32: torch.Tensor, qpos32: torch.Tensor, pos16: torch
                                        st.nhead, B)
         _, _, m, r = K.layernorm_fwd(tgt, nw["weight"], nw["bias"], 1e-5, out16=hs[i])
         saved_layers.append((sv, tgt, m, r) if c.save else None)
-    return hs, tuple(saved_layers)
+    saved = ((S, B, E, Q), tuple(saved_layers)) if c.save else None
+    return (hs,), saved
 
 
-class DecoderFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, c: Call, mem32, qpos32, pos16, key_mask, *params):
-        hs, saved = decoder_fwd(c, mem32, qpos32, pos16, key_mask)
-        ctx.c = c
-        ctx.shapes = (tuple(mem32.shape), tuple(qpos32.shape))
-        if c.save:
-            _save(ctx, saved)
-        return hs
+def decoder_bwd(c: Call, saved, needs, dhs):
+    st = c.stage
+    (S, B, E, Q), saved_layers = saved
+    grads: Dict[str, torch.Tensor] = {}
+    np_ = st.prefix + "norm."
+    d_next = None
+    d_qpos = d_mem = None
+    for i in range(st.num_layers - 1, -1, -1):
+        sv, t3, m, r = saved_layers[i]
+        dy = Bk.ln_bwd(WView(c.w, np_), GView(grads, np_), RView(c.req, np_), "", dhs[i], t3, m, r)
+        pre = st.prefix + f"layers.{i}."
+        d_tgt, dq, dmp, dm = Bk.decoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dy, d_next,
+                                                  sv, st.nhead, B, need_tgt=i > 0)
+        d_next = d_tgt
+        d_qpos = dq if d_qpos is None else K.add_bf16(d_qpos, dq)
+        d_mem = K.add_bf16(dmp, dm) if d_mem is None else K.add_bf16(d_mem, dmp, dm)
+    dmem32 = K.cast_f32(d_mem).view(S, B, E) if needs[0] else None
+    dqpos32 = K.cast_f32(d_qpos).view(Q, B, E) if needs[1] else None
+    return (dmem32, dqpos32, None, None), grads
 
-    @staticmethod
-    def backward(ctx, dhs):
-        c = ctx.c
-        st = c.stage
-        saved_layers = _load(ctx)
-        (S, B, E), (Q, _, _) = ctx.shapes
-        grads: Dict[str, torch.Tensor] = {}
-        dhs = dhs.contiguous()
-        np_ = st.prefix + "norm."
-        d_next = None
-        d_qpos = d_mem = None
-        for i in range(st.num_layers - 1, -1, -1):
-            sv, t3, m, r = saved_layers[i]
-            dy = Bk.ln_bwd(WView(c.w, np_), GView(grads, np_), RView(c.req, np_), "", dhs[i], t3, m, r)
-            pre = st.prefix + f"layers.{i}."
-            d_tgt, dq, dmp, dm = Bk.decoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dy,
-                                                      d_next, sv, st.nhead, B, need_tgt=i > 0)
-            d_next = d_tgt
-            d_qpos = dq if d_qpos is None else K.add_bf16(d_qpos, dq)
-            d_mem = K.add_bf16(dmp, dm) if d_mem is None else K.add_bf16(d_mem, dmp, dm)
-        dmem32 = K.cast_f32(d_mem).view(S, B, E) if ctx.needs_input_grad[1] else None
-        dqpos32 = K.cast_f32(d_qpos).view(Q, B, E) if ctx.needs_input_grad[2] else None
-        return (None, dmem32, dqpos32, None, None) + _grads_for(st.names, grads, st.shapes)
+
+DECODER = Spec("decoder", 4, decoder_fwd, decoder_bwd)
 
 
 # ------------------------------------------------------------------------------------------------ heads
-def heads_fwd(c: Call, hs: torch.Tensor, text_mem32: Optional[torch.Tensor], B: int):
-    """hs bf16 [L, Q*B, E] -> logits [L,B,Q,C], boxes [L,B,Q,4] (sigmoid), proj_queries [L,B,Q,D], proj_tokens [B,T,D]."""
+def heads_fwd(c: Call, hs: torch.Tensor, text_mem32: Optional[torch.Tensor]):
+    """hs bf16 [L, Q*B, E] -> logits [L,B,Q,C], boxes [L,B,Q,4] (sigmoid), proj_queries [L,B,Q,D], proj_tokens [B,T,D].
+    The reference evaluates the contrastive-alignment loss under torch.no_grad (models/mdetr.py:600), so the two
+    projections never receive a gradient; they are emitted as constants (non-differentiable outputs)."""
     st = c.stage
+    B = c.B
     w = WView(c.w, st.prefix)
     L, QB, E = hs.shape
     Q = QB // B
@@ -500,47 +588,35 @@ def heads_fwd(c: Call, hs: torch.Tensor, text_mem32: Optional[torch.Tensor], B: 
                                    w["contrastive_align_projection_text.bias"], 1, T, B)
         pt, _ = K.l2norm_fwd(rawt.view(-1, D))
         pt = pt.view(B, T, D)
-    return logits, boxes, pq, pt, (h1, h2)
+    saved = (hs, h1, h2, boxes) if c.save else None
+    return (logits, boxes, pq, pt), saved
 
 
-class HeadsFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, c: Call, hs, text_mem32, *params):
-        logits, boxes, pq, pt, (h1, h2) = heads_fwd(c, hs, text_mem32, c.B)
-        ctx.c = c
-        if c.save:
-            ctx.save_for_backward(hs, h1, h2, boxes)
-        if pq is None:
-            return logits, boxes
-        # the reference evaluates the contrastive-alignment loss under torch.no_grad (models/mdetr.py:601), so the
-        # projections never receive a gradient; they are emitted as constants
-        ctx.mark_non_differentiable(pq, pt)
-        return logits, boxes, pq, pt
+def heads_bwd(c: Call, saved, needs, dlogits, dboxes, *unused):
+    st = c.stage
+    hs, h1, h2, boxes = saved
+    L, QB, E = hs.shape
+    B = c.B
+    Q = QB // B
+    grads: Dict[str, torch.Tensor] = {}
+    g, rq, w = GView(grads, st.prefix), RView(c.req, st.prefix), WView(c.w, st.prefix)
+    dhs = None
+    if dboxes is not None:
+        dpre = K.sigmoid_bwd(dboxes.contiguous(), boxes)
+        d16 = K.cast_pad_bf16(dpre, 8)
+        dh2 = Bk.heads_linear_bwd(g, rq, "bbox_embed.layers.2.weight", "bbox_embed.layers.2.bias", d16,
+                                  h2.view(L, QB, E), w["bbox_embed.layers.2.weight"], L, Q, B,
+                                  mask=h2.view(L, QB, E)).view(L * QB, E)
+        Bk.lin_param_grads(g, rq, "bbox_embed.layers.1.weight", "bbox_embed.layers.1.bias", dh2, h1, (E, E))
+        dh1 = K.linear_dgrad(dh2, w["bbox_embed.layers.1.weight"], mask=h1)
+        Bk.lin_param_grads(g, rq, "bbox_embed.layers.0.weight", "bbox_embed.layers.0.bias", dh1, hs.view(L * QB, E),
+                           (E, E))
+        dhs = K.linear_dgrad(dh1, w["bbox_embed.layers.0.weight"]).view(L, QB, E)
+    if dlogits is not None:
+        d16 = K.cast_bf16(dlogits.contiguous())
+        dhs = Bk.heads_linear_bwd(g, rq, "class_embed.weight", "class_embed.bias", d16, hs, w["class_embed.weight"], L,
+                                  Q, B, res=dhs)
+    return (dhs, None), grads
 
-    @staticmethod
-    def backward(ctx, dlogits, dboxes, *unused):
-        c = ctx.c
-        st = c.stage
-        hs, h1, h2, boxes = ctx.saved_tensors
-        L, QB, E = hs.shape
-        B = c.B
-        Q = QB // B
-        grads: Dict[str, torch.Tensor] = {}
-        g, rq, w = GView(grads, st.prefix), RView(c.req, st.prefix), WView(c.w, st.prefix)
-        dhs = None
-        if dboxes is not None:
-            dpre = K.sigmoid_bwd(dboxes.contiguous(), boxes)
-            d16 = K.cast_pad_bf16(dpre, 8)
-            dh2 = Bk.heads_linear_bwd(g, rq, "bbox_embed.layers.2.weight", "bbox_embed.layers.2.bias", d16,
-                                      h2.view(L, QB, E), w["bbox_embed.layers.2.weight"], L, Q, B,
-                                      mask=h2.view(L, QB, E)).view(L * QB, E)
-            Bk.lin_param_grads(g, rq, "bbox_embed.layers.1.weight", "bbox_embed.layers.1.bias", dh2, h1, (E, E))
-            dh1 = K.linear_dgrad(dh2, w["bbox_embed.layers.1.weight"], mask=h1)
-            Bk.lin_param_grads(g, rq, "bbox_embed.layers.0.weight", "bbox_embed.layers.0.bias", dh1, hs.view(L * QB, E),
-                               (E, E))
-            dhs = K.linear_dgrad(dh1, w["bbox_embed.layers.0.weight"]).view(L, QB, E)
-        if dlogits is not None:
-            d16 = K.cast_bf16(dlogits.contiguous())
-            dhs = Bk.heads_linear_bwd(g, rq, "class_embed.weight", "class_embed.bias", d16, hs,
-                                      w["class_embed.weight"], L, Q, B, res=dhs)
-        return (None, dhs, None) + _grads_for(st.names, grads, st.shapes)
+
+HEADS = Spec("heads", 2, heads_fwd, heads_bwd, nondiff=(2, 3))

@@ -129,6 +129,42 @@ def run_case(name: str) -> bool:
             K.conv_wgrad(dy, x, dw, stride=stride, pad=pad)
             ref = torch.nn.grad.conv2d_weight(x_nchw, (cout, cin, k, k), dy_nchw, stride=stride, padding=pad)
             return _err_report(name, dw, ref.permute(0, 2, 3, 1), 3e-5)
+    if name.startswith("epi_"):
+        # bf16 outputs: the shared-memory / TMA epilogue (res and mask tiles by TMA load, TMA store with clipping)
+        ok = True
+        if name == "epi_linear_ragged":
+            for (M, Kd, N) in ((300, 200, 264), (128, 64, 8), (1000, 512, 1032), (77, 256, 256)):
+                x, w = rn(M, Kd), rn(N, Kd, scale=Kd ** -0.5)
+                bias, res = torch.randn(N, device=dev), rn(M, N)
+                y = K.linear_fwd(x, w, bias, act=ACT_RELU, res=res)
+                ref = F.relu(x.float() @ w.float().t() + bias + res.float()).to(bf).float()
+                ok &= _err_report(f"{name}/{M}x{Kd}x{N} fwd+res", y, ref, 8e-3)
+                dy, act = rn(M, N), rn(M, Kd)
+                w2 = rn(N, Kd, scale=N ** -0.5)
+                dx = K.linear_dgrad(dy, w2, mask=act, res=act)
+                ref = ((dy.float() @ w2.float() + act.float()) * (act.float() > 0)).to(bf).float()
+                ok &= _err_report(f"{name}/{M}x{N}x{Kd} dgrad+res+mask", dx, ref, 8e-3)
+            return ok
+        if name == "epi_conv":
+            for (n, H, cin, cout, k, stride) in ((8, 40, 256, 1024, 1, 1), (8, 40, 256, 512, 3, 1), (3, 21, 64, 256, 1, 1),
+                                                 (2, 40, 128, 256, 3, 2), (8, 20, 512, 2048, 1, 1)):
+                pad = k // 2
+                x = rn(n, H, H, cin)
+                w = rn(cout, k, k, cin, scale=(k * k * cin) ** -0.5)
+                Ho = (H + 2 * pad - k) // stride + 1
+                shift, res = torch.randn(cout, device=dev), rn(n, Ho, Ho, cout)
+                y = K.conv_fwd(x, w, shift, stride=stride, pad=pad, act=ACT_RELU, res=res)
+                x_nchw, w_oihw = x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2)
+                ref = F.relu(F.conv2d(x_nchw, w_oihw, shift, stride=stride, padding=pad).permute(0, 2, 3, 1) + res.float())
+                ok &= _err_report(f"{name}/fwd {n}x{H}x{cin}->{cout} k{k}s{stride}", y, ref.to(bf).float(), 8e-3)
+                dy = rn(n, Ho, Ho, cout, scale=0.1)
+                gi = rn(n, H, H, cin, scale=0.1)
+                dx = K.conv_dgrad(dy, w, (H, H), stride=stride, pad=pad, mask=x, res=gi)
+                ref = torch.nn.grad.conv2d_input((n, cin, H, H), w_oihw, dy.float().permute(0, 3, 1, 2), stride=stride,
+                                                 padding=pad).permute(0, 2, 3, 1)
+                ref = ((ref + gi.float()) * (x.float() > 0)).to(bf).float()
+                ok &= _err_report(f"{name}/dgrad {n}x{H}x{cout}->{cin} k{k}s{stride}", dx, ref, 8e-3)
+            return ok
     if name == "attn_batched":
         # scores[b,h,q,k] = Q[q,b,h,:] . K[k,b,h,:]   from a packed [S, B, 3, H, D] projection (D = 32)
         S, B, Hh, D = 416, 2, 8, 32
@@ -175,7 +211,7 @@ CASES = [
     "conv_fwd_7_s2_40",
     "conv_dgrad_3_s1_40", "conv_dgrad_3_s1_20", "conv_dgrad_3_s2_40", "conv_dgrad_1_s2_40",
     "conv_wgrad_3_s1_40", "conv_wgrad_3_s1_20", "conv_wgrad_3_s2_40", "conv_wgrad_1_s1_40",
-    "attn_batched",
+    "attn_batched", "epi_linear_ragged", "epi_conv",
 ]
 
 
@@ -183,9 +219,14 @@ def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--case")
     ap.add_argument("--only", default="")
+    ap.add_argument("--inproc", action="store_true", help="run every case in this process (fast; a trap kills all)")
     args = ap.parse_args()
     if args.case:
         return 0 if run_case(args.case) else 1
+    if args.inproc:
+        bad = [c for c in CASES if (not args.only or args.only in c) and not run_case(c)]
+        print(f"gemm_selftest: {len(bad)} failed {bad}")
+        return 1 if bad else 0
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
     lines = []
