@@ -39,6 +39,10 @@ const char* toist_last_error(void);
 size_t toist_sizeof_gemm_desc(void);
 /* 1 when the current device is compute capability 10.x (tcgen05 / TMEM present) */
 int toist_device_ok(void);
+/* Measurement hook used by bench.py's roofline pass only: while `on` is non-zero toist_gemm returns immediately
+ * without launching, so (step time) - (step time without GEMMs) is the in-situ time of the tensor-core kernels.
+ * Returns the previous setting.  Results computed while it is set are garbage by construction. */
+int toist_debug_skip_gemm(int on);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM engine (tcgen05.mma + TMEM accumulators, operands staged by TMA, SWIZZLE_128B).

@@ -7,6 +7,9 @@
 namespace toist {
 
 static thread_local char g_err[512] = "";
+static int g_skip_gemm = 0;
+
+bool skip_gemm() { return g_skip_gemm != 0; }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -79,6 +82,12 @@ int toist_abi_version(void) { return TOIST_ABI_VERSION; }
 const char* toist_last_error(void) { return toist::g_err; }
 
 size_t toist_sizeof_gemm_desc(void) { return sizeof(toist_gemm_desc); }
+
+int toist_debug_skip_gemm(int on) {
+  const int prev = toist::g_skip_gemm;
+  toist::g_skip_gemm = on;
+  return prev;
+}
 
 int toist_device_ok(void) {
   int dev = 0;

@@ -53,15 +53,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a broken pipeline traps instead of hanging the GPU box.
+// Bounded spin: a broken pipeline traps instead of hanging the GPU box.  The report lives out of line so that
+// the wait itself stays a three-instruction loop.
+static __device__ __noinline__ void mbar_timeout() {
+  printf("toist: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("toist: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout();
   }
 }
 

@@ -42,7 +42,7 @@ struct GemmKParams {
   int accumulate;
   int vec_ok;   // 1: every row base and column tile is 16-byte aligned for all epilogue pointers
   int stages;   // depth of the TMA -> MMA shared-memory ring
-  int tma_epi;  // 1: bf16 epilogue through shared memory: res / mask tiles by TMA load, output by TMA store
+  int epi;      // epilogue flavour (template parameter EPI of the kernel)
   toist_tap taps[TOIST_MAX_TAPS];
 };
 
@@ -53,7 +53,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BN, int MODE>
+// EPI: 0 = bf16 tile through shared memory + TMA (res / mask by TMA load; act none / relu)
+//      1 = fp32 direct stores (alpha, column / row scaling, activation, optional atomic accumulate)
+//      2 = generic direct path (any dtype, aux output, every activation, unaligned shapes)
+// One epilogue per instantiation keeps the SASS small: the tiles are short-lived and instruction fetch of a
+// 100+ KB kernel showed up as the second largest stall reason (profiles/r01_ncu_gemm_notes.md).
+template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
@@ -232,8 +237,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
-    if constexpr (MODE != TOIST_GEMM_WGRAD) {
-      if (p.tma_epi) {
+    if constexpr (EPI == 0) {
+      {
         // ---- bf16 epilogue staged through shared memory.  The accumulator barrier implies that every MMA has
         // retired, so the operand ring is idle and is reused: [out | res | mask], each BN/64 slabs of 128 rows x 128 B
         // in the SWIZZLE_128B layout (16-byte chunk index XOR row % 8), which makes the per-row accesses of the 128
@@ -267,19 +272,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int i = 0; i < 32; ++i) raw[i] = 0u;
           }
           const int ncol = n0 + c0;
-          const int nvalid = min(32, p.n_cols - ncol);
+          const int last = p.n_cols - 1;  // columns past n_cols are clipped by the TMA store: clamp, do not branch
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
           if (p.col_scale != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) v[i] *= __ldg(p.col_scale + ncol + i);
+            for (int i = 0; i < 32; ++i) v[i] *= __ldg(p.col_scale + min(ncol + i, last));
           }
           if (p.col_shift != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) v[i] += __ldg(p.col_shift + ncol + i);
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(p.col_shift + min(ncol + i, last));
           }
           const uint32_t row_base = (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
           const uint32_t cb = (uint32_t)(c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group (0 or 4)
@@ -307,9 +310,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               if (!(f3.y > 0.f)) v[g * 8 + 7] = 0.f;
             }
           }
-          if (p.act != TOIST_ACT_NONE) {
+          if (p.act == TOIST_ACT_RELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -330,9 +333,64 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           tma_store_commit();
           tma_store_wait_read();
         }
-        goto epilogue_done;
       }
     }
+    if constexpr (EPI == 1) {
+      // ---- fp32 outputs (weight gradients, attention scores, prediction heads): direct stores / atomics
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.n_cols) break;  // warp-uniform
+        uint32_t raw[32];
+        if (n_iters > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = 0u;
+        }
+        if (!row_ok) continue;
+        const int ncol = n0 + c0;
+        const int last = p.n_cols - 1;
+        const int nvalid = min(32, p.n_cols - ncol);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
+        if (p.col_scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= __ldg(p.col_scale + min(ncol + i, last));
+        }
+        if (p.col_shift != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(p.col_shift + min(ncol + i, last));
+        }
+        if (p.row_scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= rscale;
+        }
+        if (p.act == TOIST_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (p.act == TOIST_ACT_SIGMOID) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+        }
+        float* op = reinterpret_cast<float*>(p.out) + row_off + ncol;
+        if (p.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) atomicAdd(op + i, v[i]);
+        } else if (p.vec_ok && nvalid == 32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(op)[g] = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) op[i] = v[i];
+        }
+      }
+    }
+    if constexpr (EPI == 2) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.n_cols) break;  // warp-uniform
@@ -475,9 +533,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       }
     }
+    }
   }
 
-epilogue_done:
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
@@ -487,13 +545,13 @@ epilogue_done:
   }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int EPI>
 static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
   constexpr int kMaxStages = (BN == 128) ? 3 : 4;
   constexpr int max_smem = kMaxStages * (kABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
   const int smem = kp.stages * (kABytes + BN * 128) + 1024 + 256;
   static bool configured = false;
-  auto kfn = gemm_kernel<BN, MODE>;
+  auto kfn = gemm_kernel<BN, MODE, EPI>;
   if (!configured) {
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
@@ -503,13 +561,26 @@ static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid
   return TOIST_OK;
 }
 
+template <int BN, int MODE>
+static int dispatch_epi(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
+  if constexpr (MODE == TOIST_GEMM_WGRAD) {
+    return launch_gemm<BN, MODE, 1>(maps, kp, grid, stream);
+  } else {
+    switch (kp.epi) {
+      case 0: return launch_gemm<BN, MODE, 0>(maps, kp, grid, stream);
+      case 1: return launch_gemm<BN, MODE, 1>(maps, kp, grid, stream);
+      default: return launch_gemm<BN, MODE, 2>(maps, kp, grid, stream);
+    }
+  }
+}
+
 template <int MODE>
 static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 grid, cudaStream_t stream) {
   // ring depth: 2 CTAs per SM for BN <= 128 (one tile's epilogue overlaps the other's main loop)
   switch (bn) {
-    case 256: kp.stages = 4; return launch_gemm<256, MODE>(maps, kp, grid, stream);
-    case 128: kp.stages = 3; return launch_gemm<128, MODE>(maps, kp, grid, stream);
-    default:  kp.stages = 4; return launch_gemm<64, MODE>(maps, kp, grid, stream);
+    case 256: kp.stages = 4; return dispatch_epi<256, MODE>(maps, kp, grid, stream);
+    case 128: kp.stages = 3; return dispatch_epi<128, MODE>(maps, kp, grid, stream);
+    default:  kp.stages = 4; return dispatch_epi<64, MODE>(maps, kp, grid, stream);
   }
 }
 
@@ -521,6 +592,7 @@ using namespace toist;
 
 extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (skip_gemm()) return TOIST_OK;
   TOIST_REQUIRE(d != nullptr, "toist_gemm: null descriptor");
   TOIST_REQUIRE(d->mode >= 0 && d->mode <= 2, "toist_gemm: bad mode %d", d->mode);
   TOIST_REQUIRE(d->out != nullptr && d->a.ptr != nullptr && d->b.ptr != nullptr, "toist_gemm: null tensor");
@@ -584,6 +656,10 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   const int n_tiles = (int)ceil_div(d->n_cols, bn);
   kp.n_tiles = n_tiles;
 
+  // epilogue flavour: fp32 outputs without residual / mask / aux take the compact direct path, everything unusual the
+  // generic one; aligned bf16 outputs are switched to the TMA path below
+  kp.epi = (d->out_dtype == TOIST_F32 && d->res == nullptr && d->mask == nullptr && d->aux == nullptr &&
+            d->act != TOIST_ACT_GELU) ? 1 : 2;
   CUtensorMap maps[5];
   memset(maps, 0, sizeof(maps));
   CUtensorMap& ma = maps[0];
@@ -593,14 +669,14 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   if (d->mode != TOIST_GEMM_WGRAD) {
     // bf16 outputs go through the shared-memory / TMA epilogue (full-line stores, res / mask tiles by TMA load)
     if (vec && d->out_dtype == TOIST_BF16 && (d->res == nullptr || d->res_dtype == TOIST_BF16) && d->aux == nullptr &&
-        !d->accumulate) {
+        !d->accumulate && d->row_scale == nullptr && (d->act == TOIST_ACT_NONE || d->act == TOIST_ACT_RELU)) {
       const int64_t odim[4] = {d->n_cols, d->ext_x, d->ext_y, d->ext_n};
       const int64_t ostr[4] = {1, d->out_sx, d->out_sy, d->out_sn};
       const uint32_t obox[4] = {64, (uint32_t)d->tile_x, (uint32_t)d->tile_y, (uint32_t)d->tile_n};
       if ((rc = encode_tmap_bf16_4d(&maps[2], d->out, odim, ostr, obox, ones)) != TOIST_OK) return rc;
       if (d->res && (rc = encode_tmap_bf16_4d(&maps[3], d->res, odim, ostr, obox, ones)) != TOIST_OK) return rc;
       if (d->mask && (rc = encode_tmap_bf16_4d(&maps[4], d->mask, odim, ostr, obox, ones)) != TOIST_OK) return rc;
-      kp.tma_epi = 1;
+      kp.epi = 0;
     }
     TOIST_REQUIRE(tile_rows == kBM, "toist_gemm: FWD/DGRAD pixel tile must hold 128 rows (got %d)", tile_rows);
     TOIST_REQUIRE(d->k_per_tap >= 1, "toist_gemm: k_per_tap must be positive");

@@ -33,4 +33,7 @@ int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4],
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// measurement hook (toist_debug_skip_gemm): when set, toist_gemm validates nothing and launches nothing
+bool skip_gemm();
+
 }  // namespace toist

@@ -286,6 +286,13 @@ class GraphCache:
         return outputs
 
 
+def _numel(shape) -> int:
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
 def _sig(tensors) -> tuple:
     return tuple(None if t is None else (tuple(t.shape), t.dtype, tuple(t.stride())) for t in tensors)
 
@@ -321,11 +328,18 @@ class StageFn(torch.autograd.Function):
         saved = _load(ctx)
         needs = tuple(ctx.needs_input_grad[2: 2 + ctx.n_in])
         gouts = [None if g is None else g.contiguous() for g in gouts]
+        dev = next((g.device for g in gouts if g is not None), None)
+        numel = sum((_numel(shp) + 63) // 64 * 64 for n, shp in zip(c.stage.names, c.stage.shapes) if n in c.req)
+
+        def body(*g):
+            with Bk.zero_arena(numel, dev):
+                return spec.bwd(c, saved, needs, *g)
+
         if c.graphs is None:
-            gin, grads = spec.bwd(c, saved, needs, *gouts)
+            gin, grads = body(*gouts)
         else:
             key = ("bwd", ctx.fkey, needs, _sig(gouts))
-            gin, grads = c.graphs.run(key, lambda *g: spec.bwd(c, saved, needs, *g), gouts)
+            gin, grads = c.graphs.run(key, body, gouts)
         return (None, None) + tuple(gin) + _grads_for(c.stage.names, grads, c.stage.shapes)
 
 
@@ -454,7 +468,7 @@ def text_bwd(c: Call, saved, needs, dout: torch.Tensor):
     bufs = []
     for nm in names:
         if (pre + nm) in c.req:
-            t = torch.zeros_like(e[nm], dtype=torch.float32)
+            t = Bk._zeros(tuple(e[nm].shape), e[nm].device)
             grads[pre + nm] = t
             bufs.append(t)
         else:
