@@ -180,6 +180,11 @@ typedef struct toist_prep_item {
 int toist_weight_prep(const void* items_dev, int32_t n_items, int32_t total_blocks, void* stream);
 int toist_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 int toist_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* nn.Dropout: out[i] = keep(i) ? x[i] / (1 - p) : 0 (+ res[i]); keep(i) is a counter-based hash of (seed[0] on the
+ * device, site, i), so the backward pass re-derives the mask by calling this again on the upstream gradient.
+ * dtype TOIST_BF16 | TOIST_F32 for x, res and out; out may alias x. */
+int toist_dropout(const void* x, const void* res, void* out, int64_t n, int32_t dtype, float p, const uint64_t* seed,
+                  uint32_t site, void* stream);
 /* dst[r, 0:ld] = bf16(src[r, 0:n]), zero padded (rows narrower than 16 bytes cannot be described to TMA) */
 int toist_cast_pad_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n, int32_t ld, void* stream);
 int toist_add_bf16(const void* a, const void* b, const void* c /* may be null */, void* out, int64_t n, void* stream);
@@ -217,10 +222,15 @@ int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const
 int toist_l2norm_fwd(const float* x, float* y, float* nrm, int64_t rows, int32_t n, float eps, void* stream);
 int toist_l2norm_bwd(const float* dy, const float* y, const float* nrm, float* dx, int64_t rows, int32_t n,
                      void* stream);
-int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* probs, int64_t rows, int32_t sk,
-                           int32_t ld_s, int32_t ld_p, int32_t rows_per_batch, void* stream);
+/* probs_dropped (may be null): dropout(probs) with probability p_drop, the operand of the PV product in training
+ * (nn.MultiheadAttention dropout on the attention weights); the mask is a counter-based hash of (seed[0], site, index)
+ * and is regenerated, never stored, by toist_attn_softmax_bwd when it is given the same seed / site. */
+int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* probs, void* probs_dropped,
+                           int64_t rows, int32_t sk, int32_t ld_s, int32_t ld_p, int32_t rows_per_batch, float p_drop,
+                           const uint64_t* seed, uint32_t site, void* stream);
 int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores, int64_t rows, int32_t sk,
-                           int32_t ld_s, int32_t ld_p, float scale, void* stream);
+                           int32_t ld_s, int32_t ld_p, float scale, float p_drop, const uint64_t* seed, uint32_t site,
+                           void* stream);
 int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t batch, int32_t h, int32_t w,
                    int32_t num_pos_feats, float temperature, void* stream);
 /* ids [batch, len]; rows of out / pos_ids / dx are b*len + l, or l*batch + b when seq_first != 0 */

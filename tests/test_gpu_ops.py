@@ -155,13 +155,15 @@ def test_attn_softmax(K):
 
     L = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(L.toist_attn_softmax_fwd(s.data_ptr(), km.data_ptr(), p.data_ptr(), b * h * sq, sk, ld, ld, h * sq, st))
+    _lib.check(L.toist_attn_softmax_fwd(s.data_ptr(), km.data_ptr(), p.data_ptr(), None, b * h * sq, sk, ld, ld, h * sq,
+                                        0.0, None, 0, st))
     ref = s[..., :sk].masked_fill(km.bool()[:, None, None, :], float("-inf")).softmax(-1)
     assert rel_err(p[..., :sk].float(), ref) < 3e-3
     assert bool((p[..., sk:] == 0).all())
     dp = rn(b, h, sq, ld)
     ds = torch.empty_like(p)
-    _lib.check(L.toist_attn_softmax_bwd(dp.data_ptr(), p.data_ptr(), ds.data_ptr(), b * h * sq, sk, ld, ld, 0.25, st))
+    _lib.check(L.toist_attn_softmax_bwd(dp.data_ptr(), p.data_ptr(), ds.data_ptr(), b * h * sq, sk, ld, ld, 0.25, 0.0,
+                                        None, 0, st))
     pf = p[..., :sk].float()
     refd = pf * (dp[..., :sk] - (dp[..., :sk] * pf).sum(-1, keepdim=True)) * 0.25
     assert rel_err(ds[..., :sk].float(), refd) < 4e-3

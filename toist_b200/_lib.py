@@ -93,7 +93,8 @@ def check(rc: int) -> None:
 
 
 _HEADER = Path(__file__).resolve().parent.parent / "include" / "toist_b200.h"
-_SCALARS = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "float": C.c_float, "size_t": C.c_size_t}
+_SCALARS = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "float": C.c_float, "size_t": C.c_size_t,
+            "uint32_t": C.c_uint32}
 
 
 def parse_header():

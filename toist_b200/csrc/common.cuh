@@ -196,6 +196,24 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, bool a_mn_major, b
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- counter-based RNG for dropout
+// "Squares" (Widynski 2020): four rounds of square-and-swap on a 64-bit counter times an odd key; one 32-bit output
+// per element index, reproducible in the backward pass from (seed, site, index) alone, so no mask is ever stored.
+__device__ __forceinline__ uint32_t squares32(uint64_t ctr, uint64_t key) {
+  uint64_t x = ctr * key, y = x, z = y + key;
+  x = x * x + y; x = (x >> 32) | (x << 32);
+  x = x * x + z; x = (x >> 32) | (x << 32);
+  x = x * x + y; x = (x >> 32) | (x << 32);
+  return (uint32_t)((x * x + z) >> 32);
+}
+__device__ __forceinline__ uint64_t dropout_key(const unsigned long long* seed, uint32_t site) {
+  return (seed[0] + (uint64_t)site * 0x9E3779B97F4A7C15ull) | 1ull;
+}
+// true = element survives; thr = p * 2^32
+__device__ __forceinline__ bool dropout_keep(uint64_t idx, uint64_t key, uint32_t thr) {
+  return squares32(idx, key) >= thr;
+}
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -307,6 +307,23 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __
   dst[i] = __float2bfloat16_rn(c < n ? src[r * n + c] : 0.f);
 }
 
+// out[i] = keep(i) ? x[i] / (1 - p) : 0  (+ res[i]);  nn.Dropout forward, and (with x = upstream gradient, res = null)
+// its backward.  In place (out == x) is allowed.
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ out, long long n,
+                               const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thr, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = dropout_key(seed, site);
+  float v;
+  if constexpr (sizeof(T) == 2) v = __bfloat162float(x[i]); else v = x[i];
+  v = dropout_keep((uint64_t)i, key, thr) ? v * scale : 0.f;
+  if (res != nullptr) {
+    if constexpr (sizeof(T) == 2) v += __bfloat162float(res[i]); else v += res[i];
+  }
+  if constexpr (sizeof(T) == 2) out[i] = __float2bfloat16_rn(v); else out[i] = v;
+}
+
 // dst[a, c, b] = src[a, b, c]  (fp32) — conv weight gradients come out of the WGRAD engine as [Cout][taps][Cin]
 __global__ void permute_021_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int B, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -503,6 +520,23 @@ int toist_cast_pad_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n
   TOIST_REQUIRE(src && dst && ld >= n, "toist_cast_pad_f32_bf16: bad arguments");
   if (rows * ld == 0) return TOIST_OK;
   cast_pad_kernel<<<nblk(rows * ld, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, n, ld);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_dropout(const void* x, const void* res, void* out, int64_t n, int32_t dtype, float p, const uint64_t* seed,
+                  uint32_t site, void* stream) {
+  TOIST_REQUIRE(x && out && seed, "toist_dropout: null pointer");
+  TOIST_REQUIRE(p >= 0.f && p < 1.f, "toist_dropout: p = %f out of [0, 1)", p);
+  if (n == 0) return TOIST_OK;
+  const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
+  const float scale = 1.f / (1.f - p);
+  if (dtype == TOIST_BF16)
+    dropout_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, n, (const unsigned long long*)seed, site, thr, scale);
+  else
+    dropout_kernel<float><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)x, (const float*)res, (float*)out, n, (const unsigned long long*)seed, site, thr, scale);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

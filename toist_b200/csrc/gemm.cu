@@ -564,7 +564,9 @@ static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid
 template <int BN, int MODE>
 static int dispatch_epi(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
   if constexpr (MODE == TOIST_GEMM_WGRAD) {
-    return launch_gemm<BN, MODE, 1>(maps, kp, grid, stream);
+    // weight gradients are fp32; the batched dV / dK products of attention write bf16 through the generic path
+    if (kp.epi == 1) return launch_gemm<BN, MODE, 1>(maps, kp, grid, stream);
+    return launch_gemm<BN, MODE, 2>(maps, kp, grid, stream);
   } else {
     switch (kp.epi) {
       case 0: return launch_gemm<BN, MODE, 0>(maps, kp, grid, stream);

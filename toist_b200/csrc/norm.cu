@@ -140,10 +140,14 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ attention softmax
-// scores fp32 [rows, ld_s] (already scaled) -> P bf16 [rows, ld_p]; rows = B*H*Sq, key mask [B, Sk] (1 = padded)
+// scores fp32 [rows, ld_s] (already scaled) -> P bf16 [rows, ld_p]; rows = B*H*Sq, key mask [B, Sk] (1 = padded).
+// With dropout (pd != null): P keeps the un-dropped probabilities (needed by the backward pass), pd = dropout(P) is
+// what the PV product consumes (nn.MultiheadAttention applies dropout to the attention weights).
 __global__ void attn_softmax_fwd_kernel(const float* __restrict__ s, const uint8_t* __restrict__ kmask,
-                                        __nv_bfloat16* __restrict__ p, long long rows, int Sk, int ld_s, int ld_p,
-                                        int rows_per_batch) {
+                                        __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ pd, long long rows,
+                                        int Sk, int ld_s, int ld_p, int rows_per_batch,
+                                        const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thr,
+                                        float keep_scale) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -162,6 +166,8 @@ __global__ void attn_softmax_fwd_kernel(const float* __restrict__ s, const uint8
   }
   sum = warp_sum(sum);
   __nv_bfloat16* pr = p + row * ld_p;
+  __nv_bfloat16* pdr = pd ? pd + row * ld_p : nullptr;
+  const uint64_t key = pd ? dropout_key(seed, site) : 0ull;
   for (int c = lane; c < ld_p; c += 32) {
     float o = 0.f;
     if (c < Sk) {
@@ -169,25 +175,37 @@ __global__ void attn_softmax_fwd_kernel(const float* __restrict__ s, const uint8
       o = expf(v - mx) / sum;
     }
     pr[c] = __float2bfloat16_rn(o);
+    if (pdr) pdr[c] = __float2bfloat16_rn(dropout_keep((uint64_t)(row * ld_p + c), key, thr) ? o * keep_scale : 0.f);
   }
 }
 
-// dS = P * (dP - sum_k dP * P) * scale   (dP fp32 [rows, ld_s], P bf16, dS bf16 [rows, ld_p])
+// dS = P * (dP - sum_k dP * P) * scale   (dP fp32 [rows, ld_s], P bf16, dS bf16 [rows, ld_p]); with dropout the incoming
+// gradient is w.r.t. dropout(P): dP = keep ? dPd / (1 - p) : 0 (mask regenerated from the seed)
 __global__ void attn_softmax_bwd_kernel(const float* __restrict__ dp, const __nv_bfloat16* __restrict__ p,
                                         __nv_bfloat16* __restrict__ ds, long long rows, int Sk, int ld_s, int ld_p,
-                                        float scale) {
+                                        float scale, const unsigned long long* __restrict__ seed, uint32_t site,
+                                        uint32_t thr, float keep_scale) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* dr = dp + row * ld_s;
   const __nv_bfloat16* pr = p + row * ld_p;
+  const uint64_t key = seed ? dropout_key(seed, site) : 0ull;
   float dot = 0.f;
-  for (int c = lane; c < Sk; c += 32) dot += dr[c] * __bfloat162float(pr[c]);
+  for (int c = lane; c < Sk; c += 32) {
+    float g = dr[c];
+    if (seed) g = dropout_keep((uint64_t)(row * ld_p + c), key, thr) ? g * keep_scale : 0.f;
+    dot += g * __bfloat162float(pr[c]);
+  }
   dot = warp_sum(dot);
   __nv_bfloat16* o = ds + row * ld_p;
   for (int c = lane; c < ld_p; c += 32) {
     float v = 0.f;
-    if (c < Sk) v = __bfloat162float(pr[c]) * (dr[c] - dot) * scale;
+    if (c < Sk) {
+      float g = dr[c];
+      if (seed) g = dropout_keep((uint64_t)(row * ld_p + c), key, thr) ? g * keep_scale : 0.f;
+      v = __bfloat162float(pr[c]) * (g - dot) * scale;
+    }
     o[c] = __float2bfloat16_rn(v);
   }
 }
@@ -338,22 +356,31 @@ int toist_l2norm_bwd(const float* dy, const float* y, const float* nrm, float* d
   return TOIST_OK;
 }
 
-int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* probs, int64_t rows, int32_t sk,
-                           int32_t ld_s, int32_t ld_p, int32_t rows_per_batch, void* stream) {
+int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* probs, void* probs_dropped,
+                           int64_t rows, int32_t sk, int32_t ld_s, int32_t ld_p, int32_t rows_per_batch, float p_drop,
+                           const uint64_t* seed, uint32_t site, void* stream) {
   TOIST_REQUIRE(scores && probs && rows_per_batch > 0, "toist_attn_softmax_fwd: bad arguments");
+  TOIST_REQUIRE(probs_dropped == nullptr || (seed != nullptr && p_drop > 0.f && p_drop < 1.f),
+                "toist_attn_softmax_fwd: dropout needs a seed and 0 < p < 1");
   if (rows == 0) return TOIST_OK;
+  const uint32_t thr = (uint32_t)((double)p_drop * 4294967296.0);
   attn_softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      scores, key_mask, (__nv_bfloat16*)probs, rows, sk, ld_s, ld_p, rows_per_batch);
+      scores, key_mask, (__nv_bfloat16*)probs, (__nv_bfloat16*)probs_dropped, rows, sk, ld_s, ld_p, rows_per_batch,
+      (const unsigned long long*)seed, site, thr, 1.f / (1.f - p_drop));
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
 
 int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores, int64_t rows, int32_t sk,
-                           int32_t ld_s, int32_t ld_p, float scale, void* stream) {
+                           int32_t ld_s, int32_t ld_p, float scale, float p_drop, const uint64_t* seed, uint32_t site,
+                           void* stream) {
   TOIST_REQUIRE(dprobs && probs && dscores, "toist_attn_softmax_bwd: null pointer");
   if (rows == 0) return TOIST_OK;
+  const bool drop = seed != nullptr && p_drop > 0.f;
+  const uint32_t thr = (uint32_t)((double)p_drop * 4294967296.0);
   attn_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      dprobs, (const __nv_bfloat16*)probs, (__nv_bfloat16*)dscores, rows, sk, ld_s, ld_p, scale);
+      dprobs, (const __nv_bfloat16*)probs, (__nv_bfloat16*)dscores, rows, sk, ld_s, ld_p, scale,
+      drop ? (const unsigned long long*)seed : nullptr, site, thr, 1.f / (1.f - p_drop));
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

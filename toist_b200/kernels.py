@@ -192,8 +192,8 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
 
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, mask: Optional[torch.Tensor] = None,
                  res: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dx[M,K] = (dy[M,N] @ w[N,K] + res) * (mask > 0)."""
+                 out: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+    """dx[M,K] = (alpha * dy[M,N] @ w[N,K] + res) * (mask > 0)."""
     M, N = dy.shape
     K = w.shape[1]
     assert w.shape[0] == N and dy.stride(1) == 1 and w.stride(1) == 1
@@ -201,7 +201,7 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, mask: Optional[torch.Tens
         out = torch.empty((M, K), dtype=out_dtype, device=dy.device)
     gemm(GEMM_DGRAD, t4(dy, (N, M, 1, 1), (1, dy.stride(0), 0, 0)), t4(w, (K, N, 1, 1), (1, w.stride(0), 0, 0)), out,
          ext=(M, 1, 1), tile=(128, 1, 1), n_cols=K, out_strides=(out.stride(0), 0, 0), k_per_tap=N, res=res,
-         mask=mask)
+         mask=mask, alpha=alpha)
     return out
 
 
@@ -323,6 +323,17 @@ def cast_f32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tenso
     y = out if out is not None else torch.empty_like(x, dtype=torch.float32)
     assert y.dtype == torch.float32 and y.is_contiguous() and y.numel() == x.numel()
     _ck(_L().toist_cast_bf16_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+def dropout(x: torch.Tensor, drop, res: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.Dropout with a regenerable mask: drop = (p, seed uint64-as-int64 device tensor [1], site id).
+    out = keep ? x / (1 - p) : 0 (+ res).  Calling it again on the upstream gradient is the backward pass."""
+    p, seed, site = drop
+    assert x.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == x.dtype))
+    y = out if out is not None else torch.empty_like(x)
+    _ck(_L().toist_dropout(x.data_ptr(), _ptr(res), y.data_ptr(), x.numel(), _dt(x), float(p), seed.data_ptr(),
+                           int(site), _stream()))
     return y
 
 
@@ -565,12 +576,13 @@ def _ld8(n: int) -> int:
 
 
 def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8: Optional[torch.Tensor], nhead: int,
-                  need_probs: bool = True, ctx: Optional[torch.Tensor] = None):
+                  need_probs: bool = True, ctx: Optional[torch.Tensor] = None, drop=None):
     """Multi-head attention core on packed projections.
 
     q [Sq, B, E], k [Sk, B, E], v [Sk, B, E]: bf16 views whose last dim is contiguous (they may be column slices of a
-    wider projection output).  Returns (ctx bf16 [Sq, B, E], probs bf16 [B, H, Sq, ld] or None).
-    Three launches: QK^T (fp32 scores, scaled), masked softmax, PV.
+    wider projection output).  Returns (ctx bf16 [Sq, B, E], probs) where probs is the bf16 [B, H, Sq, ld] softmax
+    (None if not needed) or, with dropout (`drop` = (p, seed, site)), the pair (softmax, dropout(softmax)).
+    Three launches: QK^T (fp32 scores, scaled), masked softmax (+ dropout), PV.
     """
     sq, b, e = q.shape
     sk = k.shape[0]
@@ -579,35 +591,46 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8
     dev = q.device
     scores = torch.empty((b, nhead, sq, ld), dtype=torch.float32, device=dev)
     with gemm_tag("attn_core"):
-        return _attention_fwd(q, k, v, key_mask_u8, nhead, need_probs, ctx, scores, sq, sk, b, e, d, ld, dev)
+        return _attention_fwd(q, k, v, key_mask_u8, nhead, need_probs, ctx, scores, sq, sk, b, e, d, ld, dev, drop)
 
 
-def _attention_fwd(q, k, v, key_mask_u8, nhead, need_probs, ctx, scores, sq, sk, b, e, d, ld, dev):
+def _attention_fwd(q, k, v, key_mask_u8, nhead, need_probs, ctx, scores, sq, sk, b, e, d, ld, dev, drop):
     gemm(GEMM_FWD, t4(q, (d, sq, nhead, b), (1, q.stride(0), d, q.stride(1))),
          t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), scores, ext=(sq, nhead, b), tile=(128, 1, 1),
          n_cols=sk, out_strides=(ld, sq * ld, nhead * sq * ld), k_per_tap=d, b_batched=True, alpha=float(d) ** -0.5)
     probs = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=dev)
+    probs_d = torch.empty_like(probs) if drop is not None else None
+    p_drop, seed, site = drop if drop is not None else (0.0, None, 0)
     with _prof("attn_core"):
-        _ck(_L().toist_attn_softmax_fwd(scores.data_ptr(), _ptr(key_mask_u8), probs.data_ptr(), b * nhead * sq, sk, ld,
-                                        ld, nhead * sq, _stream()))
+        _ck(_L().toist_attn_softmax_fwd(scores.data_ptr(), _ptr(key_mask_u8), probs.data_ptr(), _ptr(probs_d),
+                                        b * nhead * sq, sk, ld, ld, nhead * sq, float(p_drop), _ptr(seed), int(site),
+                                        _stream()))
+    pv = probs_d if probs_d is not None else probs
     if ctx is None:
         ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=dev)
     assert ctx.shape == (sq, b, e) and ctx.stride(2) == 1
-    gemm(GEMM_DGRAD, t4(probs, (sk, sq, nhead, b), (1, ld, sq * ld, nhead * sq * ld)),
+    gemm(GEMM_DGRAD, t4(pv, (sk, sq, nhead, b), (1, ld, sq * ld, nhead * sq * ld)),
          t4(v, (d, sk, nhead, b), (1, v.stride(0), d, v.stride(1))), ctx, ext=(sq, nhead, b), tile=(128, 1, 1),
          n_cols=d, out_strides=(ctx.stride(0), d, ctx.stride(1)), k_per_tap=sk, b_batched=True)
-    return ctx, (probs if need_probs else None)
+    if not need_probs:
+        return ctx, None
+    return ctx, (probs if probs_d is None else (probs, probs_d))
 
 
-def attention_bwd(dctx: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, probs: torch.Tensor,
-                  nhead: int, dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor) -> None:
-    """Backward of attention_fwd.  dq/dk/dv are bf16 outputs with the same [S, B, E] indexing as q/k/v (they may be
-    column slices of one packed gradient buffer)."""
+def attention_bwd(dctx: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, probs, nhead: int,
+                  dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, drop=None) -> None:
+    """Backward of attention_fwd (`probs` exactly as it returned them, `drop` the same triple).  dq/dk/dv are bf16
+    outputs with the same [S, B, E] indexing as q/k/v (they may be column slices of one packed gradient buffer)."""
     with gemm_tag("attn_core"):
-        _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv)
+        _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv, drop)
 
 
-def _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv) -> None:
+def _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv, drop) -> None:
+    probs_d = None
+    if isinstance(probs, (tuple, list)):
+        probs, probs_d = probs
+    pv = probs_d if probs_d is not None else probs
+    p_drop, seed, site = drop if drop is not None else (0.0, None, 0)
     sq, b, e = q.shape
     sk = k.shape[0]
     d = e // nhead
@@ -615,7 +638,7 @@ def _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv) -> None:
     dev = q.device
     sP = (1, ld, sq * ld, nhead * sq * ld)
     # dV[k] = P^T dO      (WGRAD mode: reduction over queries, batched over (h, b))
-    gemm(GEMM_WGRAD, t4(probs, (sk, sq, nhead, b), sP),
+    gemm(GEMM_WGRAD, t4(pv, (sk, sq, nhead, b), sP),
          t4(dctx, (d, sq, nhead, b), (1, dctx.stride(0), d, dctx.stride(1))), dv, ext=(sq, 1, 1), tile=(64, 1, 1),
          n_cols=d, m_rows=sk, out_strides=(dv.stride(0), d, dv.stride(1)), batch=(nhead, b))
     # dP = dO V^T
@@ -626,7 +649,7 @@ def _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv) -> None:
     ds = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=dev)
     with _prof("attn_core"):
         _ck(_L().toist_attn_softmax_bwd(dp.data_ptr(), probs.data_ptr(), ds.data_ptr(), b * nhead * sq, sk, ld, ld,
-                                        float(d) ** -0.5, _stream()))
+                                        float(d) ** -0.5, float(p_drop), _ptr(seed), int(site), _stream()))
     # dQ = dS K   (DGRAD mode: B = K is MN-major, reduction over keys)
     gemm(GEMM_DGRAD, t4(ds, (sk, sq, nhead, b), sP), t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), dq,
          ext=(sq, nhead, b), tile=(128, 1, 1), n_cols=d, out_strides=(dq.stride(0), d, dq.stride(1)), k_per_tap=sk,
