@@ -185,7 +185,7 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    args = make_args("resnet101", device="cuda", dropout=0.0)
+    args = make_args("resnet101", device="cuda", dropout=a.dropout)
     torch.manual_seed(0)
     model, criterion, _, weight_dict = build_model(args)
     model.to(dev).train()
@@ -322,7 +322,7 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": 0.0,
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": a.dropout,
                        "cuda_graphs": not a.no_graphs,
                        "l2": "320 MB buffer rewritten between steps (> 126 MB L2)",
                        "parallelism": f"dp{world}" + (" (DDP bucketed NCCL all-reduce)" if world > 1 else "")},
@@ -343,6 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="transformer dropout (reference default 0.1, main.py:137)")
     ap.add_argument("--no-graphs", action="store_true", help="issue every kernel launch from Python (no CUDA graphs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)

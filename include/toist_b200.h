@@ -241,6 +241,45 @@ int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, co
                         float* dpos, float* dtype0, int32_t batch, int32_t len, int32_t dim, int32_t seq_first,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Mask branch of DETRsegm (reference models/segmentation.py:157-241, 244-273; models/mdetr.py:827-853).
+ * Maps are NHWC bf16 [n_maps = B*Q, H, W, C]; the 3x3 / 1x1 convolutions run on toist_gemm.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* x0[(b*Q+q), pix, :] = concat(src_proj[pix, b, :dim], attn[b, :, q, pix])   (MaskHeadSmallConv input,
+ * segmentation.py:205-207); src_proj bf16 [hw, B, dim], attn bf16 [B, n_heads, Q, ld_attn] */
+int toist_mask_input(const void* src_proj, const void* attn, void* x0, int32_t batch, int32_t n_queries, int32_t hw,
+                     int32_t dim, int32_t n_heads, int32_t ld_attn, void* stream);
+/* dsrc_proj (bf16, may be null) = sum over queries; dattn fp32 [B, n_heads, Q, ld_attn] */
+int toist_mask_input_bwd(const void* dx0, void* dsrc_proj, float* dattn, int32_t batch, int32_t n_queries, int32_t hw,
+                         int32_t dim, int32_t n_heads, int32_t ld_attn, void* stream);
+/* a = relu(GroupNorm(z)) with `groups` groups (torch.nn.GroupNorm(8, C) + F.relu, segmentation.py:209-240);
+ * mean / rstd [n_maps, groups] are outputs kept for the backward pass */
+int toist_groupnorm_relu_fwd(const void* z, const float* gamma, const float* beta, void* a, float* mean, float* rstd,
+                             int32_t n_maps, int32_t hw, int32_t channels, int32_t groups, float eps, void* stream);
+/* dz from da; dgamma / dbeta accumulate (may be null together); scratch: 2 * n_maps * groups floats */
+int toist_groupnorm_relu_bwd(const void* da, const void* z, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, void* dz, float* dgamma, float* dbeta, float* scratch, int32_t n_maps,
+                             int32_t hw, int32_t channels, int32_t groups, void* stream);
+/* out = fpn[map / n_queries] + nearest_upsample(xs)   (cur_fpn + F.interpolate(x, size), segmentation.py:217-220) */
+int toist_upsample_add(const void* xs, const void* fpn, void* out, int32_t n_maps, int32_t n_queries, int32_t out_h,
+                       int32_t out_w, int32_t in_h, int32_t in_w, int32_t channels, void* stream);
+/* dxs = window sums of dout; dfpn (may be null) = sum over the queries of an image */
+int toist_upsample_add_bwd(const void* dout, void* dxs, void* dfpn, int32_t n_maps, int32_t n_queries, int32_t out_h,
+                           int32_t out_w, int32_t in_h, int32_t in_w, int32_t channels, void* stream);
+/* loss_masks (mdetr.py:827-853): bilinear upsample (align_corners = false) of the matched predictions to the target
+ * size fused with sigmoid focal (alpha .25, gamma 2) and dice.  pred_masks fp32 [B, Q, mh, mw]; tgt_masks uint8
+ * [B, t_max, th, tw]; match_q int32 [B, t_max]; sums [B, t_max, 4] scratch kept for the backward pass;
+ * out[0] = loss_mask, out[1] = loss_dice (both already divided by num_boxes[0]) */
+int toist_mask_loss_fwd(const float* pred_masks, const uint8_t* tgt_masks, const int32_t* match_q,
+                        const int32_t* tgt_count, const float* num_boxes, float* sums, float* out, int32_t batch,
+                        int32_t n_queries, int32_t t_max, int32_t mask_h, int32_t mask_w, int32_t tgt_h, int32_t tgt_w,
+                        void* stream);
+/* dpred [B, Q, mh, mw] = gout[0] * d loss_mask + gout[1] * d loss_dice (gout on the device) */
+int toist_mask_loss_bwd(const float* pred_masks, const uint8_t* tgt_masks, const int32_t* match_q,
+                        const int32_t* tgt_count, const float* sums, const float* num_boxes, const float* gout,
+                        float* dpred, int32_t batch, int32_t n_queries, int32_t t_max, int32_t mask_h, int32_t mask_w,
+                        int32_t tgt_h, int32_t tgt_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,18 +84,6 @@ def test_two_phase_protocol_and_autograd_link():
     assert torch.isfinite(total)
 
 
-def test_training_mode_dropout_is_reported_not_silently_skipped():
-    from toist_b200.models import build_model
-    from toist_b200.synth import make_args, make_batch
-    from toist_b200.util.misc import NestedTensor
-
-    model, _, _, _ = build_model(make_args("resnet50", dropout=0.1))
-    model.cuda().train()
-    images, mask, captions, _, _ = make_batch(1, 64, 8)
-    with pytest.raises(NotImplementedError):
-        model(NestedTensor(images.cuda(), mask.cuda()), captions, encode_and_save=True)
-
-
 def test_cuda_graph_replay_matches_eager():
     """The graph-captured stages reproduce the eager launch sequence bit for bit, step after step."""
     from toist_b200.models import build_model
@@ -109,6 +97,7 @@ def test_cuda_graph_replay_matches_eager():
 
     def step(b):
         images, mask, captions, targets, pm = b
+        torch.manual_seed(int(images[0, 0, 0, 0].abs() * 1e6))  # same dropout seed for the eager and the graph run
         s = NestedTensor(images.cuda(), mask.cuda())
         model.zero_grad(set_to_none=True)
         mc = model(s, captions, encode_and_save=True)

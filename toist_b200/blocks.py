@@ -64,6 +64,40 @@ def _zeros(shape, dev):
     return torch.zeros(shape, dtype=torch.float32, device=dev)
 
 
+class Drop:
+    """Dropout context of one block: probability, device seed tensor and the block's first site id.  `site(k)` is the
+    (p, seed, site) triple of the k-th dropout application inside the block; forward and backward use the same k."""
+
+    __slots__ = ("p", "seed", "base")
+
+    def __init__(self, p: float, seed: torch.Tensor, base: int):
+        self.p, self.seed, self.base = float(p), seed, int(base)
+
+    def site(self, k: int):
+        return (self.p, self.seed, self.base + k)
+
+    @property
+    def keep_scale(self) -> float:
+        return 1.0 / (1.0 - self.p)
+
+
+def _site(drop: Optional["Drop"], k: int):
+    return None if drop is None else drop.site(k)
+
+
+def lin_drop_res(x, wt, bias, res, drop_site):
+    """res + dropout(linear(x)): the residual branches of the transformer layers (dropout1/2/3/4, HF hidden dropout)."""
+    if drop_site is None:
+        return K.linear_fwd(x, wt, bias, res=res)
+    y = K.linear_fwd(x, wt, bias)
+    return K.dropout(y, drop_site, res=res, out=y)
+
+
+def drop_grad(ds, drop_site):
+    """Gradient w.r.t. the linear output behind `lin_drop_res` (ds = gradient of the sum)."""
+    return ds if drop_site is None else K.dropout(ds, drop_site)
+
+
 # ------------------------------------------------------------------------------------------------ linear pieces
 def lin_param_grads(g: G, req: Set[str], wname: str, bname: Optional[str], dy: torch.Tensor, x: torch.Tensor,
                     w_shape) -> None:
@@ -94,7 +128,7 @@ def ln_bwd(w: W, g: G, req: Set[str], pre: str, dy, x, mean, rstd, dy2=None, dx_
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int):
+def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int, drop_site=None):
     """nn.MultiheadAttention up to (excluding) out_proj.  xq/xk/xv: [rows, E] bf16; xq is xk -> fused q|k GEMM."""
     E = xq.shape[1]
     Wi, bi = w[pre + "in_proj_weight"], w[pre + "in_proj_bias"]
@@ -106,11 +140,13 @@ def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int):
         k2 = K.linear_fwd(xk, Wi[E: 2 * E], bi[E: 2 * E])
     v2 = K.linear_fwd(xv, Wi[2 * E:], bi[2 * E:])
     Sq, Sk = xq.shape[0] // B, xk.shape[0] // B
-    ctx, probs = K.attention_fwd(q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), key_mask, nhead)
+    ctx, probs = K.attention_fwd(q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), key_mask, nhead,
+                                 drop=drop_site)
     return ctx.view(Sq * B, E), (xq, xk, xv, q2, k2, v2, probs)
 
 
-def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int, need=(True, True, True)):
+def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int, need=(True, True, True),
+            drop_site=None):
     """Returns (dxq, dxk, dxv); for self-attention (xq is xk) dxq is the gradient of the shared input and dxk None."""
     xq, xk, xv, q2, k2, v2, probs = saved
     E = xq.shape[1]
@@ -126,7 +162,7 @@ def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int
         dk2 = torch.empty((xk.shape[0], E), dtype=BF, device=dev)
     dv2 = torch.empty((xv.shape[0], E), dtype=BF, device=dev)
     K.attention_bwd(dctx.view(Sq, B, E), q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), probs, nhead,
-                    dq2.view(Sq, B, E), dk2.view(Sk, B, E), dv2.view(Sk, B, E))
+                    dq2.view(Sq, B, E), dk2.view(Sk, B, E), dv2.view(Sk, B, E), drop=drop_site)
     wn, bn = pre + "in_proj_weight", pre + "in_proj_bias"
     if wn in req:
         dw = _zeros((3 * E, E), dev)
@@ -160,84 +196,99 @@ def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int
     return dxq, dxk, dxv
 
 
-def _ffn_fwd(w: W, x):
+def _ffn_fwd(w: W, x, drop: Optional[Drop] = None, k_hidden: int = 0, k_out: int = 1):
+    """x + dropout(linear2(dropout(relu(linear1(x))))).  The hidden dropout is applied in place, so the saved `h` is
+    zero exactly where either the ReLU or the dropout mask is zero."""
     h = K.linear_fwd(x, w["linear1.weight"], w["linear1.bias"], act=ACT_RELU)
-    s = K.linear_fwd(h, w["linear2.weight"], w["linear2.bias"], res=x)
+    if drop is not None:
+        K.dropout(h, drop.site(k_hidden), out=h)
+    s = lin_drop_res(h, w["linear2.weight"], w["linear2.bias"], x, _site(drop, k_out))
     return s, h
 
 
-def _ffn_bwd(w: W, g: G, req: Set[str], ds, x, h):
-    """ds: gradient of (x + linear2(relu(linear1(x)))); returns dx including the residual path."""
-    lin_param_grads(g, req, "linear2.weight", "linear2.bias", ds, h, w["linear2.weight"].shape)
-    dh = K.linear_dgrad(ds, w["linear2.weight"], mask=h)
+def _ffn_bwd(w: W, g: G, req: Set[str], ds, x, h, drop: Optional[Drop] = None, k_out: int = 1):
+    """ds: gradient of the FFN sum; returns dx including the residual path."""
+    dy = drop_grad(ds, _site(drop, k_out))
+    lin_param_grads(g, req, "linear2.weight", "linear2.bias", dy, h, w["linear2.weight"].shape)
+    # (h > 0) is the product of the ReLU and hidden-dropout masks; the surviving elements carry the 1/(1-p) factor
+    dh = K.linear_dgrad(dy, w["linear2.weight"], mask=h, alpha=1.0 if drop is None else drop.keep_scale)
     lin_param_grads(g, req, "linear1.weight", "linear1.bias", dh, x, w["linear1.weight"].shape)
     return K.linear_dgrad(dh, w["linear1.weight"], res=ds)
 
 
 # ------------------------------------------------------------------------------------------------ encoder layer
-def encoder_layer_fwd(w: W, x, pos, key_mask, nhead: int, B: int):
-    """models/transformer.py:290-304 (post-norm).  x, pos [S*B, E] bf16."""
+def encoder_layer_fwd(w: W, x, pos, key_mask, nhead: int, B: int, drop: Optional[Drop] = None):
+    """models/transformer.py:290-304 (post-norm).  x, pos [S*B, E] bf16.  Dropout sites (training): 0 attention
+    weights, 1 dropout1, 2 FFN hidden, 3 dropout2."""
     xp = K.add_bf16(x, pos)
-    ctx, sv = mha_fwd(w, "self_attn.", xp, xp, x, key_mask, nhead, B)
-    s1 = K.linear_fwd(ctx, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], res=x)
+    ctx, sv = mha_fwd(w, "self_attn.", xp, xp, x, key_mask, nhead, B, _site(drop, 0))
+    s1 = lin_drop_res(ctx, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], x, _site(drop, 1))
     x1, _, m1, r1 = ln_fwd(w, "norm1.", s1, 1e-5)
-    s2, h = _ffn_fwd(w, x1)
+    s2, h = _ffn_fwd(w, x1, drop, 2, 3)
     x2, _, m2, r2 = ln_fwd(w, "norm2.", s2, 1e-5)
     return x2, (sv, ctx, s1, m1, r1, x1, h, s2, m2, r2)
 
 
-def encoder_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int):
+def encoder_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, drop: Optional[Drop] = None):
     sv, ctx, s1, m1, r1, x1, h, s2, m2, r2 = saved
     ds2 = ln_bwd(w, g, req, "norm2.", dy, s2, m2, r2)
-    dx1 = _ffn_bwd(w, g, req, ds2, x1, h)
+    dx1 = _ffn_bwd(w, g, req, ds2, x1, h, drop, 3)
     ds1 = ln_bwd(w, g, req, "norm1.", dx1, s1, m1, r1)
-    lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", ds1, ctx,
+    dy1 = drop_grad(ds1, _site(drop, 1))
+    lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", dy1, ctx,
                     w["self_attn.out_proj.weight"].shape)
-    dctx = K.linear_dgrad(ds1, w["self_attn.out_proj.weight"])
-    dxp, _, dxv = mha_bwd(w, g, req, "self_attn.", dctx, sv, nhead, B)
+    dctx = K.linear_dgrad(dy1, w["self_attn.out_proj.weight"])
+    dxp, _, dxv = mha_bwd(w, g, req, "self_attn.", dctx, sv, nhead, B, drop_site=_site(drop, 0))
     return K.add_bf16(ds1, dxp, dxv)  # residual + (q,k) path + v path; pos carries no gradient (sine embedding)
 
 
 # ------------------------------------------------------------------------------------------------ decoder layer
-def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: int):
-    """models/transformer.py:362-408 (post-norm; the text cross-attention is disabled in the reference)."""
+def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: int, drop: Optional[Drop] = None):
+    """models/transformer.py:362-408 (post-norm; the text cross-attention is disabled in the reference).  Dropout
+    sites: 0 self-attention weights, 1 dropout1, 2 cross-attention weights, 3 dropout3, 4 FFN hidden, 5 dropout4."""
     tq = K.add_bf16(tgt, qpos)
-    ctx1, sv1 = mha_fwd(w, "self_attn.", tq, tq, tgt, None, nhead, B)
-    s1 = K.linear_fwd(ctx1, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], res=tgt)
+    ctx1, sv1 = mha_fwd(w, "self_attn.", tq, tq, tgt, None, nhead, B, _site(drop, 0))
+    s1 = lin_drop_res(ctx1, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], tgt, _site(drop, 1))
     t1, _, m1, r1 = ln_fwd(w, "norm1.", s1, 1e-5)
     cq = K.add_bf16(t1, qpos)
-    ctx2, sv2 = mha_fwd(w, "cross_attn_image.", cq, mem_pos, mem, key_mask, nhead, B)
-    s2 = K.linear_fwd(ctx2, w["cross_attn_image.out_proj.weight"], w["cross_attn_image.out_proj.bias"], res=t1)
+    ctx2, sv2 = mha_fwd(w, "cross_attn_image.", cq, mem_pos, mem, key_mask, nhead, B, _site(drop, 2))
+    s2 = lin_drop_res(ctx2, w["cross_attn_image.out_proj.weight"], w["cross_attn_image.out_proj.bias"], t1,
+                      _site(drop, 3))
     t2, _, m2, r2 = ln_fwd(w, "norm3.", s2, 1e-5)
-    s3, h = _ffn_fwd(w, t2)
+    s3, h = _ffn_fwd(w, t2, drop, 4, 5)
     t3, _, m3, r3 = ln_fwd(w, "norm4.", s3, 1e-5)
     return t3, (sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3)
 
 
-def decoder_layer_bwd(w: W, g: G, req: Set[str], dy, dy2, saved, nhead: int, B: int, need_tgt: bool = True):
+def decoder_layer_bwd(w: W, g: G, req: Set[str], dy, dy2, saved, nhead: int, B: int, need_tgt: bool = True,
+                      drop: Optional[Drop] = None):
     """dy (+ dy2): gradient of the layer output.  Returns (d_tgt, d_qpos, d_mem_pos, d_mem)."""
     sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3 = saved
     ds3 = ln_bwd(w, g, req, "norm4.", dy, s3, m3, r3, dy2=dy2)
-    dt2 = _ffn_bwd(w, g, req, ds3, t2, h)
+    dt2 = _ffn_bwd(w, g, req, ds3, t2, h, drop, 5)
     ds2 = ln_bwd(w, g, req, "norm3.", dt2, s2, m2, r2)
-    lin_param_grads(g, req, "cross_attn_image.out_proj.weight", "cross_attn_image.out_proj.bias", ds2, ctx2,
+    dy2_ = drop_grad(ds2, _site(drop, 3))
+    lin_param_grads(g, req, "cross_attn_image.out_proj.weight", "cross_attn_image.out_proj.bias", dy2_, ctx2,
                     w["cross_attn_image.out_proj.weight"].shape)
-    dctx2 = K.linear_dgrad(ds2, w["cross_attn_image.out_proj.weight"])
-    dcq, dmem_pos, dmem = mha_bwd(w, g, req, "cross_attn_image.", dctx2, sv2, nhead, B)
+    dctx2 = K.linear_dgrad(dy2_, w["cross_attn_image.out_proj.weight"])
+    dcq, dmem_pos, dmem = mha_bwd(w, g, req, "cross_attn_image.", dctx2, sv2, nhead, B, drop_site=_site(drop, 2))
     dt1 = K.add_bf16(ds2, dcq)
     ds1 = ln_bwd(w, g, req, "norm1.", dt1, s1, m1, r1)
-    lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", ds1, ctx1,
+    dy1 = drop_grad(ds1, _site(drop, 1))
+    lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", dy1, ctx1,
                     w["self_attn.out_proj.weight"].shape)
-    dctx1 = K.linear_dgrad(ds1, w["self_attn.out_proj.weight"])
-    dtq, _, dtv = mha_bwd(w, g, req, "self_attn.", dctx1, sv1, nhead, B, need=(True, True, need_tgt))
+    dctx1 = K.linear_dgrad(dy1, w["self_attn.out_proj.weight"])
+    dtq, _, dtv = mha_bwd(w, g, req, "self_attn.", dctx1, sv1, nhead, B, need=(True, True, need_tgt),
+                          drop_site=_site(drop, 0))
     d_qpos = K.add_bf16(dcq, dtq)
     d_tgt = K.add_bf16(ds1, dtq, dtv) if need_tgt else None
     return d_tgt, d_qpos, dmem_pos, dmem
 
 
 # ------------------------------------------------------------------------------------------------ RoBERTa layer
-def roberta_layer_fwd(w: W, x, key_mask, nhead: int, B: int, eps: float):
-    """transformers RobertaLayer (post-LN BERT block, erf GELU).  x [L*B, E] bf16, rows l*B + b."""
+def roberta_layer_fwd(w: W, x, key_mask, nhead: int, B: int, eps: float, drop: Optional[Drop] = None):
+    """transformers RobertaLayer (post-LN BERT block, erf GELU).  x [L*B, E] bf16, rows l*B + b.  Dropout sites:
+    0 attention_probs_dropout, 1 attention.output.dropout, 2 output.dropout (hidden_dropout_prob)."""
     M, E = x.shape
     L = M // B
     Wqkv = w["attention.self.qkv"]
@@ -245,36 +296,39 @@ def roberta_layer_fwd(w: W, x, key_mask, nhead: int, B: int, eps: float):
     for i, nm in enumerate(("query", "key", "value")):
         K.linear_fwd(x, Wqkv[i * E:(i + 1) * E], w[f"attention.self.{nm}.bias"], out=qkv[:, i * E:(i + 1) * E])
     q3, k3, v3 = (qkv[:, i * E:(i + 1) * E].view(L, B, E) for i in range(3))
-    ctx, probs = K.attention_fwd(q3, k3, v3, key_mask, nhead)
+    ctx, probs = K.attention_fwd(q3, k3, v3, key_mask, nhead, drop=_site(drop, 0))
     ctx = ctx.view(M, E)
-    s1 = K.linear_fwd(ctx, w["attention.output.dense.weight"], w["attention.output.dense.bias"], res=x)
+    s1 = lin_drop_res(ctx, w["attention.output.dense.weight"], w["attention.output.dense.bias"], x, _site(drop, 1))
     x1, _, m1, r1 = ln_fwd(w, "attention.output.LayerNorm.", s1, eps)
     pre = torch.empty((M, w["intermediate.dense.weight"].shape[0]), dtype=BF, device=x.device)
     h = K.linear_fwd(x1, w["intermediate.dense.weight"], w["intermediate.dense.bias"], act=ACT_GELU, aux=pre)
-    s2 = K.linear_fwd(h, w["output.dense.weight"], w["output.dense.bias"], res=x1)
+    s2 = lin_drop_res(h, w["output.dense.weight"], w["output.dense.bias"], x1, _site(drop, 2))
     x2, _, m2, r2 = ln_fwd(w, "output.LayerNorm.", s2, eps)
     return x2, (x, qkv, probs, ctx, s1, m1, r1, x1, pre, h, s2, m2, r2)
 
 
-def roberta_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, need_dx: bool = True):
+def roberta_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, need_dx: bool = True,
+                      drop: Optional[Drop] = None):
     x, qkv, probs, ctx, s1, m1, r1, x1, pre, h, s2, m2, r2 = saved
     M, E = x.shape
     L = M // B
     ds2 = ln_bwd(w, g, req, "output.LayerNorm.", dy, s2, m2, r2)
-    lin_param_grads(g, req, "output.dense.weight", "output.dense.bias", ds2, h, w["output.dense.weight"].shape)
-    dh = K.linear_dgrad(ds2, w["output.dense.weight"])
+    dy2 = drop_grad(ds2, _site(drop, 2))
+    lin_param_grads(g, req, "output.dense.weight", "output.dense.bias", dy2, h, w["output.dense.weight"].shape)
+    dh = K.linear_dgrad(dy2, w["output.dense.weight"])
     dpre = K.gelu_bwd(dh, pre)
     lin_param_grads(g, req, "intermediate.dense.weight", "intermediate.dense.bias", dpre, x1,
                     w["intermediate.dense.weight"].shape)
     dx1 = K.linear_dgrad(dpre, w["intermediate.dense.weight"], res=ds2)
     ds1 = ln_bwd(w, g, req, "attention.output.LayerNorm.", dx1, s1, m1, r1)
-    lin_param_grads(g, req, "attention.output.dense.weight", "attention.output.dense.bias", ds1, ctx,
+    dy1 = drop_grad(ds1, _site(drop, 1))
+    lin_param_grads(g, req, "attention.output.dense.weight", "attention.output.dense.bias", dy1, ctx,
                     w["attention.output.dense.weight"].shape)
-    dctx = K.linear_dgrad(ds1, w["attention.output.dense.weight"])
+    dctx = K.linear_dgrad(dy1, w["attention.output.dense.weight"])
     dqkv = torch.empty((M, 3 * E), dtype=BF, device=x.device)
     q3, k3, v3 = (qkv[:, i * E:(i + 1) * E].view(L, B, E) for i in range(3))
     d3 = [dqkv[:, i * E:(i + 1) * E].view(L, B, E) for i in range(3)]
-    K.attention_bwd(dctx.view(L, B, E), q3, k3, v3, probs, nhead, d3[0], d3[1], d3[2])
+    K.attention_bwd(dctx.view(L, B, E), q3, k3, v3, probs, nhead, d3[0], d3[1], d3[2], drop=_site(drop, 0))
     for i, nm in enumerate(("query", "key", "value")):
         lin_param_grads(g, req, f"attention.self.{nm}.weight", f"attention.self.{nm}.bias",
                         dqkv[:, i * E:(i + 1) * E], x, (E, E))

@@ -207,7 +207,12 @@ __device__ __forceinline__ uint32_t squares32(uint64_t ctr, uint64_t key) {
   return (uint32_t)((x * x + z) >> 32);
 }
 __device__ __forceinline__ uint64_t dropout_key(const unsigned long long* seed, uint32_t site) {
-  return (seed[0] + (uint64_t)site * 0x9E3779B97F4A7C15ull) | 1ull;
+  // splitmix64 finaliser over (seed, site): neighbouring seeds / sites give unrelated odd keys
+  uint64_t z = seed[0] + ((uint64_t)site + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z | 1ull;
 }
 // true = element survives; thr = p * 2^32
 __device__ __forceinline__ bool dropout_keep(uint64_t idx, uint64_t key, uint32_t thr) {

@@ -6,6 +6,8 @@
 // CTAs are co-resident per SM for BN <= 128 so one tile's epilogue overlaps the other's main loop.
 //
 // See include/toist_b200.h for the three traversal modes (FWD / DGRAD / WGRAD) and the epilogue contract.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -643,6 +645,10 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   const int64_t z_mult = (d->mode == TOIST_GEMM_WGRAD) ? (int64_t)kp.batch_y * kp.batch_n * kp.splits * d->n_taps : 1;
   int bn = 64;
   const int cands[3] = {256, 128, 64};
+  static const int min_ctas = []() {  // tuning knob: smallest grid for which a wider column tile is preferred
+    const char* e = getenv("TOIST_GEMM_MIN_CTAS");
+    return e ? atoi(e) : 96;
+  }();
   // short reductions are epilogue bound: keep two CTAs per SM (BN <= 128) so epilogues overlap main loops
   const int64_t k_iters = (d->mode == TOIST_GEMM_WGRAD) ? 1 << 20 : (int64_t)ceil_div(d->k_per_tap, kBK) * d->n_taps;
   for (int c = 0; c < 3; ++c) {
@@ -650,7 +656,7 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
     if (cand > 64 && d->n_cols <= cand / 2) continue;  // more than half the tile would be padding
     if (cand == 256 && k_iters < 8) continue;
     const int64_t ctas = m_tiles * ceil_div(d->n_cols, cand) * z_mult;
-    if (ctas >= 132 || cand == 64) {
+    if (ctas >= min_ctas || cand == 64) {
       bn = cand;
       break;
     }

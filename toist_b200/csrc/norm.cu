@@ -236,7 +236,8 @@ __global__ void pos_sine_kernel(const uint8_t* __restrict__ mask, float* __restr
   }
   __syncthreads();
   const float scale = 6.283185307179586f, eps = 1e-6f;
-  for (int i = threadIdx.x; i < H * W * 2 * F; i += blockDim.x) {
+  // blockIdx.y slices the output; every slice recomputes the (cheap) cumulative sums above
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < H * W * 2 * F; i += gridDim.y * blockDim.x) {
     const int c = i % (2 * F);
     const int pix = i / (2 * F);
     const int y = pix / W, x = pix % W;
@@ -395,7 +396,8 @@ int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t 
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(pos_sine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  pos_sine_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, batch, h, w,
+  const int slices = (h * w * 2 * num_pos_feats + 4095) / 4096 < 32 ? (h * w * 2 * num_pos_feats + 4095) / 4096 : 32;
+  pos_sine_kernel<<<dim3(batch, slices > 0 ? slices : 1), 256, smem, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, batch, h, w,
                                                               num_pos_feats, temperature,
                                                               (long long)batch * 2 * num_pos_feats);
   TOIST_CHECK_CUDA(cudaGetLastError());

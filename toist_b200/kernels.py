@@ -256,9 +256,9 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, shift: Optional[torch.Tensor] = N
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], *, stride: int = 1, pad: int = 0,
                mask: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx[N,H,W,Cin] = (conv_transpose(dy[N,Ho,Wo,Cout], w[Cout,kh,kw,Cin]) + res) * (mask > 0)."""
-    n, ho, wo, cout = dy.shape
+    n, ho, wo, cout = dy.shape  # dy may carry zero-padded channels beyond the filter count (16-byte TMA rows)
     cout2, kh, kw, cin = w.shape
-    assert cout == cout2 and w.is_contiguous()
+    assert cout >= cout2 and w.is_contiguous()
     h, wd = in_hw
     dx = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dy.device)
     a = _nhwc_t4(dy)
@@ -285,10 +285,10 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], *, str
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, *, stride: int = 1, pad: int = 0,
                accumulate: bool = True, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dw[Cout,kh,kw,Cin] (+)= sum_pixels dy[pix, Cout] * x[pix*stride + tap, Cin]  (fp32)."""
-    n, ho, wo, cout = dy.shape
+    n, ho, wo, cout_dy = dy.shape  # may be zero padded beyond dw's filter count
     n2, h, wd, cin = x.shape
-    cout2, kh, kw, cin2 = dw.shape
-    assert n == n2 and cout == cout2 and cin == cin2 and dw.dtype == torch.float32 and dw.is_contiguous()
+    cout, kh, kw, cin2 = dw.shape
+    assert n == n2 and cout_dy >= cout and cin == cin2 and dw.dtype == torch.float32 and dw.is_contiguous()
     taps = [(kx - pad, ky - pad, 0, (ky * kw + kx) * cin) for ky in range(kh) for kx in range(kw)]
     tile = pick_tile(wo, ho, n, 64, 64)
     ptiles = -(-wo // tile[0]) * -(-ho // tile[1]) * -(-n // tile[2])
@@ -780,3 +780,124 @@ def scale_layers2(x1, g1, x2, g2) -> torch.Tensor:
     _ck(_L().toist_scale_layers2(x1.data_ptr(), g1.data_ptr(), x2.data_ptr(), g2.data_ptr(), y.data_ptr(), L,
                                  x1.numel() // L, _stream()))
     return y
+
+
+# ------------------------------------------------------------------------------------------------ mask branch
+def attn_map_fwd(q: torch.Tensor, k: torch.Tensor, key_mask_u8: Optional[torch.Tensor], nhead: int) -> torch.Tensor:
+    """MHAttentionMap core (models/segmentation.py:262-273): softmax_k(q . k * dh**-0.5) per head, no value product.
+    q [Sq, B, E], k [Sk, B, E] bf16 -> probs bf16 [B, H, Sq, ld]."""
+    sq, b, e = q.shape
+    sk = k.shape[0]
+    d = e // nhead
+    ld = _ld8(sk)
+    scores = torch.empty((b, nhead, sq, ld), dtype=torch.float32, device=q.device)
+    gemm(GEMM_FWD, t4(q, (d, sq, nhead, b), (1, q.stride(0), d, q.stride(1))),
+         t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), scores, ext=(sq, nhead, b), tile=(128, 1, 1),
+         n_cols=sk, out_strides=(ld, sq * ld, nhead * sq * ld), k_per_tap=d, b_batched=True, alpha=float(d) ** -0.5)
+    probs = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=q.device)
+    _ck(_L().toist_attn_softmax_fwd(scores.data_ptr(), _ptr(key_mask_u8), probs.data_ptr(), None, b * nhead * sq, sk, ld,
+                                    ld, nhead * sq, 0.0, None, 0, _stream()))
+    return probs
+
+
+def attn_map_bwd(dprobs: torch.Tensor, q: torch.Tensor, k: torch.Tensor, probs: torch.Tensor, nhead: int,
+                 dq: torch.Tensor, dk: torch.Tensor) -> None:
+    """dprobs fp32 [B, H, Sq, ld] -> dq, dk (bf16, same indexing as q, k)."""
+    sq, b, e = q.shape
+    sk = k.shape[0]
+    d = e // nhead
+    ld = probs.shape[-1]
+    sP = (1, ld, sq * ld, nhead * sq * ld)
+    ds = torch.empty((b, nhead, sq, ld), dtype=torch.bfloat16, device=q.device)
+    _ck(_L().toist_attn_softmax_bwd(dprobs.data_ptr(), probs.data_ptr(), ds.data_ptr(), b * nhead * sq, sk, ld, ld,
+                                    float(d) ** -0.5, 0.0, None, 0, _stream()))
+    gemm(GEMM_DGRAD, t4(ds, (sk, sq, nhead, b), sP), t4(k, (d, sk, nhead, b), (1, k.stride(0), d, k.stride(1))), dq,
+         ext=(sq, nhead, b), tile=(128, 1, 1), n_cols=d, out_strides=(dq.stride(0), d, dq.stride(1)), k_per_tap=sk,
+         b_batched=True)
+    gemm(GEMM_WGRAD, t4(ds, (sk, sq, nhead, b), sP), t4(q, (d, sq, nhead, b), (1, q.stride(0), d, q.stride(1))), dk,
+         ext=(sq, 1, 1), tile=(64, 1, 1), n_cols=d, m_rows=sk, out_strides=(dk.stride(0), d, dk.stride(1)),
+         batch=(nhead, b))
+
+
+def mask_input(src_proj: torch.Tensor, probs: torch.Tensor, B: int, Q: int, h: int, w: int) -> torch.Tensor:
+    """src_proj bf16 [hw, B, E], probs bf16 [B, NH, Q, ld] -> x0 bf16 NHWC [B*Q, h, w, E + NH]."""
+    hw, _, E = src_proj.shape
+    NH, ld = probs.shape[1], probs.shape[-1]
+    assert src_proj.is_contiguous() and probs.is_contiguous() and hw == h * w
+    x0 = torch.empty((B * Q, h, w, E + NH), dtype=torch.bfloat16, device=src_proj.device)
+    _ck(_L().toist_mask_input(src_proj.data_ptr(), probs.data_ptr(), x0.data_ptr(), B, Q, hw, E, NH, ld, _stream()))
+    return x0
+
+
+def mask_input_bwd(dx0: torch.Tensor, B: int, Q: int, E: int, NH: int, ld: int, want_src: bool):
+    n, h, w, c = dx0.shape
+    hw = h * w
+    dsrc = torch.empty((hw, B, E), dtype=torch.bfloat16, device=dx0.device) if want_src else None
+    dattn = torch.zeros((B, NH, Q, ld), dtype=torch.float32, device=dx0.device)
+    _ck(_L().toist_mask_input_bwd(dx0.data_ptr(), _ptr(dsrc), dattn.data_ptr(), B, Q, hw, E, NH, ld, _stream()))
+    return dsrc, dattn
+
+
+def groupnorm_relu_fwd(z: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 8, eps: float = 1e-5):
+    """z NHWC bf16 [N, H, W, C] -> (a, mean [N, G], rstd [N, G])."""
+    n, h, w, c = z.shape
+    assert z.is_contiguous() and z.dtype == torch.bfloat16
+    a = torch.empty_like(z)
+    mean = torch.empty((n, groups), dtype=torch.float32, device=z.device)
+    rstd = torch.empty((n, groups), dtype=torch.float32, device=z.device)
+    _ck(_L().toist_groupnorm_relu_fwd(z.data_ptr(), gamma.data_ptr(), beta.data_ptr(), a.data_ptr(), mean.data_ptr(),
+                                      rstd.data_ptr(), n, h * w, c, groups, eps, _stream()), 2)
+    return a, mean, rstd
+
+
+def groupnorm_relu_bwd(da: torch.Tensor, z: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                       beta: torch.Tensor, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
+                       groups: int = 8) -> torch.Tensor:
+    n, h, w, c = z.shape
+    assert da.is_contiguous() and da.shape == z.shape
+    dz = torch.empty_like(z)
+    scratch = torch.empty((2, n, groups), dtype=torch.float32, device=z.device)
+    _ck(_L().toist_groupnorm_relu_bwd(da.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                      beta.data_ptr(), dz.data_ptr(), _ptr(dgamma), _ptr(dbeta), scratch.data_ptr(), n,
+                                      h * w, c, groups, _stream()), 2)
+    return dz
+
+
+def upsample_add(xs: torch.Tensor, fpn: torch.Tensor, Q: int) -> torch.Tensor:
+    """fpn[n // Q] + nearest_upsample(xs) : xs [N, h, w, C], fpn [N / Q, H, W, C] bf16 NHWC."""
+    n, h, w, c = xs.shape
+    nb, H, W, c2 = fpn.shape
+    assert c == c2 and nb * Q == n and xs.is_contiguous() and fpn.is_contiguous()
+    out = torch.empty((n, H, W, c), dtype=torch.bfloat16, device=xs.device)
+    _ck(_L().toist_upsample_add(xs.data_ptr(), fpn.data_ptr(), out.data_ptr(), n, Q, H, W, h, w, c, _stream()))
+    return out
+
+
+def upsample_add_bwd(dout: torch.Tensor, in_hw: Tuple[int, int], Q: int, want_fpn: bool):
+    n, H, W, c = dout.shape
+    h, w = in_hw
+    dxs = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dout.device)
+    dfpn = torch.empty((n // Q, H, W, c), dtype=torch.bfloat16, device=dout.device) if want_fpn else None
+    _ck(_L().toist_upsample_add_bwd(dout.data_ptr(), dxs.data_ptr(), _ptr(dfpn), n, Q, H, W, h, w, c, _stream()), 2)
+    return dxs, dfpn
+
+
+def mask_loss_fwd(pred_masks, tgt_masks_u8, match_q, tgt_count, num_boxes):
+    B, Q, mh, mw = pred_masks.shape
+    _, tmax, th, tw = tgt_masks_u8.shape
+    sums = torch.empty((B, tmax, 4), dtype=torch.float32, device=pred_masks.device)
+    out = torch.empty(2, dtype=torch.float32, device=pred_masks.device)
+    _ck(_L().toist_mask_loss_fwd(pred_masks.data_ptr(), tgt_masks_u8.data_ptr(), match_q.data_ptr(), tgt_count.data_ptr(),
+                                 num_boxes.data_ptr(), sums.data_ptr(), out.data_ptr(), B, Q, tmax, mh, mw, th, tw,
+                                 _stream()), 2)
+    return out, sums
+
+
+def mask_loss_bwd(pred_masks, tgt_masks_u8, match_q, tgt_count, sums, num_boxes, gout):
+    B, Q, mh, mw = pred_masks.shape
+    _, tmax, th, tw = tgt_masks_u8.shape
+    dpred = torch.empty_like(pred_masks)
+    _ck(_L().toist_mask_loss_bwd(pred_masks.data_ptr(), tgt_masks_u8.data_ptr(), match_q.data_ptr(), tgt_count.data_ptr(),
+                                 sums.data_ptr(), num_boxes.data_ptr(), gout.data_ptr(), dpred.data_ptr(), B, Q, tmax,
+                                 mh, mw, th, tw, _stream()))
+    return dpred

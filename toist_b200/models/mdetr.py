@@ -38,6 +38,8 @@ class ModelRuntime:
         self.bank = ShadowBank()
         self.stages: Optional[Dict[str, Stage]] = None
         self.graphs: Optional[GraphCache] = None
+        self.seed: Optional[torch.Tensor] = None  # device int64 [1]: dropout seed of the current step
+        self.dirty = True  # parameters may have moved / been reloaded since the shadow bank was built
 
     def __deepcopy__(self, memo):  # the EMA copy (main.py:322) rebuilds its own
         return ModelRuntime()
@@ -59,7 +61,8 @@ class ModelRuntime:
             "text": Stage(m, "text", pick("transformer.text_encoder.", "transformer.resizer.", exclude=("pooler.",)),
                           prefix="transformer.text_encoder.", resizer_prefix="transformer.resizer.",
                           num_layers=tcfg.num_hidden_layers, num_heads=tcfg.num_attention_heads,
-                          eps=float(tcfg.layer_norm_eps), pad_id=int(tcfg.pad_token_id)),
+                          eps=float(tcfg.layer_norm_eps), pad_id=int(tcfg.pad_token_id),
+                          resizer_p=float(tr.resizer.dropout_p)),
             "encoder": Stage(m, "encoder", pick("input_proj.", "transformer.encoder."), prefix="transformer.encoder.",
                              input_proj_prefix="input_proj.", num_layers=tr.encoder.num_layers, nhead=tr.nhead),
             "decoder": Stage(m, "decoder", pick("transformer.decoder."), prefix="transformer.decoder.",
@@ -71,12 +74,25 @@ class ModelRuntime:
         if self.stages is None:
             self.build(m)
         sig = self.bank._sig
-        self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body)
+        # full scan every 64 steps even when nothing flagged a change (e.g. a buffer edited in place by user code)
+        self.steps = getattr(self, "steps", 0) + 1
+        dirty = self.dirty or self.steps % 64 == 0
+        self.dirty = False
+        self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body, dirty)
         if self.graphs is not None and sig is not None and sig != self.bank._sig:
             self.graphs.clear()  # shadow buffers moved: captured pointers are stale
 
-    def call(self, name: str, save: bool, **kw) -> Call:
-        return Call(self.stages[name], self.bank.w, save, graphs=self.graphs, **kw)
+    def call(self, name: str, save: bool, drop_p: float = 0.0, **kw) -> Call:
+        return Call(self.stages[name], self.bank.w, save, graphs=self.graphs, drop_p=drop_p,
+                    seed=self.seed, **kw)
+
+    def new_step_seed(self, device) -> None:
+        """Draws the dropout seed of this step from torch's CPU generator (reproducible under torch.manual_seed)."""
+        s = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+        if self.seed is None or self.seed.device != device:
+            self.seed = s.to(device)
+        else:
+            self.seed.copy_(s, non_blocking=True)
 
 
 class MDETR(nn.Module):
@@ -102,12 +118,25 @@ class MDETR(nn.Module):
         self._rt = ModelRuntime()
 
     # ------------------------------------------------------------------ helpers
-    def _check_mode(self) -> None:
-        p = float(getattr(self.transformer, "dropout_p", 0.0))
-        if self.training and p > 0:
-            raise NotImplementedError(
-                "toist_b200 round 1 implements the deterministic path (model.eval() or --dropout 0); training-mode "
-                f"dropout (p={p}) is not wired into the kernels yet")
+    def _drop_probs(self):
+        """Training-mode dropout probabilities per stage (the reference's nn.Dropout modules): transformer layers
+        `--dropout` (models/transformer.py:273-283,337-353), RoBERTa its config's hidden / attention dropout, the
+        resizer 0.1 (models/transformer.py:73).  All zero in eval()."""
+        if not self.training:
+            return None
+        cfg = self.transformer.text_encoder.config
+        text_p = float(cfg.hidden_dropout_prob)
+        if abs(float(cfg.attention_probs_dropout_prob) - text_p) > 1e-12:
+            raise NotImplementedError("RoBERTa with different hidden / attention dropout probabilities")
+        return {"text": text_p, "transformer": float(self.transformer.dropout_p)}
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): parameter storage may move
+        self._rt.dirty = True
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._rt.dirty = True
+        return super().load_state_dict(*args, **kwargs)
 
     def enable_cuda_graphs(self, on: bool = True) -> "MDETR":
         """Capture each stage's forward / backward launch sequence into CUDA graphs (one per input-shape signature)
@@ -121,14 +150,18 @@ class MDETR(nn.Module):
 
     # ------------------------------------------------------------------ phase A (engine.py:63)
     def encode(self, samples: NestedTensor, captions, want_features: bool = False) -> dict:
-        self._check_mode()
         rt = self._rt
         rt.refresh(self)
         save = self._grad_wanted()
+        dp = self._drop_probs()
         images = samples.tensors
         if images.dtype != torch.float32 or not images.is_cuda:
             raise RuntimeError("toist_b200 expects fp32 CUDA images (sm_100a); there is no CPU path")
         images = images.contiguous()
+        if dp is not None:
+            rt.new_step_seed(images.device)
+        else:
+            rt.seed = None
         feats = run_stage(BACKBONE, rt.call("backbone", save), images)
         c5 = feats[-1]
         B, h, w, _ = c5.shape
@@ -141,7 +174,8 @@ class MDETR(nn.Module):
             ids = tokenized["input_ids"].contiguous()
             attn = tokenized["attention_mask"].to(torch.int64).contiguous()
             text_attention_mask = attn.ne(1)
-            text_resized = run_stage(TEXT, rt.call("text", save), ids, text_attention_mask.view(torch.uint8))[0]
+            text_resized = run_stage(TEXT, rt.call("text", save, dp["text"] if dp else 0.0), ids,
+                                     text_attention_mask.view(torch.uint8))[0]
         else:  # already encoded (models/transformer.py:139-141)
             text_attention_mask, text_resized, tokenized = captions
             attn = (~text_attention_mask).to(torch.int64).contiguous()
@@ -152,7 +186,8 @@ class MDETR(nn.Module):
         npf = self.backbone[1].num_pos_feats
         pos32, pos16 = K.pos_sine(small, npf, float(self.backbone[1].temperature), extra_rows=L)
         S = h * w + L
-        enc_out = run_stage(ENCODER, rt.call("encoder", save), c5, text_resized, pos16.view(S * B, E), key)
+        enc_out = run_stage(ENCODER, rt.call("encoder", save, dp["transformer"] if dp else 0.0), c5, text_resized,
+                            pos16.view(S * B, E), key)
         img_memory = enc_out[0]
         query_embed = self.query_embed.weight.unsqueeze(1).repeat(1, B, 1)
         memory_cache = {
@@ -175,17 +210,20 @@ class MDETR(nn.Module):
 
     # ------------------------------------------------------------------ phase B (engine.py:66)
     def decode(self, memory_cache: dict, want_hs: bool = False) -> dict:
-        self._check_mode()
         rt = self._rt
         if rt.stages is None:
             rt.refresh(self)
         save = self._grad_wanted()
+        dp = self._drop_probs()
+        if dp is not None and rt.seed is None:
+            rt.new_step_seed(memory_cache["img_memory"].device)
         cluster = bool(getattr(self.args, "cluster", False))
         mem = memory_cache["img_memory_mod"] if cluster else memory_cache["img_memory"]
         S, B, E = mem.shape
         pos16 = K.cast_bf16(memory_cache["pos_embed"].contiguous()).view(S * B, E)
         key = memory_cache["mask"].contiguous().view(torch.uint8)
-        hs = run_stage(DECODER, rt.call("decoder", save), mem, memory_cache["query_embed"], pos16, key)[0]
+        hs = run_stage(DECODER, rt.call("decoder", save, dp["transformer"] if dp else 0.0), mem,
+                       memory_cache["query_embed"], pos16, key)[0]
         res = run_stage(HEADS, rt.call("heads", save, B=B), hs, memory_cache["text_memory"])
         logits, boxes = res[0], res[1]
         out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
@@ -245,6 +283,35 @@ def _criterion_bwd(c: Call, saved, needs, gout, *unused):
 CRITERION = Spec("criterion", 9, _criterion_fwd, _criterion_bwd, nondiff=(1, 2))
 
 
+def _mask_loss_fwd(c: Call, pred_masks, tgt_masks, match_q, tgt_count, num_boxes):
+    """loss_masks (models/mdetr.py:827-853): matched predictions, bilinear upsample to the padded target size,
+    sigmoid focal + dice, fused in one pass; returns [loss_mask, loss_dice]."""
+    out, sums = K.mask_loss_fwd(pred_masks, tgt_masks, match_q, tgt_count, num_boxes)
+    return (out,), ((pred_masks, tgt_masks, match_q, tgt_count, sums, num_boxes) if c.save else None)
+
+
+def _mask_loss_bwd(c: Call, saved, needs, gout):
+    pred_masks, tgt_masks, match_q, tgt_count, sums, num_boxes = saved
+    dpred = K.mask_loss_bwd(pred_masks, tgt_masks, match_q, tgt_count, sums, num_boxes, gout.contiguous())
+    return (dpred, None, None, None, None), {}
+
+
+MASKLOSS = Spec("mask_loss", 5, _mask_loss_fwd, _mask_loss_bwd)
+
+
+def pack_target_masks(targets, t_max: int, device) -> torch.Tensor:
+    """uint8 [B, t_max, H, W]: every image's target masks padded to the largest height / width of the batch
+    (NestedTensor.from_tensor_list in the reference, models/mdetr.py:840)."""
+    H = max(int(t["masks"].shape[-2]) for t in targets)
+    W = max(int(t["masks"].shape[-1]) for t in targets)
+    out = torch.zeros((len(targets), t_max, H, W), dtype=torch.uint8, device=device)
+    for i, t in enumerate(targets):
+        m = t["masks"]
+        if m.shape[0]:
+            out[i, : m.shape[0], : m.shape[-2], : m.shape[-1]] = m.to(device=device, dtype=torch.uint8)
+    return out
+
+
 def _token_spans(tokenized, i: int, spans):
     """char span -> token span with the reference's fallbacks (models/mdetr.py:622-643)."""
     res = []
@@ -298,9 +365,10 @@ class SetCriterion(nn.Module):
         self.eos_coef = eos_coef
         self.losses = losses
         self.temperature = temperature
-        unsupported = [l for l in losses if l not in ("labels", "boxes", "cardinality", "contrastive_align")]
+        unsupported = [l for l in losses if l not in ("labels", "boxes", "cardinality", "contrastive_align", "masks")]
         self._unsupported = unsupported
         self._stage = Stage.empty("criterion")
+        self._stage_mask = Stage.empty("mask_loss")
         self._graphs: Optional[GraphCache] = None
 
     def enable_cuda_graphs(self, on: bool = True) -> "SetCriterion":
@@ -366,10 +434,23 @@ class SetCriterion(nn.Module):
         terms = [("loss_ce", 0), ("loss_bbox", 1), ("loss_giou", 2), ("cardinality_error", 3)]
         if pq is not None:
             terms.append(("loss_contrastive_align", 4))
+        mask_out = None
+        if "masks" in self.losses:  # last decoder layer only (models/mdetr.py:1013-1015)
+            assert "pred_masks" in outputs
+            pm_ = outputs["pred_masks"]
+            tgt_masks = pack_target_masks(targets, packed.t_max, dev)
+            msave = torch.is_grad_enabled() and pm_.requires_grad
+            mcall = Call(self._stage_mask, {}, msave, graphs=self._graphs)
+            mask_out = run_stage(MASKLOSS, mcall, pm_, tgt_masks, match_q[L - 1].contiguous(), packed.count, nb)[0]
         losses = {}
         for name, row in terms:
+            if name == "loss_contrastive_align" and mask_out is not None:
+                losses["loss_mask"], losses["loss_dice"] = mask_out[0], mask_out[1]
+                mask_out = None
             v = out[row, L - 1]
             losses[name] = v.detach() if row >= 3 else v
+        if mask_out is not None:
+            losses["loss_mask"], losses["loss_dice"] = mask_out[0], mask_out[1]
         if use_aux:
             for i in range(L - 1):
                 for name, row in terms:

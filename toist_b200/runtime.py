@@ -119,22 +119,24 @@ class ShadowBank:
         return ShadowBank()
 
     @staticmethod
-    def _signature(model) -> tuple:
-        ps = tuple(p.data_ptr() for p in model.parameters())
-        bs = tuple((b.data_ptr(), b._version) for b in model.buffers())
+    def _signature(params, buffers) -> tuple:
+        ps = tuple(p.data_ptr() for p in params.values())
+        bs = tuple((b.data_ptr(), b._version) for b in buffers)
         return ps + bs
 
-    def ensure(self, model, backbone_prefix: str, body) -> None:
+    def ensure(self, model, backbone_prefix: Optional[str], body, dirty: bool = True, only=None) -> None:
         """(Re)builds the bank when parameters moved (device change, load of a new module) or BN buffers changed,
-        then refreshes every shadow from its fp32 master."""
-        sig = self._signature(model)
-        if sig != self._sig:
-            self._build(model, backbone_prefix, body)
-            self._sig = sig
+        then refreshes every shadow from its fp32 master.  `dirty=False` (nothing called Module._apply or
+        load_state_dict since the last check) skips the pointer / version scan of ~1000 tensors."""
+        if dirty or self._sig is None:
+            params = {n: p for n, p in model.named_parameters() if only is None or n.startswith(only)}
+            sig = self._signature(params, list(model.buffers()) if body is not None else [])
+            if sig != self._sig:
+                self._build(params, backbone_prefix, body)
+                self._sig = sig
         self.prep.run()
 
-    def _build(self, model, backbone_prefix: str, body) -> None:
-        params = dict(model.named_parameters())
+    def _build(self, params, backbone_prefix: Optional[str], body) -> None:
         dev = next(iter(params.values())).device
         if dev.type != "cuda":
             raise RuntimeError("toist_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
@@ -142,7 +144,7 @@ class ShadowBank:
         w: Dict[str, torch.Tensor] = {}
         conv_names = set()
         # ---- backbone: conv + FrozenBatchNorm pairs
-        for conv_name, bn_name in body.conv_bn_pairs():
+        for conv_name, bn_name in (body.conv_bn_pairs() if body is not None else ()):
             conv_w = params[backbone_prefix + conv_name + ".weight"]
             bn = body.get_submodule(bn_name)
             scale = (bn.weight * (bn.running_var + 1e-5).rsqrt()).float().contiguous()  # models/backbone.py:54-57
@@ -163,7 +165,12 @@ class ShadowBank:
             if name in conv_names:
                 continue
             qkv_part = ".attention.self." in name and name.endswith(("query.weight", "key.weight", "value.weight"))
-            if p.dim() >= 2 and not qkv_part and not any(k in name for k in _EMBEDDING_KEYS):
+            if p.dim() == 4 and p.shape[2] * p.shape[3] > 1:  # biased k x k convolution (mask head): OIHW -> OHWI
+                cout, cin, kh, kw = p.shape
+                sh = torch.empty((cout, kh, kw, cin), dtype=BF, device=dev)
+                prep.add(p.detach(), sh, cout, cin * kh * kw, None, None, taps=kh * kw)
+                w[name] = sh
+            elif p.dim() >= 2 and not qkv_part and not any(k in name for k in _EMBEDDING_KEYS):
                 rows = p.shape[0]
                 cols = p.numel() // rows
                 sh = torch.empty((rows, cols), dtype=BF, device=dev)
@@ -222,16 +229,21 @@ class Call:
     """Per-invocation context handed to a Function (non-tensor argument)."""
 
     def __init__(self, stage: Stage, w: Dict[str, torch.Tensor], save: bool, graphs: "Optional[GraphCache]" = None,
-                 **kw):
+                 drop_p: float = 0.0, seed: Optional[torch.Tensor] = None, **kw):
         self.stage, self.w = stage, w
         self.req = stage.req() if save else set()
         self.save = save  # keep activations for a backward pass (some tensor upstream or here wants a gradient)
         self.graphs = graphs
+        self.drop_p = float(drop_p) if seed is not None else 0.0  # training-mode dropout probability of this stage
+        self.seed = seed  # device int64 [1]; rewritten by the host every step, read by the kernels
         self.extra = tuple(sorted(kw.items()))
         self.__dict__.update(kw)
 
     def signature(self) -> tuple:
-        return (self.stage.name, self.save, frozenset(self.req), self.extra)
+        return (self.stage.name, self.save, frozenset(self.req), self.extra, self.drop_p)
+
+    def drop(self, base: int) -> Optional[Bk.Drop]:
+        return Bk.Drop(self.drop_p, self.seed, base) if self.drop_p > 0.0 else None
 
 
 # ------------------------------------------------------------------------------------------------ CUDA graphs
@@ -337,10 +349,21 @@ class StageFn(torch.autograd.Function):
 
         if c.graphs is None:
             gin, grads = body(*gouts)
+            pg = _grads_for(c.stage.names, grads, c.stage.shapes)
         else:
             key = ("bwd", ctx.fkey, needs, _sig(gouts))
             gin, grads = c.graphs.run(key, body, gouts)
-        return (None, None) + tuple(gin) + _grads_for(c.stage.names, grads, c.stage.shapes)
+            pg = _grads_for(c.stage.names, grads, c.stage.shapes)
+            # The gradient buffers are static memory of the backward graph.  When no parameter holds a gradient yet
+            # (the usual zero_grad(set_to_none=True) loop) hand autograd fresh aliases: AccumulateGrad then adopts them
+            # without a copy.  With gradients already present (accumulation over several backward passes) the next
+            # replay would overwrite what was accumulated, so copies are returned instead.
+            if all(p.grad is None for p in c.stage.params):
+                pg = tuple(None if t is None else t.detach() for t in pg)
+            else:
+                pg = tuple(None if t is None else t.clone() for t in pg)
+            gin = tuple(None if t is None else t.detach() for t in gin)
+        return (None, None) + tuple(gin) + pg
 
 
 class Spec:
@@ -431,13 +454,19 @@ def text_fwd(c: Call, input_ids: torch.Tensor, text_mask_u8: torch.Tensor):
     x32, pos_ids = K.embed_gather(input_ids, e["word_embeddings.weight"], e["position_embeddings.weight"],
                                   e["token_type_embeddings.weight"], st.pad_id, seq_first=True)
     x, _, m0, r0 = Bk.ln_fwd(e, "LayerNorm.", x32, st.eps)
+    d_emb = c.drop(10)
+    if d_emb is not None:  # RobertaEmbeddings.dropout
+        K.dropout(x, d_emb.site(0), out=x)
     saved_layers = []
     for i in range(st.num_layers):
-        x, sv = Bk.roberta_layer_fwd(w.sub(f"encoder.layer.{i}."), x, text_mask_u8, st.num_heads, B, st.eps)
+        x, sv = Bk.roberta_layer_fwd(w.sub(f"encoder.layer.{i}."), x, text_mask_u8, st.num_heads, B, st.eps,
+                                     c.drop(100 + 8 * i))
         saved_layers.append(sv if c.save else None)
     r = WView(c.w, st.resizer_prefix)
     y = K.linear_fwd(x, r["fc.weight"], r["fc.bias"], out_dtype=torch.float32)
     _, out, m1, r1 = Bk.ln_fwd(r, "layer_norm.", y, 1e-12, want_bf16=False, want_f32=True)
+    if c.seed is not None and st.resizer_p > 0:  # FeatureResizer.dropout (models/transformer.py:491)
+        K.dropout(out, (st.resizer_p, c.seed, 20), out=out)
     saved = (input_ids, pos_ids, x32, m0, r0, tuple(saved_layers), x, y, m1, r1) if c.save else None
     return (out.view(L, B, -1),), saved
 
@@ -451,6 +480,8 @@ def text_bwd(c: Call, saved, needs, dout: torch.Tensor):
     rp = st.resizer_prefix
     r = WView(c.w, rp)
     d = dout.contiguous().view(L * B, -1)
+    if c.seed is not None and st.resizer_p > 0:
+        d = K.dropout(d, (st.resizer_p, c.seed, 20))
     dy = Bk.ln_bwd(r, GView(grads, rp), RView(c.req, rp), "layer_norm.", d, y, m1, r1)
     Bk.lin_param_grads(GView(grads, rp), RView(c.req, rp), "fc.weight", "fc.bias", dy, x_last, r["fc.weight"].shape)
     body_req = any(n.startswith(st.prefix) for n in c.req)
@@ -460,7 +491,10 @@ def text_bwd(c: Call, saved, needs, dout: torch.Tensor):
     for i in range(st.num_layers - 1, -1, -1):
         pre = st.prefix + f"encoder.layer.{i}."
         dx = Bk.roberta_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dx, saved_layers[i],
-                                  st.num_heads, B)
+                                  st.num_heads, B, drop=c.drop(100 + 8 * i))
+    d_emb = c.drop(10)
+    if d_emb is not None:
+        dx = K.dropout(dx, d_emb.site(0))
     pre = st.prefix + "embeddings."
     e = WView(c.w, pre)
     dx32 = Bk.ln_bwd(e, GView(grads, pre), RView(c.req, pre), "LayerNorm.", dx, x32, m0, r0, dx_dtype=torch.float32)
@@ -497,7 +531,8 @@ def encoder_fwd(c: Call, feat: torch.Tensor, text: torch.Tensor, pos16: torch.Te
     x = src
     saved_layers = []
     for i in range(st.num_layers):
-        x, sv = Bk.encoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), x, pos16, key_mask, st.nhead, B)
+        x, sv = Bk.encoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), x, pos16, key_mask, st.nhead, B,
+                                     c.drop(1000 + 8 * i))
         saved_layers.append(sv if c.save else None)
     mem = K.cast_f32(x).view(S, B, E)
     saved = (feat, (L, B, E), tuple(saved_layers)) if c.save else None
@@ -513,7 +548,8 @@ def encoder_bwd(c: Call, saved, needs, dmem, dsrc_proj=None):
     d = K.cast_bf16(dmem.contiguous().view(-1, E))
     for i in range(st.num_layers - 1, -1, -1):
         pre = st.prefix + f"layers.{i}."
-        d = Bk.encoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), d, saved_layers[i], st.nhead, B)
+        d = Bk.encoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), d, saved_layers[i], st.nhead, B,
+                                 c.drop(1000 + 8 * i))
     d_img = d[: hw * B]
     if dsrc_proj is not None:  # the mask head reads src_proj (models/segmentation.py:77-78)
         d_img = K.add_bf16(d_img, dsrc_proj.contiguous().view(-1, E))
@@ -542,7 +578,7 @@ def decoder_fwd(c: Call, mem32: torch.Tensor, qpos32: torch.Tensor, pos16: torch
     saved_layers = []
     for i in range(st.num_layers):
         tgt, sv = Bk.decoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), tgt, qpos, mem, mem_pos, key_mask,
-                                       st.nhead, B)
+                                       st.nhead, B, c.drop(2000 + 8 * i))
         _, _, m, r = K.layernorm_fwd(tgt, nw["weight"], nw["bias"], 1e-5, out16=hs[i])
         saved_layers.append((sv, tgt, m, r) if c.save else None)
     saved = ((S, B, E, Q), tuple(saved_layers)) if c.save else None
@@ -561,7 +597,7 @@ def decoder_bwd(c: Call, saved, needs, dhs):
         dy = Bk.ln_bwd(WView(c.w, np_), GView(grads, np_), RView(c.req, np_), "", dhs[i], t3, m, r)
         pre = st.prefix + f"layers.{i}."
         d_tgt, dq, dmp, dm = Bk.decoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dy, d_next,
-                                                  sv, st.nhead, B, need_tgt=i > 0)
+                                                  sv, st.nhead, B, need_tgt=i > 0, drop=c.drop(2000 + 8 * i))
         d_next = d_tgt
         d_qpos = dq if d_qpos is None else K.add_bf16(d_qpos, dq)
         d_mem = K.add_bf16(dmp, dm) if d_mem is None else K.add_bf16(d_mem, dmp, dm)
