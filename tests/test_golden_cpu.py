@@ -75,6 +75,48 @@ def test_oracle_model_reproduces_reference_golden(config1_gold):
             assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist(), l
 
 
+def test_oracle_mask_branch_reproduces_reference_golden():
+    """DETRsegm mask branch + mask losses (BASELINE config 3 recipe, small): same-seed initialisation is bit-identical
+    to the reference's and the oracle reproduces pred_masks, the six loss terms and the mask-branch gradients."""
+    from toist_b200.models import build_model
+
+    g = torch.load(GOLD / "config3_r50_segm_small.pt", weights_only=False)
+    torch.set_num_threads(max(torch.get_num_threads(), 4))
+    torch.manual_seed(0)
+    args = make_args("resnet50", device="cpu", masks=True, mask_model="smallconv", frozen_weights="unused",
+                     aux_loss=False, contrastive_align_loss=False)
+    model, _, _, weight_dict = build_model(args)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert set(sd) == set(g["state_checksum"])
+    for k, v in g["state_checksum"].items():
+        assert abs(float(sd[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), k
+    assert dict(weight_dict) == g["weight_dict"]
+    trainable = sorted(n for n, p in model.named_parameters() if p.requires_grad)
+    assert trainable == sorted(g["grads"])
+    b = g["batch"]
+    images, mask, captions, targets, pm = make_batch(b["batch"], b["size"], b["tokens"], seed=b["seed"], pad=b["pad"],
+                                                     masks=True)
+    tokd = model.detr.transformer.tokenizer(captions)
+    cfg = O.Config(backbone="resnet50", prefix="detr.", aux_loss=False, contrastive_align_loss=False)
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    mc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+    out = O.decode(sd, cfg, mc)
+    out["pred_masks"] = O.decode_masks(sd, cfg, mc, out)
+    losses, idx = O.criterion(cfg, out, tokd, targets, pm, masks=True)
+    assert rel_err(out["pred_masks"], g["pred_masks"]) < 1e-5
+    for k, v in g["losses"].items():
+        assert abs(float(losses[k]) - v) <= 2e-4 * max(1.0, abs(v)), k
+    for (r0, c0), (r1, c1) in zip(idx[0], g["indices"]):
+        assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist()
+    sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict).backward()
+    for k in trainable:
+        if k == "bbox_attention.k_linear.bias":  # softmax is shift invariant: this gradient is rounding noise around 0
+            assert float(sd[k].grad.abs().max()) < 1e-12
+            continue
+        assert rel_err(sd[k].grad, g["grads"][k]) < 1e-4, k
+
+
 def test_c_abi_library_loads_and_exports_every_declared_symbol():
     from toist_b200 import _lib
 

@@ -82,6 +82,38 @@ def test_losses_and_indices_match_reference(ref):
             assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist(), l
 
 
+def test_segmentation_branch_matches_reference():
+    """DETRsegm (models/segmentation.py:40-168) + loss_masks (models/mdetr.py:827-853): the recipe of BASELINE config 3
+    (`--mask_model smallconv --frozen_weights --no_aux_loss --no_contrastive_align_loss`) on a small ragged batch."""
+    tok = CharTokenizer()
+    models = shims.load_reference(tok)
+    args = shims.reference_args(["--backbone", "resnet50", "--mask_model", "smallconv", "--frozen_weights", "unused",
+                                 "--no_aux_loss", "--no_contrastive_align_loss"])
+    torch.manual_seed(0)
+    model, criterion, _, weight_dict = models.build_model(args)
+    model.eval()
+    from util.misc import NestedTensor
+
+    images, mask, captions, targets, pm = make_batch(2, 128, 8, seed=7, pad=True, masks=True)
+    with torch.no_grad():
+        rmc = model(NestedTensor(images, mask), captions, encode_and_save=True)
+        rout = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=rmc)
+        rl = criterion(rmc, rout, targets, pm, None)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cfg = O.Config(backbone="resnet50", prefix="detr.", aux_loss=False, contrastive_align_loss=False)
+    tokd = tok(captions)
+    with torch.no_grad():
+        mc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+        out = O.decode(sd, cfg, mc)
+        out["pred_masks"] = O.decode_masks(sd, cfg, mc, out)
+        losses, _ = O.criterion(cfg, out, tokd, targets, pm, masks=True)
+    assert out["pred_masks"].shape == rout["pred_masks"].shape == (2, 100, 32, 32)
+    assert rel_err(out["pred_masks"], rout["pred_masks"]) < 1e-5
+    assert set(losses) == set(rl)
+    for k, v in rl.items():
+        assert abs(float(losses[k]) - float(v)) <= 2e-4 * max(1.0, abs(float(v))), (k, float(losses[k]), float(v))
+
+
 def test_matcher_cost_matches_reference_ops(ref):
     from util import box_ops  # reference
 

@@ -54,13 +54,14 @@ __global__ void mask_input_bwd_kernel(const __nv_bfloat16* __restrict__ dx0, __n
 // ------------------------------------------------------------------------------------------------ GroupNorm + ReLU
 // z NHWC bf16 [N, HW, C]; one CTA per map.  stats[n, g] = (mean, rstd) over the C/G channels x HW pixels of group g.
 constexpr int kGNMaxC = 512;
+constexpr int kGNMaxThreads = 256;
 
 __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ mean,
                                        float* __restrict__ rstd, int HW, int C, int G, float eps) {
+  // deterministic: per-thread partials -> fixed-order sum per channel -> fixed-order sum per group (no atomics)
   __shared__ float s_sum[kGNMaxC], s_sq[kGNMaxC];
+  __shared__ float p_sum[kGNMaxThreads * 8], p_sq[kGNMaxThreads * 8];
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = s_sq[c] = 0.f;
-  __syncthreads();
   const int chunks = C / 8;                 // 16-byte chunks per pixel
   const int chunk = threadIdx.x % chunks;   // fixed channel chunk per thread (blockDim is a multiple of `chunks`)
   const int prow = threadIdx.x / chunks, pstride = blockDim.x / chunks;
@@ -68,22 +69,30 @@ __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ z, floa
   float a[8], q[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a[k] = q[k] = 0.f;
-  if (prow < pstride) {
-    for (int p = prow; p < HW; p += pstride) {
-      const uint4 u = *reinterpret_cast<const uint4*>(zn + (long long)p * C + chunk * 8);
-      const uint32_t* pu = &u.x;
+  for (int p = prow; p < HW; p += pstride) {
+    const uint4 u = *reinterpret_cast<const uint4*>(zn + (long long)p * C + chunk * 8);
+    const uint32_t* pu = &u.x;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16(pu[k]);
-        a[2 * k] += f.x; q[2 * k] += f.x * f.x;
-        a[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(pu[k]);
+      a[2 * k] += f.x; q[2 * k] += f.x * f.x;
+      a[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
     }
+  }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(&s_sum[chunk * 8 + k], a[k]);
-      atomicAdd(&s_sq[chunk * 8 + k], q[k]);
+  for (int k = 0; k < 8; ++k) {
+    p_sum[(prow * chunks + chunk) * 8 + k] = a[k];   // == [prow][channel]
+    p_sq[(prow * chunks + chunk) * 8 + k] = q[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int r = 0; r < pstride; ++r) {
+      s += p_sum[r * C + c];
+      ss += p_sq[r * C + c];
     }
+    s_sum[c] = s;
+    s_sq[c] = ss;
   }
   __syncthreads();
   const int cpg = C / G;
@@ -140,9 +149,8 @@ __global__ void groupnorm_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict
                                                  float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C,
                                                  int G) {
   __shared__ float c_dyx[kGNMaxC], c_dy[kGNMaxC];
+  __shared__ float p_dyx[kGNMaxThreads * 8], p_dy[kGNMaxThreads * 8];
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) c_dyx[c] = c_dy[c] = 0.f;
-  __syncthreads();
   const int chunks = C / 8, cpg = C / G;
   const int chunk = threadIdx.x % chunks;
   const int prow = threadIdx.x / chunks, pstride = blockDim.x / chunks;
@@ -157,7 +165,7 @@ __global__ void groupnorm_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict
     ga[k] = gamma[c];
     be[k] = beta[c];
   }
-  if (prow < pstride) {
+  {
     for (int p = prow; p < HW; p += pstride) {
       const long long off = base + (long long)p * C + chunk * 8;
       const uint4 uz = *reinterpret_cast<const uint4*>(z + off), ud = *reinterpret_cast<const uint4*>(da + off);
@@ -179,9 +187,19 @@ __global__ void groupnorm_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&c_dyx[chunk * 8 + k], adyx[k]);
-      atomicAdd(&c_dy[chunk * 8 + k], ady[k]);
+      p_dyx[(prow * chunks + chunk) * 8 + k] = adyx[k];
+      p_dy[(prow * chunks + chunk) * 8 + k] = ady[k];
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < pstride; ++r) {
+      a += p_dyx[r * C + c];
+      b += p_dy[r * C + c];
+    }
+    c_dyx[c] = a;
+    c_dy[c] = b;
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -468,8 +486,7 @@ static inline unsigned nblk(long long n, int per) { return (unsigned)((n + per -
 // threads per CTA for the per-map GroupNorm reductions: a multiple of C/8 close to 256 (each thread owns one chunk)
 static int gn_threads(int C) {
   const int chunks = C / 8;
-  int t = (256 / chunks) * chunks;
-  if (t == 0) t = chunks;
+  int t = (kGNMaxThreads / chunks) * chunks;  // C <= 512 -> chunks <= 64 <= kGNMaxThreads
   return t;
 }
 

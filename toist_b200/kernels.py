@@ -262,7 +262,8 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], *, str
     h, wd = in_hw
     dx = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dy.device)
     a = _nhwc_t4(dy)
-    b = t4(w, (kh * kw * cin, cout, 1, 1), (1, kh * kw * cin, 0, 0))
+    # B rows = the filters that exist: the zero-padded channels of dy meet TMA zero fill, never memory past the tensor
+    b = t4(w, (kh * kw * cin, cout2, 1, 1), (1, kh * kw * cin, 0, 0))
     for phy in range(stride):
         for phx in range(stride):
             qh, qw = -(-(h - phy) // stride), -(-(wd - phx) // stride)

@@ -25,7 +25,7 @@ def make_args(backbone: str = "resnet50", **over) -> argparse.Namespace:
     return argparse.Namespace(**d)
 
 
-def make_batch(batch: int, size: int, n_tokens: int, seed: int = 1234, pad: bool = False):
+def make_batch(batch: int, size: int, n_tokens: int, seed: int = 1234, pad: bool = False, masks: bool = False):
     """images [B,3,size,size] fp32, pad mask [B,size,size] bool, captions of exactly n_tokens - 2 characters ending
     in 'something', targets (T_i = 1 + i % 4 boxes) and the normalised positive map [sum T_i, 256]."""
     g = torch.Generator().manual_seed(seed)
@@ -57,6 +57,11 @@ def make_batch(batch: int, size: int, n_tokens: int, seed: int = 1234, pad: bool
             "tokens_positive": [[[0, len(cap)]] for _ in range(t)],
             "noun_tokens_positive": [[[max(s, 0), len(cap)]] for _ in range(t)],
         })
+    if masks:  # drawn after everything else so that the detection batches of a given seed do not change
+        for i, t in enumerate(targets):
+            n = len(t["boxes"])
+            h, w = (size - size // 4, size - size // 8) if (pad and batch > 1 and i == batch - 1) else (size, size)
+            t["masks"] = torch.rand(n, h, w, generator=g) < 0.5
     total = sum(len(t["boxes"]) for t in targets)
     pm = torch.zeros(total, 256)
     pm[:, 1: n_tokens - 1] = 1.0

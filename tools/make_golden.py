@@ -9,6 +9,9 @@ Fixtures (torch.save, fp32 unless noted; library versions recorded in each file)
   config1_r50.pt     BASELINE config 1: ResNet-50 TOIST, 2 x 3 x 480 x 480, 8-token captions, seed-0 random init,
                      eval mode: memory_cache tensors, all-layer outputs, the 30 loss terms, the assignments of all 6
                      decoder layers, and per-tensor checksums of the state dict          (models/mdetr.py:377-462,990-1021)
+  config3_r50_segm_small.pt  the mask recipe of BASELINE config 3 (frozen detector + DETRsegm mask head) on a
+                     2 x 3 x 128 x 128 ragged batch: pred_masks, the 6 loss terms, the assignment, and the gradients of
+                     every mask-branch parameter                          (models/segmentation.py:40-273, mdetr.py:827-853)
 """
 from __future__ import annotations
 
@@ -106,6 +109,38 @@ def config1(models, tok):
     }
 
 
+def config3_small(models, tok):
+    """BASELINE config 3's recipe (frozen detector + mask head, no aux / contrastive losses) at a size the CPU suite
+    can afford: ResNet-50, 2 x 3 x 128 x 128 ragged, Bernoulli(.5) target masks."""
+    args = shims.reference_args(["--backbone", "resnet50", "--mask_model", "smallconv", "--frozen_weights", "unused",
+                                 "--no_aux_loss", "--no_contrastive_align_loss"])
+    torch.manual_seed(0)
+    model, criterion, _, weight_dict = models.build_model(args)
+    model.eval()
+    from util.misc import NestedTensor  # reference
+
+    images, mask, captions, targets, pm = make_batch(2, 128, 8, seed=7, pad=True, masks=True)
+    mc = model(NestedTensor(images, mask), captions, encode_and_save=True)
+    out = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc)
+    losses = criterion(mc, out, targets, pm, None)
+    total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+    total.backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    with torch.no_grad():
+        indices = criterion.matcher(out, targets, pm)
+    sd = model.state_dict()
+    return {
+        "batch": {"size": 128, "tokens": 8, "batch": 2, "seed": 7, "pad": True, "masks": True},
+        "state_checksum": {k: float(v.double().abs().sum()) for k, v in sd.items()},
+        "pred_masks": out["pred_masks"].detach().clone(),
+        "pred_logits": out["pred_logits"].detach().clone(), "pred_boxes": out["pred_boxes"].detach().clone(),
+        "losses": {k: float(v) for k, v in losses.items()},
+        "indices": [(i.clone(), j.clone()) for i, j in indices],
+        "grads": grads,  # mask-branch parameters only: the detector is frozen
+        "weight_dict": dict(weight_dict),
+    }
+
+
 def main():
     torch.set_num_threads(8)
     OUT.mkdir(parents=True, exist_ok=True)
@@ -114,6 +149,7 @@ def main():
     v = versions()
     torch.save({"versions": v, "cases": matcher_cases(models)}, OUT / "matcher_cases.pt")
     torch.save({"versions": v, **config1(models, tok)}, OUT / "config1_r50.pt")
+    torch.save({"versions": v, **config3_small(models, tok)}, OUT / "config3_r50_segm_small.pt")
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size // 1024, "KiB")
 
