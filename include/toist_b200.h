@@ -280,6 +280,54 @@ int toist_mask_loss_bwd(const float* pred_masks, const uint8_t* tgt_masks, const
                         float* dpred, int32_t batch, int32_t n_queries, int32_t t_max, int32_t mask_h, int32_t mask_w,
                         int32_t tgt_h, int32_t tgt_w, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Noun-pronoun distillation (BASELINE config 5).
+ * Soft-KD (reference models/mdetr.py:520-599, called per decoder layer at mdetr.py:969-988): teacher (noun) and student
+ * (pronoun) predictions of all layers at once.  Per (layer, image): two-class probabilities
+ * (sum of the first C-1 softmax entries, last entry); matched queries are paired by target index, the unmatched ones by
+ * an LSAP on  L1 + KL(teacher || student) - GIoU  (rows = student, scipy tie rules, float64);
+ * loss[l] = mean over images of kl_div(log student, teacher, "batchmean").  Gradient: student logits only.
+ *   logits_* [L, B, Q, C], boxes_* [L, B, Q, 4], match_* [L, B, t_max] (query of each target, toist_lsap_device)
+ *   workspace (caller allocated): bi_* [L, B, Q, 2] f32, fp_* [L, B, Q] i32, n_fp [2, L*B] i32, cost [L, B, Q, Q] f32,
+ *   col_of_row [L, B, Q] i32, pair_noun [L, B, Q] i32 (teacher query paired with each student query);
+ *   flags[0] |= 1 on NaN / infeasible costs (scipy's ValueError).
+ * ------------------------------------------------------------------------------------------------------------ */
+int toist_softkd_fwd(const float* logits_noun, const float* logits_sth, const float* boxes_noun, const float* boxes_sth,
+                     const int32_t* match_noun, const int32_t* match_sth, const int32_t* tgt_count, float* bi_noun,
+                     float* bi_sth, int32_t* fp_noun, int32_t* fp_sth, int32_t* n_fp, float* cost, int32_t* col_of_row,
+                     int32_t* pair_noun, int32_t* flags, float* loss, int32_t n_layers, int32_t batch, int32_t n_queries,
+                     int32_t n_classes, int32_t t_max, void* stream);
+/* dlogits_sth [L, B, Q, C] = sum_l gout[l] * d loss[l] / d logits_sth */
+int toist_softkd_bwd(const float* logits_sth, const float* bi_noun, const float* bi_sth, const int32_t* pair_noun,
+                     const int32_t* tgt_count, const int32_t* n_fp, const float* gout, float* dlogits_sth,
+                     int32_t n_layers, int32_t batch, int32_t n_queries, int32_t n_classes, int32_t t_max, void* stream);
+/* Batched LSAP, one warp per problem (scipy.optimize.linear_sum_assignment semantics incl. ties; mdetr.py:100,539):
+ * cost [P, ld_rows, ld_cols] f32 with n_rows[p] x n_cols[p] valid entries (each <= 128);
+ * col_of_row [P, ld_rows] = assigned column per row or -1. */
+int toist_lsap_batched(const float* cost, const int32_t* n_rows, const int32_t* n_cols, int32_t* col_of_row,
+                       int32_t* flags, int32_t n_problems, int32_t ld_rows, int32_t ld_cols, void* stream);
+/* ClusterCriterion arithmetic (models/mdetr.py:29-312, models/kmeans.py:21-133).
+ * toist_kmeans: Lloyd iterations on x [n, dim] from `centers` [k, dim] (updated in place) until
+ * (sum_k ||shift_k||)^2 < tol, without host round trips; choice [n]; iters (may be null) = iterations run. */
+int toist_kmeans(const float* x, float* centers, int32_t* choice, int32_t* iters, int32_t n, int32_t dim, int32_t k,
+                 float tol, int32_t max_iter, void* stream);
+int toist_kmeans_predict(const float* x, const float* centers, int32_t* choice, int32_t m, int32_t dim, int32_t k,
+                         void* stream);
+/* out[b, :] = sum_t w[b, t] * x[t, b, :]   (x f32 [n_tokens, batch, dim]; w = selection / count gives the token means of
+ * mdetr.py:141,256) and its backward dx[t, b, :] = w[b, t] * dout[b, :] */
+int toist_token_wsum(const float* x, const float* w, float* out, int32_t n_tokens, int32_t batch, int32_t dim,
+                     void* stream);
+int toist_token_wsum_bwd(const float* dout, const float* w, float* dx, int32_t n_tokens, int32_t batch, int32_t dim,
+                         void* stream);
+/* x[t, b, :] = feat[b, :] (0 when feat is null) for every selected token (mdetr.py:208,266) */
+int toist_token_fill(float* x, const uint8_t* sel, const float* feat, int32_t n_tokens, int32_t batch, int32_t dim,
+                     void* stream);
+/* loss[0] = mean over the rows with use[r] != 0 of mse(a[r], b[r]); da (may be null) = its gradient w.r.t. a */
+int toist_mse_rows(const float* a, const float* b, const uint8_t* use, float* loss, float* da, int32_t rows, int32_t dim,
+                   void* stream);
+/* out [n, m] = torch.cdist(a [n, dim], b [m, dim], p=1)   (mdetr.py:98) */
+int toist_cdist_l1(const float* a, const float* b, float* out, int32_t n, int32_t m, int32_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,19 @@ def test_oracle_mask_branch_reproduces_reference_golden():
         assert rel_err(sd[k].grad, g["grads"][k]) < 1e-4, k
 
 
+def test_oracle_softkd_reproduces_reference_golden():
+    """loss_softkd + softkd_matcher (models/mdetr.py:520-599) on the hand-made golden cases: value and gradient."""
+    g = torch.load(GOLD / "config5_softkd_small.pt", weights_only=False)
+    for c in g["softkd_cases"]:
+        ls = c["logits_sth"].clone().requires_grad_(True)
+        Q = ls.shape[1]
+        val = O.loss_softkd({"pred_logits": c["logits_noun"], "pred_boxes": c["boxes_noun"]},
+                            {"pred_logits": ls, "pred_boxes": c["boxes_sth"]}, c["idx_noun"], c["idx_sth"], Q)
+        assert abs(float(val) - c["loss"]) <= 1e-6 * max(1.0, abs(c["loss"]))
+        val.backward()
+        assert rel_err(ls.grad, c["grad_logits_sth"]) < 1e-5
+
+
 def test_c_abi_library_loads_and_exports_every_declared_symbol():
     from toist_b200 import _lib
 

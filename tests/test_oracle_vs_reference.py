@@ -114,6 +114,24 @@ def test_segmentation_branch_matches_reference():
         assert abs(float(losses[k]) - float(v)) <= 2e-4 * max(1.0, abs(float(v))), (k, float(losses[k]), float(v))
 
 
+def test_kmeans_restatement_matches_reference():
+    """models/kmeans.py:21-133 (vendored in the reference): same centres, assignments and predictions."""
+    shims.load_reference(CharTokenizer())
+    from models.kmeans import kmeans as ref_kmeans, kmeans_predict as ref_predict  # reference
+
+    torch.manual_seed(2)
+    X = torch.randn(200, 16)
+    X[:70] += 2
+    for full in (0, 1):
+        init = X[:4].clone() + 0.1
+        np.random.seed(9)
+        rc, rcen = ref_kmeans(X=X, init_cluster_centers=init.clone(), num_clusters=4, full_label=full)
+        oc, ocen = O.kmeans(X, init.clone(), 4, full, rng=np.random.RandomState(9))
+        assert torch.equal(rc, oc) and max_err(ocen, rcen) < 1e-6
+        q = torch.randn(9, 16)
+        assert torch.equal(ref_predict(q, rcen), O.kmeans_predict(q, ocen))
+
+
 def test_matcher_cost_matches_reference_ops(ref):
     from util import box_ops  # reference
 

@@ -902,3 +902,106 @@ def mask_loss_bwd(pred_masks, tgt_masks_u8, match_q, tgt_count, sums, num_boxes,
                                  sums.data_ptr(), num_boxes.data_ptr(), gout.data_ptr(), dpred.data_ptr(), B, Q, tmax,
                                  mh, mw, th, tw, _stream()))
     return dpred
+
+
+# ------------------------------------------------------------------------------------------------ distillation
+def softkd_fwd(logits_n, logits_s, boxes_n, boxes_s, match_n, match_s, tgt_count, flags):
+    """Soft-KD loss of every decoder layer (models/mdetr.py:543-599): returns (loss [L], saved workspace)."""
+    L, B, Q, C = logits_s.shape
+    tmax = match_s.shape[-1]
+    dev = logits_s.device
+    f32, i32 = torch.float32, torch.int32
+    bi_n = torch.empty((L, B, Q, 2), dtype=f32, device=dev)
+    bi_s = torch.empty((L, B, Q, 2), dtype=f32, device=dev)
+    fp_n = torch.empty((L, B, Q), dtype=i32, device=dev)
+    fp_s = torch.empty((L, B, Q), dtype=i32, device=dev)
+    n_fp = torch.empty((2, L * B), dtype=i32, device=dev)
+    cost = torch.empty((L, B, Q, Q), dtype=f32, device=dev)
+    col = torch.empty((L, B, Q), dtype=i32, device=dev)
+    pair = torch.empty((L, B, Q), dtype=i32, device=dev)
+    loss = torch.empty((L,), dtype=f32, device=dev)
+    for t in (logits_n, logits_s, boxes_n, boxes_s, match_n, match_s):
+        assert t.is_contiguous()
+    _ck(_L().toist_softkd_fwd(logits_n.data_ptr(), logits_s.data_ptr(), boxes_n.data_ptr(), boxes_s.data_ptr(),
+                              match_n.data_ptr(), match_s.data_ptr(), tgt_count.data_ptr(), bi_n.data_ptr(),
+                              bi_s.data_ptr(), fp_n.data_ptr(), fp_s.data_ptr(), n_fp.data_ptr(), cost.data_ptr(),
+                              col.data_ptr(), pair.data_ptr(), flags.data_ptr(), loss.data_ptr(), L, B, Q, C, tmax,
+                              _stream()), 6)
+    return loss, (bi_n, bi_s, pair, n_fp, cost, col, fp_n, fp_s)
+
+
+def softkd_bwd(logits_s, bi_n, bi_s, pair, tgt_count, n_fp, gout, tmax: int):
+    L, B, Q, C = logits_s.shape
+    d = torch.empty_like(logits_s)
+    _ck(_L().toist_softkd_bwd(logits_s.data_ptr(), bi_n.data_ptr(), bi_s.data_ptr(), pair.data_ptr(),
+                              tgt_count.data_ptr(), n_fp.data_ptr(), gout.data_ptr(), d.data_ptr(), L, B, Q, C, tmax,
+                              _stream()))
+    return d
+
+
+def lsap_batched(cost: torch.Tensor, n_rows: torch.Tensor, n_cols: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    """cost fp32 [P, R, C]; n_rows / n_cols int32 [P]  ->  col_of_row int32 [P, R] (-1 = unassigned)."""
+    P, R, Cc = cost.shape
+    assert cost.is_contiguous() and cost.dtype == torch.float32
+    out = torch.empty((P, R), dtype=torch.int32, device=cost.device)
+    _ck(_L().toist_lsap_batched(cost.data_ptr(), n_rows.data_ptr(), n_cols.data_ptr(), out.data_ptr(), flags.data_ptr(),
+                                P, R, Cc, _stream()))
+    return out
+
+
+def kmeans(x: torch.Tensor, centers: torch.Tensor, tol: float = 1e-4, max_iter: int = 10000):
+    """In-place Lloyd iterations on `centers` [K, D] (models/kmeans.py:21-96); returns (choice int32 [N], iters [1])."""
+    n, d = x.shape
+    k = centers.shape[0]
+    assert x.is_contiguous() and centers.is_contiguous() and x.dtype == centers.dtype == torch.float32
+    choice = torch.empty((n,), dtype=torch.int32, device=x.device)
+    iters = torch.empty((1,), dtype=torch.int32, device=x.device)
+    _ck(_L().toist_kmeans(x.data_ptr(), centers.data_ptr(), choice.data_ptr(), iters.data_ptr(), n, d, k, float(tol),
+                          int(max_iter), _stream()))
+    return choice, iters
+
+
+def kmeans_predict(x: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+    m, d = x.shape
+    choice = torch.empty((m,), dtype=torch.int32, device=x.device)
+    _ck(_L().toist_kmeans_predict(x.data_ptr(), centers.data_ptr(), choice.data_ptr(), m, d, centers.shape[0], _stream()))
+    return choice
+
+
+def token_wsum(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x fp32 [T, B, D], w fp32 [B, T] -> out[b] = sum_t w[b, t] x[t, b]."""
+    T, B, D = x.shape
+    assert x.is_contiguous() and w.is_contiguous() and w.shape == (B, T) and w.dtype == torch.float32
+    out = torch.empty((B, D), dtype=torch.float32, device=x.device)
+    _ck(_L().toist_token_wsum(x.data_ptr(), w.data_ptr(), out.data_ptr(), T, B, D, _stream()))
+    return out
+
+
+def token_wsum_bwd(dout: torch.Tensor, w: torch.Tensor, T: int) -> torch.Tensor:
+    B, D = dout.shape
+    dx = torch.empty((T, B, D), dtype=torch.float32, device=dout.device)
+    _ck(_L().toist_token_wsum_bwd(dout.data_ptr(), w.data_ptr(), dx.data_ptr(), T, B, D, _stream()))
+    return dx
+
+
+def token_fill(x: torch.Tensor, sel_u8: torch.Tensor, feat: Optional[torch.Tensor]) -> torch.Tensor:
+    """In place: x[t, b] = feat[b] (zeros when feat is None) for the selected tokens; x fp32 [T, B, D] contiguous."""
+    T, B, D = x.shape
+    assert x.is_contiguous() and sel_u8.is_contiguous() and sel_u8.shape == (B, T)
+    assert feat is None or (feat.is_contiguous() and feat.shape == (B, D))
+    _ck(_L().toist_token_fill(x.data_ptr(), sel_u8.data_ptr(), _ptr(feat), T, B, D, _stream()))
+    return x
+
+
+def mse_rows(a: torch.Tensor, b: torch.Tensor, use_u8: torch.Tensor, want_grad: bool):
+    M, D = a.shape
+    loss = torch.empty((1,), dtype=torch.float32, device=a.device)
+    da = torch.empty_like(a) if want_grad else None
+    _ck(_L().toist_mse_rows(a.data_ptr(), b.data_ptr(), use_u8.data_ptr(), loss.data_ptr(), _ptr(da), M, D, _stream()))
+    return loss, da
+
+
+def cdist_l1(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    _ck(_L().toist_cdist_l1(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], b.shape[0], a.shape[1], _stream()))
+    return out

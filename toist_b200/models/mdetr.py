@@ -299,6 +299,25 @@ def _mask_loss_bwd(c: Call, saved, needs, gout):
 MASKLOSS = Spec("mask_loss", 5, _mask_loss_fwd, _mask_loss_bwd)
 
 
+def _softkd_fwd(c: Call, logits_n, logits_s, boxes_n, boxes_s, match_n, match_s, tgt_count):
+    """loss_softkd of every decoder layer (models/mdetr.py:543-599); NaN / infeasible matching costs poison the loss
+    (the reference's scipy call raises ValueError) without a device synchronisation."""
+    flags = torch.zeros(1, dtype=torch.int32, device=logits_s.device)
+    loss, ws = K.softkd_fwd(logits_n, logits_s, boxes_n, boxes_s, match_n, match_s, tgt_count, flags)
+    bi_n, bi_s, pair, n_fp = ws[:4]
+    saved = (logits_s, bi_n, bi_s, pair, tgt_count, n_fp, int(match_s.shape[-1])) if c.save else None
+    return (loss, flags), saved
+
+
+def _softkd_bwd(c: Call, saved, needs, gout, *unused):
+    logits_s, bi_n, bi_s, pair, tgt_count, n_fp, tmax = saved
+    d = K.softkd_bwd(logits_s, bi_n, bi_s, pair, tgt_count, n_fp, gout.contiguous(), tmax) if needs[1] else None
+    return (None, d, None, None, None, None, None), {}
+
+
+SOFTKD = Spec("softkd", 7, _softkd_fwd, _softkd_bwd, nondiff=(1,))
+
+
 def pack_target_masks(targets, t_max: int, device) -> torch.Tensor:
     """uint8 [B, t_max, H, W]: every image's target masks padded to the largest height / width of the batch
     (NestedTensor.from_tensor_list in the reference, models/mdetr.py:840)."""
@@ -365,10 +384,12 @@ class SetCriterion(nn.Module):
         self.eos_coef = eos_coef
         self.losses = losses
         self.temperature = temperature
-        unsupported = [l for l in losses if l not in ("labels", "boxes", "cardinality", "contrastive_align", "masks")]
+        unsupported = [l for l in losses if l not in ("labels", "boxes", "cardinality", "contrastive_align", "masks",
+                                                      "softkd")]
         self._unsupported = unsupported
         self._stage = Stage.empty("criterion")
         self._stage_mask = Stage.empty("mask_loss")
+        self._stage_kd = Stage.empty("softkd")
         self._graphs: Optional[GraphCache] = None
 
     def enable_cuda_graphs(self, on: bool = True) -> "SetCriterion":
@@ -406,10 +427,15 @@ class SetCriterion(nn.Module):
         return torch.clamp(nb / dist.get_world_size(), min=1)
 
     def forward(self, memory_cache, outputs, targets, positive_map, example_rel=None):
-        if isinstance(outputs, list):
-            raise NotImplementedError("the distillation branch (models/mdetr.py:887-989) is not built yet")
         if self._unsupported:
             raise NotImplementedError(f"losses {self._unsupported} are not built yet")
+        if isinstance(outputs, list):
+            return self._forward_distillation(memory_cache, outputs, targets, positive_map)
+        losses, _ = self._forward_single(outputs, targets, positive_map)
+        return losses
+
+    def _forward_single(self, outputs, targets, positive_map, prefix: str = ""):
+        """models/mdetr.py:990-1021 (and, with `prefix`, one half of the distillation branch :893-951)."""
         st = self._stack(outputs)
         logits, boxes = st["pred_logits"], st["pred_boxes"]
         if logits.dtype != torch.float32 or not logits.is_cuda:
@@ -445,17 +471,46 @@ class SetCriterion(nn.Module):
         losses = {}
         for name, row in terms:
             if name == "loss_contrastive_align" and mask_out is not None:
-                losses["loss_mask"], losses["loss_dice"] = mask_out[0], mask_out[1]
+                losses[prefix + "loss_mask"], losses[prefix + "loss_dice"] = mask_out[0], mask_out[1]
                 mask_out = None
             v = out[row, L - 1]
-            losses[name] = v.detach() if row >= 3 else v
+            losses[prefix + name] = v.detach() if row >= 3 else v
         if mask_out is not None:
-            losses["loss_mask"], losses["loss_dice"] = mask_out[0], mask_out[1]
+            losses[prefix + "loss_mask"], losses[prefix + "loss_dice"] = mask_out[0], mask_out[1]
         if use_aux:
             for i in range(L - 1):
                 for name, row in terms:
                     v = out[row, i]
-                    losses[f"{name}_{i}"] = v.detach() if row >= 3 else v
+                    losses[f"{prefix}{name}_{i}"] = v.detach() if row >= 3 else v
+        return losses, (st, match_q, packed, flags)
+
+    def _forward_distillation(self, memory_cache, outputs, targets, positive_map):
+        """models/mdetr.py:887-989: teacher (noun) and student (pronoun) losses with `noun_` / `sth_` prefixes, then the
+        soft-KD term of every decoder layer."""
+        if getattr(self.args, "nsthl2_loss", False):
+            raise NotImplementedError("loss_nsthl2 (models/mdetr.py:668-781) is off in every shipped recipe; not built")
+        outputs_noun, outputs_sth = outputs
+        targets_noun, targets_sth = targets
+        pm_noun, pm_sth = positive_map
+        losses, (st_n, mq_n, pk_n, fl_n) = self._forward_single(outputs_noun, targets_noun, pm_noun, "noun_")
+        l_sth, (st_s, mq_s, pk_s, fl_s) = self._forward_single(outputs_sth, targets_sth, pm_sth, "sth_")
+        losses.update(l_sth)
+        self.last_match_pair = ((mq_n, pk_n.counts, fl_n), (mq_s, pk_s.counts, fl_s))
+        if getattr(self.args, "softkd_loss", False):
+            if pk_n.counts != pk_s.counts:
+                raise ValueError("soft-KD pairs the matched queries of teacher and student by target index: both "
+                                 "target lists must have the same length per image (models/mdetr.py:567-571,590-594)")
+            ls = st_s["pred_logits"]
+            save = torch.is_grad_enabled() and ls.requires_grad
+            call = Call(self._stage_kd, {}, save, graphs=self._graphs)
+            kd, kd_flags = run_stage(SOFTKD, call, st_n["pred_logits"].detach(), ls, st_n["pred_boxes"].detach(),
+                                     st_s["pred_boxes"].detach(), mq_n, mq_s, pk_s.count)
+            self.last_softkd_flags = kd_flags
+            L = ls.shape[0]
+            losses["loss_softkd"] = kd[L - 1]
+            if "aux_outputs" in outputs_sth:
+                for i in range(L - 1):
+                    losses[f"loss_softkd_{i}"] = kd[i]
         return losses
 
     def last_indices(self) -> List[List[tuple]]:
@@ -531,6 +586,10 @@ def build(args):
                              temperature=args.temperature_NCE, contrastive_hdim=args.contrastive_loss_hdim,
                              task_count=14)
     criterion.to(device)
+    cluster_criterion = None
     if args.cluster:
-        raise NotImplementedError("ClusterCriterion (models/mdetr.py:29-312, config 5) is not built yet")
-    return model, criterion, None, weight_dict
+        from .cluster import ClusterCriterion
+
+        cluster_criterion = ClusterCriterion(feature_dim=args.hidden_dim, memory_size=args.cluster_memory_size,
+                                             cluster_num=args.cluster_num, task_count=14, args=args)
+    return model, criterion, cluster_criterion, weight_dict

@@ -19,7 +19,7 @@ def make_args(backbone: str = "resnet50", **over) -> argparse.Namespace:
         giou_loss_coef=2.0, mask_loss_coef=1.0, dice_loss_coef=1.0, contrastive_align_loss_coef=1.0, eos_coef=0.1,
         aux_loss=True, nsthl2_loss=False, nsthl2_coef=1.0, softkd_loss=False, softkd_coef=1.0, cluster=False,
         cluster_num=3, cluster_memory_size=1024, cluster_feature_loss=1e4, cluster_choice_loss=0.0,
-        distillation=False, without_pretrain=True, device="cuda", synthetic_tokenizer=True,
+        distillation=False, train_batch_size=2, fifo_memory=False, without_pretrain=True, device="cuda", synthetic_tokenizer=True,
     )
     d.update(over)
     return argparse.Namespace(**d)

@@ -12,6 +12,10 @@ Fixtures (torch.save, fp32 unless noted; library versions recorded in each file)
   config3_r50_segm_small.pt  the mask recipe of BASELINE config 3 (frozen detector + DETRsegm mask head) on a
                      2 x 3 x 128 x 128 ragged batch: pred_masks, the 6 loss terms, the assignment, and the gradients of
                      every mask-branch parameter                          (models/segmentation.py:40-273, mdetr.py:827-853)
+  config5_softkd_small.pt  distillation branch of SetCriterion with soft-KD: fp32 predictions of teacher and student,
+                     the 66 loss terms, d(soft-KD)/d(student logits)                        (models/mdetr.py:520-599,887-989)
+  cluster_cases.pt   ClusterCriterion driven for 10 steps on random features (memory bank, k-means, replacement,
+                     cluster-feature loss and its gradient), run on the CPU by patching .cuda()  (models/mdetr.py:29-312)
 """
 from __future__ import annotations
 
@@ -141,6 +145,162 @@ def config3_small(models, tok):
     }
 
 
+def config5_softkd_small(models, tok):
+    """Distillation branch of SetCriterion (models/mdetr.py:887-989) with the soft-KD loss: teacher = deepcopy(student)
+    at initialisation (main.py:322), different inputs; ResNet-50, 2 x 3 x 128 x 128, eval mode.  Stores the fp32
+    predictions of both models (all decoder layers), the 66 loss terms, and d(sum of soft-KD terms)/d(student logits)."""
+    from copy import deepcopy
+
+    args = shims.reference_args(["--backbone", "resnet50", "--distillation", "--softkd_loss", "--softkd_coef", "50"])
+    torch.manual_seed(0)
+    model, criterion, _, weight_dict = models.build_model(args)
+    model.eval()
+    model_noun = deepcopy(model)
+    from util.misc import NestedTensor  # reference
+
+    bn = make_batch(2, 128, 8, seed=21, pad=True)
+    bs = make_batch(2, 128, 8, seed=22, pad=False)
+    outs, mcs = [], []
+    with torch.no_grad():
+        for m, (images, mask, captions, targets, pm) in ((model_noun, bn), (model, bs)):
+            mc = m(NestedTensor(images, mask), captions, encode_and_save=True)
+            outs.append(m(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc))
+            mcs.append(mc)
+        losses = criterion(mcs, outs, [bn[3], bs[3]], [bn[4], bs[4]], None)
+
+    def stacked(o, k):
+        return torch.stack([a[k] for a in o["aux_outputs"]] + [o[k]])
+
+    # gradient of the soft-KD terms alone w.r.t. the student's logits of every layer
+    leaf = []
+    for o in outs:
+        d = {k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in o.items() if k != "aux_outputs"}
+        d["aux_outputs"] = [{k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in a.items()}
+                            for a in o["aux_outputs"]]
+        leaf.append(d)
+    sth_logits = [a["pred_logits"] for a in leaf[1]["aux_outputs"]] + [leaf[1]["pred_logits"]]
+    for t in sth_logits:
+        t.requires_grad_(True)
+    l2 = criterion(mcs, leaf, [bn[3], bs[3]], [bn[4], bs[4]], None)
+    kd = sum(v for k, v in l2.items() if k.startswith("loss_softkd"))
+    kd.backward()
+    # soft-KD in isolation on hand-made predictions where the two-class probabilities differ substantially
+    from models.matcher import HungarianMatcher  # reference
+
+    hm = HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2)
+    kd_cases = []
+    for seed, B, Q, counts, tie in ((0, 2, 100, [2, 1], False), (1, 3, 100, [1, 4, 3], False), (2, 2, 16, [3, 2], True),
+                                    (3, 2, 100, [0, 2], False)):
+        g = torch.Generator().manual_seed(500 + seed)
+
+        def preds():
+            lg = torch.randn(B, Q, 256, generator=g) * 2
+            lg[..., -1] += 4 + 2 * torch.randn(B, Q, generator=g)
+            bx = torch.cat([torch.rand(B, Q, 2, generator=g) * 0.5 + 0.25, torch.rand(B, Q, 2, generator=g) * 0.3 + 0.05], -1)
+            return lg, bx
+
+        ln, bxn = preds()
+        ls, bxs = preds()
+        if tie:  # identical unmatched predictions: the LSAP tie rule decides the pairing
+            ln[:, 4:] = ln[:, 4:5]
+            bxn[:, 4:] = bxn[:, 4:5]
+        tg = []
+        for n in counts:
+            tb = torch.cat([torch.rand(n, 2, generator=g) * 0.5 + 0.25, torch.rand(n, 2, generator=g) * 0.3 + 0.05], -1)
+            tg.append({"boxes": tb, "labels": torch.ones(n, dtype=torch.long)})
+        T = sum(counts)
+        pmap = torch.zeros(T, 256)
+        pmap[:, 1:5] = 0.25
+        on = {"pred_logits": ln, "pred_boxes": bxn}
+        os_ = {"pred_logits": ls.clone().requires_grad_(True), "pred_boxes": bxs}
+        idx_n, idx_s = hm(on, tg, pmap), hm({"pred_logits": ls, "pred_boxes": bxs}, tg, pmap)
+        criterion.args.num_queries = Q
+        val = criterion.loss_softkd([None, None], [on, os_], [tg, tg], [pmap, pmap], [idx_n, idx_s], [1.0, 1.0])["loss_softkd"]
+        val.backward()
+        kd_cases.append({"logits_noun": ln, "boxes_noun": bxn, "logits_sth": ls, "boxes_sth": bxs,
+                         "tgt_boxes": [t["boxes"] for t in tg], "idx_noun": idx_n, "idx_sth": idx_s,
+                         "loss": float(val), "grad_logits_sth": os_["pred_logits"].grad.clone()})
+    criterion.args.num_queries = 100
+    return {
+        "softkd_cases": kd_cases,
+        "batch_noun": {"size": 128, "tokens": 8, "batch": 2, "seed": 21, "pad": True},
+        "batch_sth": {"size": 128, "tokens": 8, "batch": 2, "seed": 22, "pad": False},
+        "noun": {k: stacked(outs[0], k) for k in ("pred_logits", "pred_boxes", "proj_queries")},
+        "sth": {k: stacked(outs[1], k) for k in ("pred_logits", "pred_boxes", "proj_queries")},
+        "noun_proj_tokens": outs[0]["proj_tokens"], "sth_proj_tokens": outs[1]["proj_tokens"],
+        "losses": {k: float(v) for k, v in losses.items()},
+        "loss_order": list(losses.keys()),
+        "softkd_grad_sth_logits": torch.stack([t.grad for t in sth_logits]),
+        "weight_dict": dict(weight_dict),
+    }
+
+
+def cluster_cases(models, tok):
+    """ClusterCriterion (models/mdetr.py:29-312) driven like engine.py:182-190 for a few steps on random features.
+    The reference constructor needs `.cuda()` and a process group: here `.cuda()` is patched to the identity and a
+    1-rank gloo group is created, so the module runs on the CPU.  memory_size = 8 so that the banks fill up within the
+    run and both update branches (FIFO while filling, LSAP replacement afterwards) are exercised."""
+    import os
+
+    import numpy as np
+    import torch.distributed as dist
+
+    from models.mdetr import ClusterCriterion  # reference
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29517")
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        args = shims.reference_args(["--cluster", "--cluster_memory_size", "8", "--cluster_num", "3",
+                                     "--train_batch_size", "4"])
+        D, T, S_img, B = 32, 12, 5, 4
+        torch.manual_seed(3)
+        cc = ClusterCriterion(feature_dim=D, memory_size=8, cluster_num=3, task_count=14, args=args)
+        init = {k: v.clone() for k, v in cc.state_dict().items()}
+        np.random.seed(7)
+        g = torch.Generator().manual_seed(11)
+        steps = []
+        nouns = ["chair", "mug", "knife", "spade"]
+        for step in range(10):
+            tasks = [1 + int(torch.randint(0, 3, (1,), generator=g)) for _ in range(B)]
+            cap_n = [f"sit {nouns[(step + i) % 4]}" for i in range(B)]
+            cap_s = ["sit something"[: T - 2] if False else "sit something"[-(T - 2):] for _ in range(B)]
+            tg_n, tg_s = [], []
+            for i in range(B):
+                nbox = 0 if (step == 2 and i == 1) else 1 + (i % 2)
+                s = cap_n[i].find(" ") + 1
+                tg_n.append({"boxes": torch.rand(nbox, 4, generator=g), "dataset_name": f"tdod_{tasks[i]}",
+                             "noun_tokens_positive": [[[s, len(cap_n[i])]] for _ in range(nbox)]})
+                tg_s.append({"boxes": torch.rand(max(nbox, 1), 4, generator=g), "dataset_name": f"tdod_{tasks[i]}"})
+            rec = {"tasks": tasks, "cap_n": cap_n, "cap_s": cap_s,
+                   "nbox": [len(t["boxes"]) for t in tg_n],
+                   "noun_tokens_positive": [t["noun_tokens_positive"] for t in tg_n]}
+            for tag, caps, tg in (("n", cap_n, tg_n), ("s", cap_s, tg_s)):
+                img = torch.randn(S_img + T, B, D, generator=g)
+                mc = {"img_memory": img.clone().requires_grad_(tag == "s"), "tokenized": tok(caps)}
+                Tt = mc["tokenized"]["input_ids"].shape[1]
+                mc["text_memory"] = mc["img_memory"][-Tt:]
+                rec["img_" + tag] = img
+                if tag == "n":
+                    mc = cc.update_memory(mc, tg, caps)
+                    rec["mod_n"] = mc["img_memory_mod"].detach().clone()
+                else:
+                    mc, loss = cc(mc, tg, caps)
+                    rec["mod_s"] = mc["img_memory_mod"].detach().clone()
+                    rec["loss"] = {k: float(v) for k, v in loss.items()}
+                    (loss["loss_cluster_feature"] * 3.0 + mc["img_memory_mod"].sum()).backward()
+                    rec["grad_img_s"] = mc["img_memory"].grad.clone()
+            rec["state"] = {k: v.clone() for k, v in cc.state_dict().items()}
+            steps.append(rec)
+        return {"init": init, "steps": steps, "dims": {"D": D, "T": T, "S_img": S_img, "B": B, "memory_size": 8,
+                                                     "cluster_num": 3}, "numpy_seed": 7}
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+
 def main():
     torch.set_num_threads(8)
     OUT.mkdir(parents=True, exist_ok=True)
@@ -150,6 +310,8 @@ def main():
     torch.save({"versions": v, "cases": matcher_cases(models)}, OUT / "matcher_cases.pt")
     torch.save({"versions": v, **config1(models, tok)}, OUT / "config1_r50.pt")
     torch.save({"versions": v, **config3_small(models, tok)}, OUT / "config3_r50_segm_small.pt")
+    torch.save({"versions": v, **config5_softkd_small(models, tok)}, OUT / "config5_softkd_small.pt")
+    torch.save({"versions": v, **cluster_cases(models, tok)}, OUT / "cluster_cases.pt")
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size // 1024, "KiB")
 
