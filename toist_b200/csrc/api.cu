@@ -37,8 +37,23 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int encode_tmap_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
+                          const uint32_t box[4], const uint32_t elem_stride[4], int elem_bytes,
+                          CUtensorMapDataType dtype);
+
 int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
                         const uint32_t box[4], const uint32_t elem_stride[4]) {
+  return encode_tmap_4d(out, ptr, dim, stride, box, elem_stride, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+
+int encode_tmap_f32_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
+                       const uint32_t box[4], const uint32_t elem_stride[4]) {
+  return encode_tmap_4d(out, ptr, dim, stride, box, elem_stride, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
+
+static int encode_tmap_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
+                          const uint32_t box[4], const uint32_t elem_stride[4], int elem_bytes,
+                          CUtensorMapDataType dtype) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(TOIST_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   TOIST_REQUIRE(ptr != nullptr, "tensor map: null base pointer");
@@ -53,14 +68,14 @@ int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4],
     bx[i] = box[i];
     es[i] = elem_stride[i];
     if (i > 0) {
-      TOIST_REQUIRE(stride[i] % 8 == 0, "tensor map: stride[%d]=%lld elements is not a multiple of 8 (16 bytes)", i,
-                    (long long)stride[i]);
+      TOIST_REQUIRE((stride[i] * elem_bytes) % 16 == 0, "tensor map: stride[%d]=%lld elements is not a multiple of 16 bytes",
+                    i, (long long)stride[i]);
       // a size-1 dimension may carry stride 0 in a torch view; TMA needs a positive multiple of 16 bytes
-      int64_t s = stride[i] > 0 ? stride[i] : 8;
-      gstr[i - 1] = (cuuint64_t)s * 2;
+      int64_t s = stride[i] > 0 ? stride[i] : 16 / elem_bytes;
+      gstr[i - 1] = (cuuint64_t)s * (cuuint64_t)elem_bytes;
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
+  CUresult r = fn(out, dtype, 4, const_cast<void*>(ptr), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)

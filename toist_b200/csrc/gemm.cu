@@ -392,6 +392,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       }
     }
+    if constexpr (EPI == 3) {
+      // ---- fp32 weight gradients accumulated across split-K CTAs: the 128 x BN tile is staged in shared memory
+      // (BN/32 slabs of 128 rows x 128 B, SWIZZLE_128B) and added to global memory by TMA reduce, i.e. one full-line
+      // L2 reduction per row and 32 columns instead of 32 scattered fp32 atomics per thread and column.
+      // Columns past n_cols hold exact zeros (their B operand was TMA zero fill) and rows past m_rows are clipped
+      // by the tensor map, so the whole tile is written unconditionally.
+      const bool leader = (warp == 2 && lane == 0);
+      const uint32_t rx = (uint32_t)(r & 7);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.n_cols) break;  // warp-uniform
+        uint32_t raw[32];
+        if (n_iters > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = 0u;
+        }
+        const float sc = p.alpha * rscale;
+        uint8_t* slab = smem + (c0 >> 5) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 f;
+          f.x = __uint_as_float(raw[g * 4 + 0]) * sc;
+          f.y = __uint_as_float(raw[g * 4 + 1]) * sc;
+          f.z = __uint_as_float(raw[g * 4 + 2]) * sc;
+          f.w = __uint_as_float(raw[g * 4 + 3]) * sc;
+          *reinterpret_cast<float4*>(slab + ((((uint32_t)g) ^ rx) << 4)) = f;
+        }
+      }
+      fence_proxy_async();
+      named_barrier_sync(1, 128);
+      if (leader) {
+        const int col0 = p.taps[tap_w].col + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32)
+          if (n0 + c0 < p.n_cols) tma_reduce_add_4d(&tma_out, smem + (c0 >> 5) * 16384, col0 + c0, m0, by, bn);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+    }
     if constexpr (EPI == 2) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -567,6 +609,7 @@ template <int BN, int MODE>
 static int dispatch_epi(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
   if constexpr (MODE == TOIST_GEMM_WGRAD) {
     // weight gradients are fp32; the batched dV / dK products of attention write bf16 through the generic path
+    if (kp.epi == 3) return launch_gemm<BN, MODE, 3>(maps, kp, grid, stream);
     if (kp.epi == 1) return launch_gemm<BN, MODE, 1>(maps, kp, grid, stream);
     return launch_gemm<BN, MODE, 2>(maps, kp, grid, stream);
   } else {
@@ -589,6 +632,14 @@ static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 gr
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static bool reduce_epilogue_enabled() {  // TOIST_GEMM_ATOMIC_WGRAD=1 selects the scattered-atomics epilogue (A/B runs)
+  static const bool on = []() {
+    const char* e = getenv("TOIST_GEMM_ATOMIC_WGRAD");
+    return !(e && atoi(e) != 0);
+  }();
+  return on;
+}
 
 }  // namespace toist
 
@@ -715,6 +766,19 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
                       (uint32_t)d->tile_n};
   uint32_t bes[4] = {1, (uint32_t)d->stride_x, (uint32_t)d->stride_y, 1};
   if ((rc = encode_tmap_bf16_4d(&mb, d->b.ptr, d->b.dim, d->b.stride, bbox, bes)) != TOIST_OK) return rc;
+  // accumulating fp32 weight gradients: TMA reduce-add epilogue when every row / tap offset is 16-byte aligned
+  if (kp.epi == 1 && d->accumulate && vec && d->out_sx % 4 == 0 && d->act == TOIST_ACT_NONE &&
+      d->col_scale == nullptr && d->col_shift == nullptr && reduce_epilogue_enabled()) {
+    bool taps_ok = true;
+    for (int i = 0; i < d->n_taps; ++i) taps_ok = taps_ok && (d->taps[i].col % 4 == 0);
+    if (taps_ok) {
+      const int64_t odim[4] = {d->out_sx, d->m_rows, kp.batch_y, kp.batch_n};
+      const int64_t ostr[4] = {1, d->out_sx, d->out_sy, d->out_sn};
+      const uint32_t obox[4] = {32, 128, 1, 1};
+      if ((rc = encode_tmap_f32_4d(&maps[2], d->out, odim, ostr, obox, ones)) != TOIST_OK) return rc;
+      kp.epi = 3;
+    }
+  }
   dim3 grid((unsigned)m_tiles, (unsigned)(n_tiles * d->n_taps), (unsigned)(kp.batch_y * kp.batch_n * kp.splits));
   return dispatch_bn<TOIST_GEMM_WGRAD>(bn, maps, kp, grid, stream);
 }

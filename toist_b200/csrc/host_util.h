@@ -31,6 +31,10 @@ int set_error(int code, const char* fmt, ...);
 int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
                         const uint32_t box[4], const uint32_t elem_stride[4]);
 
+// Same for fp32 tensors (inner box <= 32 elements = one 128-byte swizzle row); used by the reduce-add epilogue.
+int encode_tmap_f32_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
+                       const uint32_t box[4], const uint32_t elem_stride[4]);
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // measurement hook (toist_debug_skip_gemm): when set, toist_gemm validates nothing and launches nothing
