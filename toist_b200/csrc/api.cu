@@ -1,5 +1,6 @@
 // C-ABI plumbing: version, error text, device check, TMA tensor-map encoding through the driver entry point.
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 #include "host_util.h"
@@ -10,6 +11,14 @@ static thread_local char g_err[512] = "";
 static int g_skip_gemm = 0;
 
 bool skip_gemm() { return g_skip_gemm != 0; }
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("TOIST_PDL");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

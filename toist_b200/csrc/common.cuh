@@ -26,6 +26,18 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel is launched with programmaticStreamSerializationAllowed (host_util.h: launch_pdl): its CTAs may be
+// scheduled while the previous kernel of the stream is still draining.  `pdl_trigger` lets the NEXT kernel start its
+// own prologue early; `pdl_wait` blocks until the PREVIOUS kernel has completed and its writes are visible, and must
+// precede every global-memory access.  Both are no-ops for a normally serialised launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -137,6 +137,7 @@ __device__ int lsap_warp(const float* __restrict__ c, long long si, long long sj
 __global__ void lsap_batched_kernel(const float* __restrict__ cost, const int* __restrict__ n_rows,
                                     const int* __restrict__ n_cols, int* __restrict__ col_of_row, int* __restrict__ flags,
                                     int ld_r, int ld_c) {
+  pdl_prologue();
   __shared__ LsapShared w;
   const int p = blockIdx.x, lane = threadIdx.x;
   const int R = n_rows[p], C = n_cols[p];
@@ -172,6 +173,7 @@ __global__ void lsap_batched_kernel(const float* __restrict__ cost, const int* _
 // bi[l, b, q] = (sum_{c < C-1} softmax(logits)[c], softmax(logits)[C-1])          (mdetr.py:552-556)
 // one warp per (l, b, q) row
 __global__ void biprob_kernel(const float* __restrict__ logits, float* __restrict__ bi, long long rows, int C) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -199,6 +201,7 @@ __global__ void softkd_cost_kernel(const float* __restrict__ bi_n, const float* 
                                    const int* __restrict__ match_n, const int* __restrict__ match_s,
                                    const int* __restrict__ tgt_count, int* __restrict__ fp_n, int* __restrict__ fp_s,
                                    int* __restrict__ n_fp, float* __restrict__ cost, int B, int Q, int Tmax) {
+  pdl_prologue();
   extern __shared__ int sk_smem[];
   int* tp_n = sk_smem;       // [Q] 1 = matched to a target
   int* tp_s = tp_n + Q;
@@ -260,6 +263,7 @@ __global__ void softkd_loss_kernel(const float* __restrict__ bi_n, const float* 
                                    const int* __restrict__ fp_s, const int* __restrict__ n_fp,
                                    const int* __restrict__ col_of_row, const int* __restrict__ flags, int* __restrict__ pair_n,
                                    float* __restrict__ loss, int B, int Q, int Tmax) {
+  pdl_prologue();
   const int lb = blockIdx.x, b = lb % B, l = lb / B;
   const int T = min(tgt_count[b], Tmax);
   int* pn = pair_n + (size_t)lb * Q;
@@ -307,6 +311,7 @@ __global__ void softkd_bwd_kernel(const float* __restrict__ logits_s, const floa
                                   const int* __restrict__ tgt_count, const int* __restrict__ n_fp,
                                   const float* __restrict__ gout, float* __restrict__ dlogits, long long rows, int B,
                                   int Q, int C, int Tmax) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -345,6 +350,7 @@ __global__ void softkd_bwd_kernel(const float* __restrict__ logits_s, const floa
 // One CTA; stops when (sum_k ||c_k - c_k_prev||)^2 < tol or after max_iter iterations.
 __global__ void kmeans_kernel(const float* __restrict__ X, float* __restrict__ centers, int* __restrict__ choice,
                               int* __restrict__ iters, int N, int D, int K, float tol, int max_iter) {
+  pdl_prologue();
   extern __shared__ float km_smem[];
   float* cen = km_smem;                 // [K, D]
   float* shift2 = cen + K * D;          // [K]
@@ -412,6 +418,7 @@ __global__ void kmeans_kernel(const float* __restrict__ X, float* __restrict__ c
 // choice[m] = argmin_k ||x_m - c_k||^2 (kmeans_predict, kmeans.py:99-133); one warp per row
 __global__ void kmeans_predict_kernel(const float* __restrict__ X, const float* __restrict__ centers,
                                       int* __restrict__ choice, int M, int D, int K) {
+  pdl_prologue();
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -435,6 +442,7 @@ __global__ void kmeans_predict_kernel(const float* __restrict__ X, const float* 
 // out[m, d] = sum_t w[m, t] * x[t, m, d]   (x fp32 [T, M, D] sequence layout; w carries the 1/n of the token means)
 __global__ void token_wsum_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
                                   int T, int M, int D) {
+  pdl_prologue();
   const int m = blockIdx.x;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float acc = 0.f;
@@ -449,6 +457,7 @@ __global__ void token_wsum_kernel(const float* __restrict__ x, const float* __re
 // dx[t, m, d] = w[m, t] * dout[m, d]
 __global__ void token_wsum_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ w, float* __restrict__ dx,
                                       int T, int M, int D) {
+  pdl_prologue();
   const int m = blockIdx.x % M, t = blockIdx.x / M;
   const float wt = w[m * T + t];
   for (int d = threadIdx.x; d < D; d += blockDim.x) dx[((size_t)t * M + m) * D + d] = wt * dout[(size_t)m * D + d];
@@ -457,6 +466,7 @@ __global__ void token_wsum_bwd_kernel(const float* __restrict__ dout, const floa
 // x[t, m, :] = feat[m, :] for every selected token (in-place replacement of the caption tokens by the cluster centre)
 __global__ void token_fill_kernel(float* __restrict__ x, const uint8_t* __restrict__ sel, const float* __restrict__ feat,
                                   int T, int M, int D) {
+  pdl_prologue();
   const int m = blockIdx.x;
   for (int t = 0; t < T; ++t) {
     if (!sel[m * T + t]) continue;
@@ -469,6 +479,7 @@ __global__ void token_fill_kernel(float* __restrict__ x, const uint8_t* __restri
 // gradient w.r.t. a.  One CTA.
 __global__ void mse_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ use,
                                 float* __restrict__ loss, float* __restrict__ da, int M, int D) {
+  pdl_prologue();
   int cnt = 0;
   for (int m = 0; m < M; ++m) cnt += use[m] ? 1 : 0;
   float acc = 0.f;
@@ -496,6 +507,7 @@ __global__ void mse_rows_kernel(const float* __restrict__ a, const float* __rest
 // pairwise L1 distance (torch.cdist p=1, mdetr.py:98): a [n, D], b [m, D] -> out [n, m]; one warp per entry
 __global__ void cdist_l1_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n,
                                 int m, int D) {
+  pdl_prologue();
   const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (e >= (long long)n * m) return;
@@ -519,7 +531,7 @@ int toist_lsap_batched(const float* cost, const int32_t* n_rows, const int32_t* 
                 "toist_lsap_batched: problems up to %d x %d are supported (got %d x %d)", kLsapMax, kLsapMax, ld_rows,
                 ld_cols);
   if (n_problems == 0) return TOIST_OK;
-  lsap_batched_kernel<<<n_problems, 32, 0, (cudaStream_t)stream>>>(cost, n_rows, n_cols, col_of_row, flags, ld_rows,
+  launch_pdl(lsap_batched_kernel, dim3(n_problems), dim3(32), 0, (cudaStream_t)stream, cost, n_rows, n_cols, col_of_row, flags, ld_rows,
                                                                    ld_cols);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -540,16 +552,16 @@ int toist_softkd_fwd(const float* logits_noun, const float* logits_sth, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)n_layers * batch * n_queries;
   const unsigned gb = (unsigned)((rows + 7) / 8);
-  biprob_kernel<<<gb, 256, 0, st>>>(logits_noun, bi_noun, rows, n_classes);
-  biprob_kernel<<<gb, 256, 0, st>>>(logits_sth, bi_sth, rows, n_classes);
+  launch_pdl(biprob_kernel, dim3(gb), dim3(256), 0, st, logits_noun, bi_noun, rows, n_classes);
+  launch_pdl(biprob_kernel, dim3(gb), dim3(256), 0, st, logits_sth, bi_sth, rows, n_classes);
   const int P = n_layers * batch;
-  softkd_cost_kernel<<<P, 256, (2 * n_queries + 2) * sizeof(int), st>>>(bi_noun, bi_sth, boxes_noun, boxes_sth,
+  launch_pdl(softkd_cost_kernel, dim3(P), dim3(256), (2 * n_queries + 2) * sizeof(int), st, bi_noun, bi_sth, boxes_noun, boxes_sth,
                                                                        match_noun, match_sth, tgt_count, fp_noun, fp_sth,
                                                                        n_fp, cost, batch, n_queries, t_max);
   TOIST_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * n_layers, st));
   // rows = student false positives (n_fp plane 1), columns = teacher false positives (plane 0)
-  lsap_batched_kernel<<<P, 32, 0, st>>>(cost, n_fp + P, n_fp, col_of_row, flags, n_queries, n_queries);
-  softkd_loss_kernel<<<P, 128, 0, st>>>(bi_noun, bi_sth, match_noun, match_sth, tgt_count, fp_noun, fp_sth, n_fp,
+  launch_pdl(lsap_batched_kernel, dim3(P), dim3(32), 0, st, cost, n_fp + P, n_fp, col_of_row, flags, n_queries, n_queries);
+  launch_pdl(softkd_loss_kernel, dim3(P), dim3(128), 0, st, bi_noun, bi_sth, match_noun, match_sth, tgt_count, fp_noun, fp_sth, n_fp,
                                         col_of_row, flags, pair_noun, loss, batch, n_queries, t_max);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -562,7 +574,7 @@ int toist_softkd_bwd(const float* logits_sth, const float* bi_noun, const float*
                 "toist_softkd_bwd: null pointer");
   const long long rows = (long long)n_layers * batch * n_queries;
   if (rows == 0) return TOIST_OK;
-  softkd_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(softkd_bwd_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 
       logits_sth, bi_noun, bi_sth, pair_noun, tgt_count, n_fp, gout, dlogits_sth, rows, batch, n_queries, n_classes,
       t_max);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -575,7 +587,7 @@ int toist_kmeans(const float* x, float* centers, int32_t* choice, int32_t* iters
   TOIST_REQUIRE(n >= 1 && dim >= 1 && k >= 1 && max_iter >= 1, "toist_kmeans: bad sizes");
   const size_t smem = ((size_t)k * dim + 2 * k) * sizeof(float);
   TOIST_REQUIRE(smem <= 48 * 1024, "toist_kmeans: %d x %d centres do not fit shared memory", k, dim);
-  kmeans_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(x, centers, choice, iters, n, dim, k, tol, max_iter);
+  launch_pdl(kmeans_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream, x, centers, choice, iters, n, dim, k, tol, max_iter);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -584,7 +596,7 @@ int toist_kmeans_predict(const float* x, const float* centers, int32_t* choice, 
                          void* stream) {
   TOIST_REQUIRE(x && centers && choice, "toist_kmeans_predict: null pointer");
   if (m == 0) return TOIST_OK;
-  kmeans_predict_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, centers, choice, m, dim, k);
+  launch_pdl(kmeans_predict_kernel, dim3((m + 3) / 4), dim3(128), 0, (cudaStream_t)stream, x, centers, choice, m, dim, k);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -593,7 +605,7 @@ int toist_token_wsum(const float* x, const float* w, float* out, int32_t n_token
                      void* stream) {
   TOIST_REQUIRE(x && w && out, "toist_token_wsum: null pointer");
   if (batch == 0) return TOIST_OK;
-  token_wsum_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(x, w, out, n_tokens, batch, dim);
+  launch_pdl(token_wsum_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, x, w, out, n_tokens, batch, dim);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -602,7 +614,7 @@ int toist_token_wsum_bwd(const float* dout, const float* w, float* dx, int32_t n
                          void* stream) {
   TOIST_REQUIRE(dout && w && dx, "toist_token_wsum_bwd: null pointer");
   if (batch * n_tokens == 0) return TOIST_OK;
-  token_wsum_bwd_kernel<<<batch * n_tokens, 256, 0, (cudaStream_t)stream>>>(dout, w, dx, n_tokens, batch, dim);
+  launch_pdl(token_wsum_bwd_kernel, dim3(batch * n_tokens), dim3(256), 0, (cudaStream_t)stream, dout, w, dx, n_tokens, batch, dim);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -611,7 +623,7 @@ int toist_token_fill(float* x, const uint8_t* sel, const float* feat, int32_t n_
                      void* stream) {
   TOIST_REQUIRE(x && sel, "toist_token_fill: null pointer");
   if (batch == 0) return TOIST_OK;
-  token_fill_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(x, sel, feat, n_tokens, batch, dim);
+  launch_pdl(token_fill_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, x, sel, feat, n_tokens, batch, dim);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -619,7 +631,7 @@ int toist_token_fill(float* x, const uint8_t* sel, const float* feat, int32_t n_
 int toist_mse_rows(const float* a, const float* b, const uint8_t* use, float* loss, float* da, int32_t rows, int32_t dim,
                    void* stream) {
   TOIST_REQUIRE(a && b && use && loss, "toist_mse_rows: null pointer");
-  mse_rows_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, b, use, loss, da, rows, dim);
+  launch_pdl(mse_rows_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, a, b, use, loss, da, rows, dim);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -628,7 +640,7 @@ int toist_cdist_l1(const float* a, const float* b, float* out, int32_t n, int32_
   TOIST_REQUIRE(a && b && out, "toist_cdist_l1: null pointer");
   const long long e = (long long)n * m;
   if (e == 0) return TOIST_OK;
-  cdist_l1_kernel<<<(unsigned)((e + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, m, dim);
+  launch_pdl(cdist_l1_kernel, dim3((unsigned)((e + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, a, b, out, n, m, dim);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

@@ -18,6 +18,7 @@ struct PrepItem {
 };
 
 __global__ void weight_prep_kernel(const PrepItem* __restrict__ items, int n_items) {
+  pdl_prologue();
   // binary search the item owning this block
   int lo = 0, hi = n_items - 1;
   while (lo < hi) {
@@ -54,6 +55,7 @@ __global__ void weight_prep_kernel(const PrepItem* __restrict__ items, int n_ite
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_prologue();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i);
@@ -67,6 +69,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 }
 
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_prologue();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const uint4 u = *reinterpret_cast<const uint4*>(src + i);
@@ -81,6 +84,7 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
 // out = a + b (bf16), optional third addend c; 8 elements per thread
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                 const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_prologue();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const uint4 ua = *reinterpret_cast<const uint4*>(a + i), ub = *reinterpret_cast<const uint4*>(b + i);
@@ -104,6 +108,7 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 // images fp32 NCHW [N,3,H,W] -> patches bf16 [N*Ho*Wo, ldk] for the 7x7/2 pad-3 stem conv; column = (ky*7+kx)*3+c.
 __global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W,
                                    int Ho, int Wo, int ldk) {
+  pdl_prologue();
   const long long pix = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pix >= (long long)N * Ho * Wo) return;
@@ -126,6 +131,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16*
 // NHWC bf16; each thread handles 8 channels of one output pixel
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                     int W, int C, int Ho, int Wo) {
+  pdl_prologue();
   const int cg = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * Ho * Wo * cg) return;
@@ -163,6 +169,7 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long R, int C, long long ld,
                               int rows_per_block) {
+  pdl_prologue();
   const int c = blockIdx.x * 64 + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(R, r0 + rows_per_block);
@@ -182,6 +189,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
 // load each), the 8 warps of a block take interleaved rows, partial sums meet in shared memory.
 __global__ void colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long R, int C,
                                        long long ld, int rows_per_block) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + lane * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -214,6 +222,7 @@ __global__ void colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, floa
 // dpre = dy * gelu'(pre)   (erf GELU), bf16
 __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
                                 __nv_bfloat16* __restrict__ dx, long long n) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = __bfloat162float(pre[i]);
@@ -225,6 +234,7 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
 // dz = (dy + dy2) * (y > 0), bf16, 8 elements per thread
 __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
                                 const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_prologue();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const uint4 ua = *reinterpret_cast<const uint4*>(dy + i), uy = *reinterpret_cast<const uint4*>(y + i);
@@ -249,6 +259,7 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
 // dx = dy * y * (1 - y), fp32 (sigmoid output y)
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
                                    long long n) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   dx[i] = dy[i] * y[i] * (1.f - y[i]);
@@ -257,6 +268,7 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __
 // out[a, c] (+)= sum_r x[a, r, c]   (e.g. query_embed gradient summed over the batch); bf16 or fp32 in, fp32 out
 template <typename T>
 __global__ void sum_mid_kernel(const T* __restrict__ x, float* __restrict__ out, int A, int R, int C, int accumulate) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)A * C) return;
   const int a = (int)(i / C), c = (int)(i % C);
@@ -270,6 +282,7 @@ __global__ void sum_mid_kernel(const T* __restrict__ x, float* __restrict__ out,
 
 // out[a, r, c] = x[a, c]  (bf16 out; x fp32) — query_embed broadcast over the batch
 __global__ void bcast_mid_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int A, int R, int C) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)A * R * C) return;
   const int c = (int)(i % C);
@@ -279,6 +292,7 @@ __global__ void bcast_mid_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 
 // NCHW fp32 -> NHWC bf16 and back (boundary conversions for tensors handed to / taken from the caller)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int C, int HW) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * C * HW) return;
   const int c = (int)(i % C);
@@ -288,6 +302,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
   y[i] = __float2bfloat16_rn(x[((long long)n * C + c) * HW + hw]);
 }
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int N, int C, int HW) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * C * HW) return;
   const int hw = (int)(i % HW);
@@ -300,6 +315,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 // dst[r, 0:ld] = bf16(src[r, 0:n]) zero-padded to ld columns (TMA needs 16-byte rows: e.g. the 4-wide box head)
 __global__ void cast_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int n,
                                 int ld) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ld) return;
   const long long r = i / ld;
@@ -312,6 +328,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ out, long long n,
                                const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thr, float scale) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = dropout_key(seed, site);
@@ -326,6 +343,7 @@ __global__ void dropout_kernel(const T* __restrict__ x, const T* __restrict__ re
 
 // dst[a, c, b] = src[a, b, c]  (fp32) — conv weight gradients come out of the WGRAD engine as [Cout][taps][Cin]
 __global__ void permute_021_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int B, int C) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)A * B * C) return;
   const int b = (int)(i % B);
@@ -340,6 +358,7 @@ __global__ void permute_021_kernel(const float* __restrict__ src, float* __restr
 __global__ void key_mask_kernel(const uint8_t* __restrict__ pad, const long long* __restrict__ text_attn,
                                 uint8_t* __restrict__ small, uint8_t* __restrict__ key, int B, int H, int W, int h,
                                 int w, int L) {
+  pdl_prologue();
   const int S = h * w + L;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * S) return;
@@ -372,7 +391,7 @@ extern "C" {
 // ceil(rows*cols / 2048) over items.
 int toist_weight_prep(const void* items_dev, int32_t n_items, int32_t total_blocks, void* stream) {
   TOIST_REQUIRE(items_dev != nullptr && n_items > 0 && total_blocks > 0, "toist_weight_prep: bad arguments");
-  weight_prep_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PrepItem*>(items_dev),
+  launch_pdl(weight_prep_kernel, dim3(total_blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const PrepItem*>(items_dev),
                                                                      n_items);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -381,7 +400,7 @@ int toist_weight_prep(const void* items_dev, int32_t n_items, int32_t total_bloc
 int toist_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   TOIST_REQUIRE(src && dst, "toist_cast_f32_bf16: null pointer");
   if (n == 0) return TOIST_OK;
-  cast_f32_bf16_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  launch_pdl(cast_f32_bf16_kernel, dim3(nblk(n, 2048)), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -389,7 +408,7 @@ int toist_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
 int toist_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
   TOIST_REQUIRE(src && dst, "toist_cast_bf16_f32: null pointer");
   if (n == 0) return TOIST_OK;
-  cast_bf16_f32_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, n);
+  launch_pdl(cast_bf16_f32_kernel, dim3(nblk(n, 2048)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src, dst, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -397,7 +416,7 @@ int toist_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
 int toist_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {
   TOIST_REQUIRE(a && b && out, "toist_add_bf16: null pointer");
   if (n == 0) return TOIST_OK;
-  add_bf16_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+  launch_pdl(add_bf16_kernel, dim3(nblk(n, 2048)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
                                                                    (const __nv_bfloat16*)c, (__nv_bfloat16*)out, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -407,7 +426,7 @@ int toist_stem_im2col(const float* images, void* patches, int32_t n, int32_t h, 
   TOIST_REQUIRE(images && patches && ldk >= 147 && ldk % 8 == 0, "toist_stem_im2col: bad arguments");
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
   const long long pix = (long long)n * ho * wo;
-  stem_im2col_kernel<<<nblk(pix, 8), 256, 0, (cudaStream_t)stream>>>(images, (__nv_bfloat16*)patches, n, h, w, ho, wo,
+  launch_pdl(stem_im2col_kernel, dim3(nblk(pix, 8)), dim3(256), 0, (cudaStream_t)stream, images, (__nv_bfloat16*)patches, n, h, w, ho, wo,
                                                                      ldk);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -417,7 +436,7 @@ int toist_maxpool3x3s2(const void* x, void* y, int32_t n, int32_t h, int32_t w, 
   TOIST_REQUIRE(x && y && c % 8 == 0, "toist_maxpool3x3s2: channels must be a multiple of 8");
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
-  maxpool3x3s2_kernel<<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+  launch_pdl(maxpool3x3s2_kernel, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
                                                                           n, h, w, c, ho, wo);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -434,7 +453,7 @@ int toist_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t
     if (chunks < 1) chunks = 1;
     const int rpb = (int)((rows + chunks - 1) / chunks);
     dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb));
-    colsum_bf16_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
+    launch_pdl(colsum_bf16_vec_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
     TOIST_CHECK_CUDA(cudaGetLastError());
     return TOIST_OK;
   }
@@ -443,9 +462,9 @@ int toist_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t
   const int rpb = (int)((rows + chunks - 1) / chunks);
   dim3 grid((cols + 63) / 64, chunks), block(64, 4);
   if (dtype == TOIST_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
+    launch_pdl((colsum_kernel<__nv_bfloat16>), dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, out, rows, cols, ld, rpb);
   else
-    colsum_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, out, rows, cols, ld, rpb);
+    launch_pdl((colsum_kernel<float>), dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const float*)x, out, rows, cols, ld, rpb);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -453,7 +472,7 @@ int toist_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t
 int toist_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream) {
   TOIST_REQUIRE(dy && pre && dx, "toist_gelu_bwd: null pointer");
   if (n == 0) return TOIST_OK;
-  gelu_bwd_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre,
+  launch_pdl(gelu_bwd_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pre,
                                                                   (__nv_bfloat16*)dx, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -462,7 +481,7 @@ int toist_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* s
 int toist_relu_bwd(const void* dy, const void* dy2, const void* y, void* out, int64_t n, void* stream) {
   TOIST_REQUIRE(dy && y && out, "toist_relu_bwd: null pointer");
   if (n == 0) return TOIST_OK;
-  relu_bwd_kernel<<<nblk(n, 2048), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
+  launch_pdl(relu_bwd_kernel, dim3(nblk(n, 2048)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy2,
                                                                    (const __nv_bfloat16*)y, (__nv_bfloat16*)out, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -471,7 +490,7 @@ int toist_relu_bwd(const void* dy, const void* dy2, const void* y, void* out, in
 int toist_sigmoid_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
   TOIST_REQUIRE(dy && y && dx, "toist_sigmoid_bwd: null pointer");
   if (n == 0) return TOIST_OK;
-  sigmoid_bwd_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
+  launch_pdl(sigmoid_bwd_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, dy, y, dx, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -482,9 +501,9 @@ int toist_sum_mid(const void* x, int32_t dtype, float* out, int32_t a, int32_t r
   const long long n = (long long)a * c;
   if (n == 0) return TOIST_OK;
   if (dtype == TOIST_BF16)
-    sum_mid_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, a, r, c, accumulate);
+    launch_pdl((sum_mid_kernel<__nv_bfloat16>), dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, out, a, r, c, accumulate);
   else
-    sum_mid_kernel<float><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, out, a, r, c, accumulate);
+    launch_pdl((sum_mid_kernel<float>), dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, (const float*)x, out, a, r, c, accumulate);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -493,7 +512,7 @@ int toist_bcast_mid(const float* x, void* out, int32_t a, int32_t r, int32_t c, 
   TOIST_REQUIRE(x && out, "toist_bcast_mid: null pointer");
   const long long n = (long long)a * r * c;
   if (n == 0) return TOIST_OK;
-  bcast_mid_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, a, r, c);
+  launch_pdl(bcast_mid_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)out, a, r, c);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -502,7 +521,7 @@ int toist_nchw_to_nhwc(const float* x, void* y, int32_t n, int32_t c, int32_t hw
   TOIST_REQUIRE(x && y, "toist_nchw_to_nhwc: null pointer");
   const long long t = (long long)n * c * hw;
   if (t == 0) return TOIST_OK;
-  nchw_to_nhwc_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n, c, hw);
+  launch_pdl(nchw_to_nhwc_kernel, dim3(nblk(t, 256)), dim3(256), 0, (cudaStream_t)stream, x, (__nv_bfloat16*)y, n, c, hw);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -511,7 +530,7 @@ int toist_nhwc_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw
   TOIST_REQUIRE(x && y, "toist_nhwc_to_nchw: null pointer");
   const long long t = (long long)n * c * hw;
   if (t == 0) return TOIST_OK;
-  nhwc_to_nchw_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, n, c, hw);
+  launch_pdl(nhwc_to_nchw_kernel, dim3(nblk(t, 256)), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, y, n, c, hw);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -519,7 +538,7 @@ int toist_nhwc_to_nchw(const void* x, float* y, int32_t n, int32_t c, int32_t hw
 int toist_cast_pad_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n, int32_t ld, void* stream) {
   TOIST_REQUIRE(src && dst && ld >= n, "toist_cast_pad_f32_bf16: bad arguments");
   if (rows * ld == 0) return TOIST_OK;
-  cast_pad_kernel<<<nblk(rows * ld, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, rows, n, ld);
+  launch_pdl(cast_pad_kernel, dim3(nblk(rows * ld, 256)), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, rows, n, ld);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -532,10 +551,10 @@ int toist_dropout(const void* x, const void* res, void* out, int64_t n, int32_t 
   const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
   const float scale = 1.f / (1.f - p);
   if (dtype == TOIST_BF16)
-    dropout_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl((dropout_kernel<__nv_bfloat16>), dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, n, (const unsigned long long*)seed, site, thr, scale);
   else
-    dropout_kernel<float><<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl((dropout_kernel<float>), dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const float*)x, (const float*)res, (float*)out, n, (const unsigned long long*)seed, site, thr, scale);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -545,7 +564,7 @@ int toist_permute_021(const float* src, float* dst, int32_t a, int32_t b, int32_
   TOIST_REQUIRE(src && dst, "toist_permute_021: null pointer");
   const long long t = (long long)a * b * c;
   if (t == 0) return TOIST_OK;
-  permute_021_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, a, b, c);
+  launch_pdl(permute_021_kernel, dim3(nblk(t, 256)), dim3(256), 0, (cudaStream_t)stream, src, dst, a, b, c);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -557,7 +576,7 @@ int toist_key_mask(const uint8_t* pad_mask, const int64_t* text_attention, uint8
   TOIST_REQUIRE(n_text == 0 || text_attention != nullptr || key_mask == nullptr, "toist_key_mask: text mask missing");
   const long long t = (long long)batch * (out_h * out_w + n_text);
   if (t == 0) return TOIST_OK;
-  key_mask_kernel<<<nblk(t, 256), 256, 0, (cudaStream_t)stream>>>(pad_mask, (const long long*)text_attention,
+  launch_pdl(key_mask_kernel, dim3(nblk(t, 256)), dim3(256), 0, (cudaStream_t)stream, pad_mask, (const long long*)text_attention,
                                                                   small_mask, key_mask, batch, in_h, in_w, out_h,
                                                                   out_w, n_text);
   TOIST_CHECK_CUDA(cudaGetLastError());

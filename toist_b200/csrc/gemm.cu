@@ -82,6 +82,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();  // the next kernel may start its prologue; it still waits for this grid before touching memory
 
   // ---------------- tile decode
   int x0 = 0, y0 = 0, i0 = 0;  // FWD/DGRAD: pixel-tile origin
@@ -137,6 +138,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // barrier init, descriptor prefetch and the TMEM allocation above overlap the previous kernel's tail
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -600,7 +602,7 @@ static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
-  kfn<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  launch_pdl(kfn, dim3(grid), dim3(kThreads), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

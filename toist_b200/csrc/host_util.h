@@ -35,6 +35,26 @@ int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4],
 int encode_tmap_f32_4d(CUtensorMap* out, const void* ptr, const int64_t dim[4], const int64_t stride[4],
                        const uint32_t box[4], const uint32_t elem_stride[4]);
 
+// Kernel launch with programmatic dependent launch enabled (TOIST_PDL=0 in the environment restores plain stream
+// serialisation for A/B measurements).  Every kernel launched through here calls pdl_wait() before touching memory.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // measurement hook (toist_debug_skip_gemm): when set, toist_gemm validates nothing and launches nothing

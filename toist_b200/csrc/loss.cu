@@ -26,6 +26,7 @@ __global__ void token_ce_kernel(const float* __restrict__ logits, const int* __r
                                 const int* __restrict__ tgt_count, const float* __restrict__ posmap,
                                 const float* __restrict__ num_boxes, float* __restrict__ row_loss,
                                 float* __restrict__ dlogits, int rows, int B, int Q, int C, int Tmax, float eos_coef) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -111,6 +112,7 @@ __global__ void box_loss_kernel(const float* __restrict__ boxes, const int* __re
                                 const float* __restrict__ num_boxes, float* __restrict__ pair_l1,
                                 float* __restrict__ pair_giou, float* __restrict__ dboxes_l1,
                                 float* __restrict__ dboxes_giou, int B, int Q, int Tmax) {
+  pdl_prologue();
   const int lb = blockIdx.x;
   const int b = lb % B;
   const int T = min(tgt_count[b], Tmax);
@@ -151,6 +153,7 @@ __global__ void box_loss_kernel(const float* __restrict__ boxes, const int* __re
 // ---------------------------------------------------------------------------------------------- cardinality
 // grid = L*B, one warp per query row; card[l,b] = #(argmax != C-1)
 __global__ void cardinality_kernel(const float* __restrict__ logits, int* __restrict__ card, int Q, int C) {
+  pdl_prologue();
   const int lb = blockIdx.x;
   __shared__ int cnt;
   if (threadIdx.x == 0) cnt = 0;
@@ -189,6 +192,7 @@ __global__ void contrastive_kernel(const float* __restrict__ pq, const float* __
                                    const uint8_t* __restrict__ tok_pos, const float* __restrict__ num_boxes,
                                    float* __restrict__ img_loss, float* __restrict__ dpq, float* __restrict__ dpt,
                                    int B, int Q, int K, int D, int Tmax, float inv_temp) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float* lg = sm;                                        // [Q][K]
   float* dl = lg + Q * K;                                // [Q][K]
@@ -298,6 +302,7 @@ __global__ void criterion_reduce_kernel(const float* __restrict__ row_loss, cons
                                         const float* __restrict__ img_loss, const int* __restrict__ tgt_count,
                                         const float* __restrict__ num_boxes, const int* __restrict__ flags,
                                         float* __restrict__ out, int L, int B, int Q, int Tmax) {
+  pdl_prologue();
   __shared__ float red[32];
   const int l = blockIdx.x;
   const float inv_nb = 1.f / num_boxes[0];
@@ -334,6 +339,7 @@ __global__ void criterion_reduce_kernel(const float* __restrict__ row_loss, cons
 // y[i]    = sum_l x[l, i] * g[l]      (reduce == 1)
 __global__ void scale_layers_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ y,
                                     int L, long long n, int reduce) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (reduce) {
@@ -349,6 +355,7 @@ __global__ void scale_layers_kernel(const float* __restrict__ x, const float* __
 __global__ void scale_layers2_kernel(const float* __restrict__ x1, const float* __restrict__ g1,
                                      const float* __restrict__ x2, const float* __restrict__ g2, float* __restrict__ y,
                                      int L, long long n) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   for (int l = 0; l < L; ++l) y[(size_t)l * n + i] = x1[(size_t)l * n + i] * g1[l] + x2[(size_t)l * n + i] * g2[l];
@@ -365,7 +372,7 @@ int toist_token_ce(const float* logits, const int32_t* match_q, const int32_t* t
                    int32_t n_queries, int32_t n_classes, int32_t t_max, float eos_coef, void* stream) {
   TOIST_REQUIRE(logits && match_q && tgt_count && posmap && num_boxes && row_loss, "toist_token_ce: null pointer");
   const int rows = n_layers * batch * n_queries;
-  token_ce_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(logits, match_q, tgt_count, posmap, num_boxes,
+  launch_pdl(token_ce_kernel, dim3((rows + 3) / 4), dim3(128), 0, (cudaStream_t)stream, logits, match_q, tgt_count, posmap, num_boxes,
                                                                      row_loss, dlogits, rows, batch, n_queries,
                                                                      n_classes, t_max, eos_coef);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -378,7 +385,7 @@ int toist_box_loss(const float* boxes, const int32_t* match_q, const int32_t* tg
   TOIST_REQUIRE(boxes && match_q && tgt_count && tgt_boxes && num_boxes && pair_l1 && pair_giou,
                 "toist_box_loss: null pointer");
   TOIST_REQUIRE((dboxes_l1 == nullptr) == (dboxes_giou == nullptr), "toist_box_loss: pass both gradient buffers");
-  box_loss_kernel<<<n_layers * batch, 64, 0, (cudaStream_t)stream>>>(boxes, match_q, tgt_count, tgt_boxes, num_boxes,
+  launch_pdl(box_loss_kernel, dim3(n_layers * batch), dim3(64), 0, (cudaStream_t)stream, boxes, match_q, tgt_count, tgt_boxes, num_boxes,
                                                                      pair_l1, pair_giou, dboxes_l1, dboxes_giou, batch,
                                                                      n_queries, t_max);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -388,7 +395,7 @@ int toist_box_loss(const float* boxes, const int32_t* match_q, const int32_t* tg
 int toist_cardinality(const float* logits, int32_t* card, int32_t n_layers, int32_t batch, int32_t n_queries,
                       int32_t n_classes, void* stream) {
   TOIST_REQUIRE(logits && card, "toist_cardinality: null pointer");
-  cardinality_kernel<<<n_layers * batch, 128, 0, (cudaStream_t)stream>>>(logits, card, n_queries, n_classes);
+  launch_pdl(cardinality_kernel, dim3(n_layers * batch), dim3(128), 0, (cudaStream_t)stream, logits, card, n_queries, n_classes);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -407,7 +414,7 @@ int toist_contrastive_align(const float* proj_queries, const float* proj_tokens,
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(contrastive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  contrastive_kernel<<<n_layers * batch, 128, smem, (cudaStream_t)stream>>>(
+  launch_pdl(contrastive_kernel, dim3(n_layers * batch), dim3(128), smem, (cudaStream_t)stream, 
       proj_queries, proj_tokens, match_q, tgt_count, tok_pos, num_boxes, img_loss, dpq, dpt, batch, n_queries,
       n_tokens, dim, t_max, 1.f / temperature);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -420,7 +427,7 @@ int toist_criterion_reduce(const float* row_loss, const float* pair_l1, const fl
                            int32_t t_max, void* stream) {
   TOIST_REQUIRE(row_loss && pair_l1 && pair_giou && card && tgt_count && num_boxes && out,
                 "toist_criterion_reduce: null pointer");
-  criterion_reduce_kernel<<<n_layers, 256, 0, (cudaStream_t)stream>>>(row_loss, pair_l1, pair_giou, card, img_loss,
+  launch_pdl(criterion_reduce_kernel, dim3(n_layers), dim3(256), 0, (cudaStream_t)stream, row_loss, pair_l1, pair_giou, card, img_loss,
                                                                       tgt_count, num_boxes, flags, out, n_layers,
                                                                       batch, n_queries, t_max);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -431,7 +438,7 @@ int toist_scale_layers2(const float* x1, const float* g1, const float* x2, const
                         int64_t n, void* stream) {
   TOIST_REQUIRE(x1 && g1 && x2 && g2 && y, "toist_scale_layers2: null pointer");
   if (n == 0) return TOIST_OK;
-  scale_layers2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x1, g1, x2, g2, y, n_layers, n);
+  launch_pdl(scale_layers2_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x1, g1, x2, g2, y, n_layers, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -440,7 +447,7 @@ int toist_scale_layers(const float* x, const float* g, float* y, int32_t n_layer
                        void* stream) {
   TOIST_REQUIRE(x && g && y, "toist_scale_layers: null pointer");
   if (n == 0) return TOIST_OK;
-  scale_layers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, g, y, n_layers, n, reduce);
+  launch_pdl(scale_layers_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, g, y, n_layers, n, reduce);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

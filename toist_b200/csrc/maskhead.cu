@@ -14,6 +14,7 @@ namespace toist {
 // src_proj: bf16 sequence layout [HW, B, E]; attn: bf16 [B, NH, Q, ld] (softmax over pix per head); x0 NHWC bf16.
 __global__ void mask_input_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ attn,
                                   __nv_bfloat16* __restrict__ x0, int B, int Q, int HW, int E, int NH, int ld) {
+  pdl_prologue();
   const int C = E + NH;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * Q * HW * C;
@@ -30,6 +31,7 @@ __global__ void mask_input_kernel(const __nv_bfloat16* __restrict__ src, const _
 // backward: dsrc[pix, b, c] = sum_q dx0[(b*Q+q), pix, c];  dattn[b, h, q, pix] (fp32, ld_s) = dx0[(b*Q+q), pix, E + h]
 __global__ void mask_input_bwd_kernel(const __nv_bfloat16* __restrict__ dx0, __nv_bfloat16* __restrict__ dsrc,
                                       float* __restrict__ dattn, int B, int Q, int HW, int E, int NH, int ld) {
+  pdl_prologue();
   const int C = E + NH;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * HW * C;
@@ -58,6 +60,7 @@ constexpr int kGNMaxThreads = 256;
 
 __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ z, float* __restrict__ mean,
                                        float* __restrict__ rstd, int HW, int C, int G, float eps) {
+  pdl_prologue();
   // deterministic: per-thread partials -> fixed-order sum per channel -> fixed-order sum per group (no atomics)
   __shared__ float s_sum[kGNMaxC], s_sq[kGNMaxC];
   __shared__ float p_sum[kGNMaxThreads * 8], p_sq[kGNMaxThreads * 8];
@@ -114,6 +117,7 @@ __global__ void groupnorm_relu_fwd_kernel(const __nv_bfloat16* __restrict__ z, c
                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
                                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ a, long long total8,
                                           int HW, int C, int G) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int chunks = C / 8;
@@ -148,6 +152,7 @@ __global__ void groupnorm_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict
                                                  float* __restrict__ s1, float* __restrict__ s2,
                                                  float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C,
                                                  int G) {
+  pdl_prologue();
   __shared__ float c_dyx[kGNMaxC], c_dy[kGNMaxC];
   __shared__ float p_dyx[kGNMaxThreads * 8], p_dy[kGNMaxThreads * 8];
   const int n = blockIdx.x;
@@ -224,6 +229,7 @@ __global__ void groupnorm_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict_
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 const float* __restrict__ s1, const float* __restrict__ s2,
                                                 __nv_bfloat16* __restrict__ dz, long long total8, int HW, int C, int G) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int chunks = C / 8, cpg = C / G;
@@ -257,6 +263,7 @@ __global__ void groupnorm_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict_
 __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ xs, const __nv_bfloat16* __restrict__ fpn,
                                     __nv_bfloat16* __restrict__ out, long long total8, int Q, int H, int W, int h, int w,
                                     int C) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int chunks = C / 8;
@@ -285,6 +292,7 @@ __global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ xs, const 
 // dxs[n, sy, sx, c] = sum of dout over the destination pixels that read (sy, sx)
 __global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dxs,
                                     long long total8, int H, int W, int h, int w, int C) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const int chunks = C / 8;
@@ -326,6 +334,7 @@ __global__ void upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv
 // dfpn[b, pix, c] = sum_q dout[b*Q + q, pix, c]   (the adapter output is shared by the Q queries of an image)
 __global__ void sum_queries_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dfpn,
                                    long long per_image8, int Q) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long b = blockIdx.y;
   if (i >= per_image8) return;
@@ -364,6 +373,7 @@ __device__ __forceinline__ void bilinear_src(int d, int in, int out, int& i0, in
 __global__ void mask_loss_fwd_kernel(const float* __restrict__ pred, const uint8_t* __restrict__ tgt,
                                      const int* __restrict__ match_q, const int* __restrict__ tgt_count,
                                      float* __restrict__ sums, int Q, int Tmax, int hm, int wm, int HT, int WT) {
+  pdl_prologue();
   const int pair = blockIdx.y;
   const int b = pair / Tmax, t = pair % Tmax;
   if (t >= min(tgt_count[b], Tmax)) return;
@@ -408,6 +418,7 @@ __global__ void mask_loss_bwd_kernel(const float* __restrict__ pred, const uint8
                                      const float* __restrict__ sums, const float* __restrict__ num_boxes,
                                      const float* __restrict__ gout /* [2]: d/d loss_mask, d/d loss_dice */,
                                      float* __restrict__ dpred, int Q, int Tmax, int hm, int wm, int HT, int WT) {
+  pdl_prologue();
   const int pair = blockIdx.y;
   const int b = pair / Tmax, t = pair % Tmax;
   if (t >= min(tgt_count[b], Tmax)) return;
@@ -451,6 +462,7 @@ __global__ void mask_loss_bwd_kernel(const float* __restrict__ pred, const uint8
 __global__ void mask_loss_reduce_kernel(const float* __restrict__ sums, const int* __restrict__ match_q,
                                         const int* __restrict__ tgt_count, const float* __restrict__ num_boxes,
                                         float* __restrict__ out, int B, int Tmax, float inv_pix) {
+  pdl_prologue();
   float lm = 0.f, ld = 0.f;
   for (int pair = threadIdx.x; pair < B * Tmax; pair += blockDim.x) {
     const int b = pair / Tmax, t = pair % Tmax;
@@ -497,7 +509,7 @@ int toist_mask_input(const void* src_proj, const void* attn, void* x0, int32_t b
   TOIST_REQUIRE(src_proj && attn && x0, "toist_mask_input: null pointer");
   const long long total = (long long)batch * n_queries * hw * (dim + n_heads);
   if (total == 0) return TOIST_OK;
-  mask_input_kernel<<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(mask_input_kernel, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)src_proj, (const __nv_bfloat16*)attn, (__nv_bfloat16*)x0, batch, n_queries, hw, dim, n_heads,
       ld_attn);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -509,7 +521,7 @@ int toist_mask_input_bwd(const void* dx0, void* dsrc_proj, float* dattn, int32_t
   TOIST_REQUIRE(dx0 && dattn, "toist_mask_input_bwd: null pointer");
   const long long total = (long long)batch * hw * (dim + n_heads);
   if (total == 0) return TOIST_OK;
-  mask_input_bwd_kernel<<<nblk(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(mask_input_bwd_kernel, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)dx0, (__nv_bfloat16*)dsrc_proj, dattn, batch, n_queries, hw, dim, n_heads, ld_attn);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -522,10 +534,10 @@ int toist_groupnorm_relu_fwd(const void* z, const float* gamma, const float* bet
                 "toist_groupnorm_relu_fwd: %d channels / %d groups unsupported", channels, groups);
   if (n_maps == 0) return TOIST_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  groupnorm_stats_kernel<<<n_maps, gn_threads(channels), 0, st>>>((const __nv_bfloat16*)z, mean, rstd, hw, channels,
+  launch_pdl(groupnorm_stats_kernel, dim3(n_maps), dim3(gn_threads(channels)), 0, st, (const __nv_bfloat16*)z, mean, rstd, hw, channels,
                                                                   groups, eps);
   const long long total8 = (long long)n_maps * hw * (channels / 8);
-  groupnorm_relu_fwd_kernel<<<nblk(total8, 256), 256, 0, st>>>((const __nv_bfloat16*)z, mean, rstd, gamma, beta,
+  launch_pdl(groupnorm_relu_fwd_kernel, dim3(nblk(total8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)z, mean, rstd, gamma, beta,
                                                                (__nv_bfloat16*)a, total8, hw, channels, groups);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -541,11 +553,11 @@ int toist_groupnorm_relu_bwd(const void* da, const void* z, const float* mean, c
   cudaStream_t st = (cudaStream_t)stream;
   float* s1 = scratch;
   float* s2 = scratch + (size_t)n_maps * groups;
-  groupnorm_relu_bwd_reduce_kernel<<<n_maps, gn_threads(channels), 0, st>>>(
+  launch_pdl(groupnorm_relu_bwd_reduce_kernel, dim3(n_maps), dim3(gn_threads(channels)), 0, st, 
       (const __nv_bfloat16*)da, (const __nv_bfloat16*)z, mean, rstd, gamma, beta, s1, s2, dgamma, dbeta, hw, channels,
       groups);
   const long long total8 = (long long)n_maps * hw * (channels / 8);
-  groupnorm_relu_bwd_apply_kernel<<<nblk(total8, 256), 256, 0, st>>>(
+  launch_pdl(groupnorm_relu_bwd_apply_kernel, dim3(nblk(total8, 256)), dim3(256), 0, st, 
       (const __nv_bfloat16*)da, (const __nv_bfloat16*)z, mean, rstd, gamma, beta, s1, s2, (__nv_bfloat16*)dz, total8, hw,
       channels, groups);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -557,7 +569,7 @@ int toist_upsample_add(const void* xs, const void* fpn, void* out, int32_t n_map
   TOIST_REQUIRE(xs && fpn && out && channels % 8 == 0 && n_queries >= 1, "toist_upsample_add: bad arguments");
   const long long total8 = (long long)n_maps * out_h * out_w * (channels / 8);
   if (total8 == 0) return TOIST_OK;
-  upsample_add_kernel<<<nblk(total8, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(upsample_add_kernel, dim3(nblk(total8, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)xs, (const __nv_bfloat16*)fpn, (__nv_bfloat16*)out, total8, n_queries, out_h, out_w, in_h,
       in_w, channels);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -570,12 +582,12 @@ int toist_upsample_add_bwd(const void* dout, void* dxs, void* dfpn, int32_t n_ma
   cudaStream_t st = (cudaStream_t)stream;
   const long long t8 = (long long)n_maps * in_h * in_w * (channels / 8);
   if (t8 == 0) return TOIST_OK;
-  upsample_bwd_kernel<<<nblk(t8, 256), 256, 0, st>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dxs, t8, out_h, out_w,
+  launch_pdl(upsample_bwd_kernel, dim3(nblk(t8, 256)), dim3(256), 0, st, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dxs, t8, out_h, out_w,
                                                      in_h, in_w, channels);
   if (dfpn != nullptr) {
     const long long per8 = (long long)out_h * out_w * (channels / 8);
     dim3 grid(nblk(per8, 256), n_maps / n_queries);
-    sum_queries_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dfpn, per8, n_queries);
+    launch_pdl(sum_queries_kernel, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dfpn, per8, n_queries);
   }
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -593,9 +605,9 @@ int toist_mask_loss_fwd(const float* pred_masks, const uint8_t* tgt_masks, const
   int chunks = (int)((pix + 256 * 8 - 1) / (256 * 8));
   if (chunks > 64) chunks = 64;
   dim3 grid(chunks, batch * t_max);
-  mask_loss_fwd_kernel<<<grid, 256, 0, st>>>(pred_masks, tgt_masks, match_q, tgt_count, sums, n_queries, t_max, mask_h,
+  launch_pdl(mask_loss_fwd_kernel, dim3(grid), dim3(256), 0, st, pred_masks, tgt_masks, match_q, tgt_count, sums, n_queries, t_max, mask_h,
                                              mask_w, tgt_h, tgt_w);
-  mask_loss_reduce_kernel<<<1, 256, 0, st>>>(sums, match_q, tgt_count, num_boxes, out, batch, t_max,
+  launch_pdl(mask_loss_reduce_kernel, dim3(1), dim3(256), 0, st, sums, match_q, tgt_count, num_boxes, out, batch, t_max,
                                              1.f / ((float)tgt_h * (float)tgt_w));
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -613,7 +625,7 @@ int toist_mask_loss_bwd(const float* pred_masks, const uint8_t* tgt_masks, const
   int chunks = (int)((pix + 256 * 8 - 1) / (256 * 8));
   if (chunks > 64) chunks = 64;
   dim3 grid(chunks, batch * t_max);
-  mask_loss_bwd_kernel<<<grid, 256, 0, st>>>(pred_masks, tgt_masks, match_q, tgt_count, sums, num_boxes, gout, dpred,
+  launch_pdl(mask_loss_bwd_kernel, dim3(grid), dim3(256), 0, st, pred_masks, tgt_masks, match_q, tgt_count, sums, num_boxes, gout, dpred,
                                              n_queries, t_max, mask_h, mask_w, tgt_h, tgt_w);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;

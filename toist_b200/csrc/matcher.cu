@@ -19,6 +19,7 @@ __global__ void match_cost_kernel(const float* __restrict__ logits, const float*
                                   const float* __restrict__ tgt_boxes, const int* __restrict__ tgt_count,
                                   const float* __restrict__ posmap, float* __restrict__ cost, int B, int Q, int C,
                                   int Tmax, float w_class, float w_bbox, float w_giou) {
+  pdl_prologue();
   const int lb = blockIdx.x;
   const int b = lb % B;
   const int T = min(tgt_count[b], Tmax);
@@ -67,6 +68,7 @@ __global__ void match_cost_kernel(const float* __restrict__ logits, const float*
 // cost: [P][Q][Tmax] fp32.  match_q[p][t] = query assigned to target t (or -1), flags[0] |= 1 on NaN / infeasible.
 __global__ void lsap_kernel(const float* __restrict__ cost, const int* __restrict__ tgt_count, int* __restrict__ match_q,
                             int* __restrict__ flags, int B, int Q, int Tmax) {
+  pdl_prologue();
   const int p = blockIdx.x;
   const int b = p % B;
   const int T = min(tgt_count[b], Tmax);
@@ -126,7 +128,7 @@ int toist_match_cost(const float* logits, const float* boxes, const float* tgt_b
   TOIST_REQUIRE(n_layers > 0 && batch > 0 && n_queries > 0 && n_classes > 0 && t_max > 0, "toist_match_cost: bad sizes");
   const int threads = 128;
   const size_t smem = (size_t)(threads / 32) * n_classes * sizeof(float);
-  match_cost_kernel<<<n_layers * batch, threads, smem, (cudaStream_t)stream>>>(
+  launch_pdl(match_cost_kernel, dim3(n_layers * batch), dim3(threads), smem, (cudaStream_t)stream, 
       logits, boxes, tgt_boxes, tgt_count, posmap, cost, batch, n_queries, n_classes, t_max, w_class, w_bbox, w_giou);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -144,7 +146,7 @@ int toist_lsap_device(const float* cost, const int32_t* tgt_count, int32_t* matc
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  lsap_kernel<<<n_problems, 64, smem, (cudaStream_t)stream>>>(cost, tgt_count, match_q, flags, batch, n_queries, t_max);
+  launch_pdl(lsap_kernel, dim3(n_problems), dim3(64), smem, (cudaStream_t)stream, cost, tgt_count, match_q, flags, batch, n_queries, t_max);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

@@ -29,6 +29,7 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __r
                                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y16,
                                      float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd,
                                      long long rows, int N, float eps) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -71,6 +72,7 @@ __global__ void layernorm_bwd_kernel(const TDy* __restrict__ dy, const TDy* __re
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, TDx* __restrict__ dx, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, long long rows, int N) {
+  pdl_prologue();
   extern __shared__ float acc[];  // [2][N]
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
@@ -118,6 +120,7 @@ __global__ void layernorm_bwd_kernel(const TDy* __restrict__ dy, const TDy* __re
 // y = x / max(||x||, eps) per row (fp32); bwd: dx = (dy - y * (y . dy)) / max(||x||, eps)
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ nrm,
                                   long long rows, int N, float eps) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -129,6 +132,7 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
 }
 __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                   const float* __restrict__ nrm, float* __restrict__ dx, long long rows, int N) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -148,6 +152,7 @@ __global__ void attn_softmax_fwd_kernel(const float* __restrict__ s, const uint8
                                         int Sk, int ld_s, int ld_p, int rows_per_batch,
                                         const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thr,
                                         float keep_scale) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -185,6 +190,7 @@ __global__ void attn_softmax_bwd_kernel(const float* __restrict__ dp, const __nv
                                         __nv_bfloat16* __restrict__ ds, long long rows, int Sk, int ld_s, int ld_p,
                                         float scale, const unsigned long long* __restrict__ seed, uint32_t site,
                                         uint32_t thr, float keep_scale) {
+  pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -215,6 +221,7 @@ __global__ void attn_softmax_bwd_kernel(const float* __restrict__ dp, const __nv
 __global__ void pos_sine_kernel(const uint8_t* __restrict__ mask, float* __restrict__ pos32,
                                 __nv_bfloat16* __restrict__ pos16, int B, int H, int W, int F, float temperature,
                                 long long ld_rows /* B*2F */) {
+  pdl_prologue();
   extern __shared__ float emb[];  // y_embed[H*W], x_embed[H*W]
   float* ye = emb;
   float* xe = emb + H * W;
@@ -259,6 +266,7 @@ __global__ void embed_gather_kernel(const long long* __restrict__ ids, const flo
                                     const float* __restrict__ posw, const float* __restrict__ type0,
                                     float* __restrict__ out, int* __restrict__ pos_ids, int B, int L, int E, int pad_id,
                                     int seq_first) {
+  pdl_prologue();
   const int b = blockIdx.x / L, l = blockIdx.x % L;
   const long long id = ids[blockIdx.x];
   const int row = seq_first ? l * B + b : blockIdx.x;  // output row (ids are always [B, L])
@@ -275,6 +283,7 @@ __global__ void embed_scatter_kernel(const T* __restrict__ dx, const long long* 
                                      const int* __restrict__ pos_ids, float* __restrict__ dword,
                                      float* __restrict__ dpos, float* __restrict__ dtype0, int B, int L, int E,
                                      int seq_first) {
+  pdl_prologue();
   const int b = blockIdx.x / L, l = blockIdx.x % L;
   const int row = seq_first ? l * B + b : blockIdx.x;
   const long long id = ids[blockIdx.x];
@@ -300,10 +309,10 @@ int toist_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, cons
   if (rows == 0) return TOIST_OK;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (x_dtype == TOIST_F32)
-    layernorm_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta,
+    launch_pdl((layernorm_fwd_kernel<float>), dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)x, gamma, beta,
                                                                         (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, n, eps);
   else
-    layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl((layernorm_fwd_kernel<__nv_bfloat16>), dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y_bf16, y_f32, mean, rstd, rows, n, eps);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -322,7 +331,7 @@ int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const
   const size_t smem = 2 * (size_t)n * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define LN_BWD(TX, TDY, TDX)                                                                                      \
-  layernorm_bwd_kernel<TX, TDY, TDX><<<grid, 256, smem, st>>>((const TDY*)dy, (const TDY*)dy2, (const TX*)x, mean, \
+  launch_pdl((layernorm_bwd_kernel<TX, TDY, TDX>), dim3(grid), dim3(256), smem, st, (const TDY*)dy, (const TDY*)dy2, (const TX*)x, mean, \
                                                               rstd, gamma, (TDX*)dx, dgamma, dbeta, rows, n)
   const int key = (x_dtype << 2) | (dy_dtype << 1) | dx_dtype;
   switch (key) {
@@ -343,7 +352,7 @@ int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const
 int toist_l2norm_fwd(const float* x, float* y, float* nrm, int64_t rows, int32_t n, float eps, void* stream) {
   TOIST_REQUIRE(x && y && nrm, "toist_l2norm_fwd: null pointer");
   if (rows == 0) return TOIST_OK;
-  l2norm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, y, nrm, rows, n, eps);
+  launch_pdl(l2norm_fwd_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, x, y, nrm, rows, n, eps);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -352,7 +361,7 @@ int toist_l2norm_bwd(const float* dy, const float* y, const float* nrm, float* d
                      void* stream) {
   TOIST_REQUIRE(dy && y && nrm && dx, "toist_l2norm_bwd: null pointer");
   if (rows == 0) return TOIST_OK;
-  l2norm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dy, y, nrm, dx, rows, n);
+  launch_pdl(l2norm_bwd_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, dy, y, nrm, dx, rows, n);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -365,7 +374,7 @@ int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* p
                 "toist_attn_softmax_fwd: dropout needs a seed and 0 < p < 1");
   if (rows == 0) return TOIST_OK;
   const uint32_t thr = (uint32_t)((double)p_drop * 4294967296.0);
-  attn_softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(attn_softmax_fwd_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 
       scores, key_mask, (__nv_bfloat16*)probs, (__nv_bfloat16*)probs_dropped, rows, sk, ld_s, ld_p, rows_per_batch,
       (const unsigned long long*)seed, site, thr, 1.f / (1.f - p_drop));
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -379,7 +388,7 @@ int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores
   if (rows == 0) return TOIST_OK;
   const bool drop = seed != nullptr && p_drop > 0.f;
   const uint32_t thr = (uint32_t)((double)p_drop * 4294967296.0);
-  attn_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(attn_softmax_bwd_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 
       dprobs, (const __nv_bfloat16*)probs, (__nv_bfloat16*)dscores, rows, sk, ld_s, ld_p, scale,
       drop ? (const unsigned long long*)seed : nullptr, site, thr, 1.f / (1.f - p_drop));
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -397,7 +406,7 @@ int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t 
     configured = true;
   }
   const int slices = (h * w * 2 * num_pos_feats + 4095) / 4096 < 32 ? (h * w * 2 * num_pos_feats + 4095) / 4096 : 32;
-  pos_sine_kernel<<<dim3(batch, slices > 0 ? slices : 1), 256, smem, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, batch, h, w,
+  launch_pdl(pos_sine_kernel, dim3(dim3(batch, slices > 0 ? slices : 1)), dim3(256), smem, (cudaStream_t)stream, mask, pos_f32, (__nv_bfloat16*)pos_bf16, batch, h, w,
                                                               num_pos_feats, temperature,
                                                               (long long)batch * 2 * num_pos_feats);
   TOIST_CHECK_CUDA(cudaGetLastError());
@@ -409,7 +418,7 @@ int toist_embed_gather(const int64_t* ids, const float* word, const float* pos, 
                        void* stream) {
   TOIST_REQUIRE(ids && word && pos && type0 && out, "toist_embed_gather: null pointer");
   if (batch * len == 0) return TOIST_OK;
-  embed_gather_kernel<<<batch * len, 256, 0, (cudaStream_t)stream>>>((const long long*)ids, word, pos, type0, out,
+  launch_pdl(embed_gather_kernel, dim3(batch * len), dim3(256), 0, (cudaStream_t)stream, (const long long*)ids, word, pos, type0, out,
                                                                      pos_ids, batch, len, dim, pad_id, seq_first);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -422,9 +431,9 @@ int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, co
   const int rows = batch * len;
   if (rows == 0) return TOIST_OK;
   if (dx_dtype == TOIST_BF16)
-    embed_scatter_kernel<__nv_bfloat16><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
+    launch_pdl((embed_scatter_kernel<__nv_bfloat16>), dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
   else
-    embed_scatter_kernel<float><<<rows, 256, 0, (cudaStream_t)stream>>>((const float*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
+    launch_pdl((embed_scatter_kernel<float>), dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const float*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
