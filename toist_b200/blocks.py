@@ -102,14 +102,15 @@ def drop_grad(ds, drop_site):
 def lin_param_grads(g: G, req: Set[str], wname: str, bname: Optional[str], dy: torch.Tensor, x: torch.Tensor,
                     w_shape) -> None:
     """dW = dy^T x, db = column sums of dy (nn.Linear backward)."""
-    if wname in req:
-        dw = _zeros(tuple(w_shape), dy.device)
-        K.linear_wgrad(dy, x, dw)
-        g[wname] = dw
-    if bname is not None and bname in req:
-        db = _zeros((dy.shape[1],), dy.device)
-        K.colsum(dy, db)
-        g[bname] = db
+    with K.wgrad_lane(dy, x):
+        if wname in req:
+            dw = _zeros(tuple(w_shape), dy.device)
+            K.linear_wgrad(dy, x, dw)
+            g[wname] = dw
+        if bname is not None and bname in req:
+            db = _zeros((dy.shape[1],), dy.device)
+            K.colsum(dy, db)
+            g[bname] = db
 
 
 def ln_fwd(w: W, pre: str, x: torch.Tensor, eps: float, **kw):
@@ -164,24 +165,25 @@ def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int
     K.attention_bwd(dctx.view(Sq, B, E), q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), probs, nhead,
                     dq2.view(Sq, B, E), dk2.view(Sk, B, E), dv2.view(Sk, B, E), drop=drop_site)
     wn, bn = pre + "in_proj_weight", pre + "in_proj_bias"
-    if wn in req:
-        dw = _zeros((3 * E, E), dev)
-        if fused:
-            K.linear_wgrad(dqk, xq, dw[: 2 * E])
-        else:
-            K.linear_wgrad(dq2, xq, dw[:E])
-            K.linear_wgrad(dk2, xk, dw[E: 2 * E])
-        K.linear_wgrad(dv2, xv, dw[2 * E:])
-        g[wn] = dw
-    if bn in req:
-        db = _zeros((3 * E,), dev)
-        if fused:
-            K.colsum(dqk, db[: 2 * E])
-        else:
-            K.colsum(dq2, db[:E])
-            K.colsum(dk2, db[E: 2 * E])
-        K.colsum(dv2, db[2 * E:])
-        g[bn] = db
+    with K.wgrad_lane(dq2, dk2, dv2, xq, xk, xv, dqk if fused else None):
+        if wn in req:
+            dw = _zeros((3 * E, E), dev)
+            if fused:
+                K.linear_wgrad(dqk, xq, dw[: 2 * E])
+            else:
+                K.linear_wgrad(dq2, xq, dw[:E])
+                K.linear_wgrad(dk2, xk, dw[E: 2 * E])
+            K.linear_wgrad(dv2, xv, dw[2 * E:])
+            g[wn] = dw
+        if bn in req:
+            db = _zeros((3 * E,), dev)
+            if fused:
+                K.colsum(dqk, db[: 2 * E])
+            else:
+                K.colsum(dq2, db[:E])
+                K.colsum(dk2, db[E: 2 * E])
+            K.colsum(dv2, db[2 * E:])
+            g[bn] = db
     dxq = dxk = dxv = None
     if fused:
         if need[0] or need[1]:
@@ -350,10 +352,11 @@ def bottleneck_fwd(w: W, x, stride: int, has_ds: bool):
 
 def _conv_wgrad_param(g: G, name: str, dy, x, w_shadow, scale, stride: int, pad: int) -> None:
     cout, kh, kw, cin = w_shadow.shape
-    dw = _zeros((cout, kh, kw, cin), dy.device)
-    K.conv_wgrad(dy, x, dw, stride=stride, pad=pad, row_scale=scale)
-    if kh * kw > 1:
-        dw = K.permute_021(dw.view(cout, kh * kw, cin))
+    with K.wgrad_lane(dy, x):
+        dw = _zeros((cout, kh, kw, cin), dy.device)
+        K.conv_wgrad(dy, x, dw, stride=stride, pad=pad, row_scale=scale)
+        if kh * kw > 1:
+            dw = K.permute_021(dw.view(cout, kh * kw, cin))
     g[name] = dw.view(cout, cin, kh, kw)
 
 

@@ -9,6 +9,7 @@ torch is used only to own device memory.  Layout conventions:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from functools import lru_cache
 from typing import Optional, Sequence, Tuple
 
@@ -63,6 +64,70 @@ def launches() -> int:
 def _count(n: int = 1) -> None:
     global _launch_count
     _launch_count += n
+
+
+class _WgradLane:
+    """Second stream for parameter-gradient kernels.  Inside a backward stage (StageFn.backward) the weight-gradient
+    GEMMs, bias column sums and their layout permutes do not feed the data-gradient chain, so they are issued on a side
+    stream: the GPU then always has a second kernel's CTAs to fill the SMs the (short, 100..300-CTA) data-gradient
+    kernels leave idle, and their launch / prologue / epilogue latencies overlap.  Works in eager mode and inside
+    CUDA-graph capture (fork = event wait, join = `join()` before the stage returns).  TOIST_WGRAD_LANE=0 disables."""
+
+    enabled = os.environ.get("TOIST_WGRAD_LANE", "1") != "0"
+    active = False   # only StageFn.backward turns the lane on; direct block calls stay single-stream
+    stream = None
+    dirty = False
+    keep: list = []
+
+
+class wgrad_lanes:
+    """`with wgrad_lanes():` around a backward stage body; joins the side stream on exit."""
+
+    def __enter__(self):
+        self.prev, _WgradLane.active = _WgradLane.active, _WgradLane.enabled
+        return self
+
+    def __exit__(self, *exc):
+        _WgradLane.active = self.prev
+        wgrad_join()
+        return False
+
+
+class wgrad_lane:
+    """`with wgrad_lane(dy, x):` issues the enclosed launches on the side stream (after everything already queued on
+    the current stream) and keeps the named tensors alive until the join."""
+
+    def __init__(self, *tensors):
+        self.tensors = tensors
+        self.ctx = None
+
+    def __enter__(self):
+        L = _WgradLane
+        if not L.active:
+            return self
+        main = torch.cuda.current_stream()
+        if L.stream is None or L.stream.device != main.device:
+            L.stream = torch.cuda.Stream(device=main.device)
+        L.stream.wait_stream(main)
+        L.keep.extend(t for t in self.tensors if t is not None)
+        L.dirty = True
+        self.ctx = torch.cuda.stream(L.stream)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+        return False
+
+
+def wgrad_join() -> None:
+    L = _WgradLane
+    if L.dirty:
+        torch.cuda.current_stream().wait_stream(L.stream)
+        L.keep.clear()
+        L.dirty = False
 
 
 def _stream() -> int:

@@ -344,7 +344,7 @@ class StageFn(torch.autograd.Function):
         numel = sum((_numel(shp) + 63) // 64 * 64 for n, shp in zip(c.stage.names, c.stage.shapes) if n in c.req)
 
         def body(*g):
-            with Bk.zero_arena(numel, dev):
+            with Bk.zero_arena(numel, dev), K.wgrad_lanes():
                 return spec.bwd(c, saved, needs, *g)
 
         if c.graphs is None:

@@ -49,6 +49,10 @@ def cases():
     out.append(("conv3x3_256_256_wgrad", 2.0 * px * 256 * 2304, lambda: K.conv_wgrad(x256, x256, dw33, pad=1)))
     dw11 = torch.zeros(1024, 1, 1, 256, device="cuda")
     out.append(("conv1x1_256_1024_wgrad", 2.0 * px * 256 * 1024, lambda: K.conv_wgrad(x1024, x256, dw11)))
+    # ---- large square GEMMs: the engine's main loop without wave-quantisation / launch effects
+    for n in (4096, 8192):
+        xa, wb = rn(n, n), rn(n, n)
+        out.append((f"gemm_{n}_cubed", 2.0 * n * n * n, (lambda xa=xa, wb=wb: K.linear_fwd(xa, wb))))
     # ---- layer1 / layer2 (large pixel counts, small K)
     x64 = rn(B, 160, 160, 64)
     w64 = rn(64, 3, 3, 64)
@@ -76,6 +80,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--graph", action="store_true", help="capture the inner launches into a CUDA graph")
+    ap.add_argument("--inner", type=int, default=1, help="back-to-back launches per timed region (amortises the "
+                                                        "host launch gap; L2 is then warm for all but the first)")
     a = ap.parse_args()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {
         "bf16_tflops": 1590.0}
@@ -86,15 +93,31 @@ def main():
         for _ in range(3 if a.reps > 1 else 1):
             fn()
         torch.cuda.synchronize()
+        graph = None
+        if a.graph:  # replay `inner` launches as one CUDA graph: no host launch gaps inside the timed region
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    for _ in range(a.inner):
+                        fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
         ts = []
         for _ in range(a.reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            if graph is not None:
+                graph.replay()
+            else:
+                for _ in range(a.inner):
+                    fn()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e-3)
+            ts.append(e0.elapsed_time(e1) * 1e-3 / a.inner)
         ts.sort()
         t = ts[len(ts) // 2]
         print(json.dumps({"kernel": name, "us": t * 1e6, "tflops": flops / t / 1e12,
