@@ -317,7 +317,7 @@ def test_mask_stage_against_fp32_torch():
         assert rel_err(d_mem, mem_r.grad) < atol
         assert rel_err(d_src.float(), src_r.grad) < atol  # sum over the Q queries of bf16-stored, sign-mixed dx0 rows
         for got, want, nm in ((d_c4, f_r[0], "c4"), (d_c3, f_r[1], "c3"), (d_c2, f_r[2], "c2")):
-            assert rel_err(got.float().permute(0, 3, 1, 2), want.grad) < tol, nm
+            assert rel_err(got.float().permute(0, 3, 1, 2), want.grad) < atol, nm  # sums over the Q queries (see d_src)
         bad = []
         for k, p_ in ref.items():
             if k == "bbox_attention.k_linear.bias":

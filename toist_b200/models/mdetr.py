@@ -7,6 +7,8 @@ the reference's names so state dicts are interchangeable.  Everything numerical 
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional
 
 import torch
@@ -35,9 +37,12 @@ class ModelRuntime:
     """Lazily built per-model state: bf16 shadow weights and the static description of each autograd stage."""
 
     def __init__(self):
+        self.text_stream = None
+        self.text_stream_enabled = os.environ.get("TOIST_TEXT_STREAM", "1") != "0"
         self.bank = ShadowBank()
         self.stages: Optional[Dict[str, Stage]] = None
         self.graphs: Optional[GraphCache] = None
+        self.graphs_text: Optional[GraphCache] = None
         self.seed: Optional[torch.Tensor] = None  # device int64 [1]: dropout seed of the current step
         self.dirty = True  # parameters may have moved / been reloaded since the shadow bank was built
 
@@ -81,9 +86,13 @@ class ModelRuntime:
         self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body, dirty)
         if self.graphs is not None and sig is not None and sig != self.bank._sig:
             self.graphs.clear()  # shadow buffers moved: captured pointers are stale
+            self.graphs_text.clear()
 
     def call(self, name: str, save: bool, drop_p: float = 0.0, **kw) -> Call:
-        return Call(self.stages[name], self.bank.w, save, graphs=self.graphs, drop_p=drop_p,
+        # the text stage replays concurrently with the backbone: graphs that may overlap in time must not share a
+        # memory pool (a pool is only safe for graphs replayed one after the other)
+        graphs = self.graphs_text if (name == "text" and self.text_stream_enabled) else self.graphs
+        return Call(self.stages[name], self.bank.w, save, graphs=graphs, drop_p=drop_p,
                     seed=self.seed, **kw)
 
     def new_step_seed(self, device) -> None:
@@ -143,6 +152,7 @@ class MDETR(nn.Module):
         and replay them on later steps.  For fixed-shape training / benchmarking; tensors returned by a step are
         overwritten by the next step with the same shapes."""
         self._rt.graphs = GraphCache() if on else None
+        self._rt.graphs_text = GraphCache() if on else None
         return self
 
     def _grad_wanted(self) -> bool:
@@ -162,23 +172,41 @@ class MDETR(nn.Module):
             rt.new_step_seed(images.device)
         else:
             rt.seed = None
-        feats = run_stage(BACKBONE, rt.call("backbone", save), images)
-        c5 = feats[-1]
-        B, h, w, _ = c5.shape
-        E = self.transformer.d_model
         dev = images.device
-
+        E = self.transformer.d_model
+        text_stream = None
         if isinstance(captions[0], str):
             tokenized = self.transformer.tokenizer.batch_encode_plus(captions, padding="longest",
                                                                      return_tensors="pt").to(dev)
             ids = tokenized["input_ids"].contiguous()
             attn = tokenized["attention_mask"].to(torch.int64).contiguous()
             text_attention_mask = attn.ne(1)
-            text_resized = run_stage(TEXT, rt.call("text", save, dp["text"] if dp else 0.0), ids,
-                                     text_attention_mask.view(torch.uint8))[0]
+            # The text branch (12 RoBERTa layers on B x L <= a few hundred rows: ~150 tiny, latency-bound launches) does
+            # not depend on the image: it runs on its own stream next to the backbone's large kernels, forward and
+            # (autograd replays a node's backward on its forward stream) backward.  TOIST_TEXT_STREAM=0 disables.
+            main = torch.cuda.current_stream()
+            if rt.text_stream_enabled:
+                if rt.text_stream is None or rt.text_stream.device != dev:
+                    rt.text_stream = torch.cuda.Stream(device=dev)
+                text_stream = rt.text_stream
+                text_stream.wait_stream(main)
+                with torch.cuda.stream(text_stream):
+                    text_resized = run_stage(TEXT, rt.call("text", save, dp["text"] if dp else 0.0), ids,
+                                             text_attention_mask.view(torch.uint8))[0]
+            else:
+                text_resized = run_stage(TEXT, rt.call("text", save, dp["text"] if dp else 0.0), ids,
+                                         text_attention_mask.view(torch.uint8))[0]
         else:  # already encoded (models/transformer.py:139-141)
             text_attention_mask, text_resized, tokenized = captions
             attn = (~text_attention_mask).to(torch.int64).contiguous()
+        feats = run_stage(BACKBONE, rt.call("backbone", save), images)
+        c5 = feats[-1]
+        B, h, w, _ = c5.shape
+        if text_stream is not None:
+            torch.cuda.current_stream().wait_stream(text_stream)
+            text_resized.record_stream(torch.cuda.current_stream())
+            for t in (ids, text_attention_mask):
+                t.record_stream(text_stream)
         L = text_resized.shape[0]
 
         pad_u8 = samples.mask.contiguous().view(torch.uint8)
