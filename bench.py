@@ -307,6 +307,16 @@ def run_ours(a):
         K.set_gemm_profiler(None)
         iso = prof.isolated_times()
         agg = prof.summary(iso)
+        if a.dump_shapes:  # per distinct launch shape: count, algorithmic FLOPs, isolated duration (tools/shape_table.py)
+            cnt = {}
+            for tag, f, sg, _ in prof.rec:
+                if sg is not None:
+                    c = cnt.setdefault(sg, [tag, 0, f])
+                    c[1] += 1
+            with open(a.dump_shapes, "w") as fh:
+                for sg, (tag, n, f) in cnt.items():
+                    fh.write(json.dumps({"tag": tag, "sig": [str(x) for x in sg], "count": n, "flops": f,
+                                         "us": iso[sg] * 1e6}) + "\n")
         fl = sum(v[0] for v in agg.values())
         tm = sum(v[1] for tag, v in agg.items())
         nl = sum(v[2] for v in agg.values())
@@ -363,6 +373,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="transformer dropout (reference default 0.1, main.py:137)")
+    ap.add_argument("--dump-shapes", default="", help="write one JSON line per distinct tensor-core launch shape")
     ap.add_argument("--no-graphs", action="store_true", help="issue every kernel launch from Python (no CUDA graphs)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)

@@ -231,6 +231,53 @@ int toist_attn_softmax_fwd(const float* scores, const uint8_t* key_mask, void* p
 int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores, int64_t rows, int32_t sk,
                            int32_t ld_s, int32_t ld_p, float scale, float p_drop, const uint64_t* seed, uint32_t site,
                            void* stream);
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused attention core (csrc/attention.cu): O = dropout(softmax(Q K^T / sqrt(d) + key mask)) V in one launch with the
+ * scores in TMEM, and its backward (dQ, dK, dV) in one launch + a deterministic reduction.  Replaces the
+ * bmm / softmax / dropout / bmm sequence inside nn.MultiheadAttention (reference models/transformer.py:273,337-338
+ * -> F.multi_head_attention_forward) and inside RobertaSelfAttention (transformer.py:130).
+ *
+ * q, k, v, out, dout, dq, dk, dv are bf16 with element (s, b, head * d + i) at ptr[s * ss + b * sb + head * d + i]
+ * (ss, sb in elements, multiples of 8; bases 16-byte aligned): the reference's [S, B, E] layout, or column slices of
+ * a packed projection.  key_mask: uint8 [b, sk], non-zero = key ignored (key_padding_mask), may be null.
+ * lse: f32 [b, h, sq] row log-sum-exp, written by the forward when non-null and required by the backward.
+ * Dropout (p_drop > 0): decisions are a hash of (seed[0], site, row, key pair) regenerated in the backward;
+ * p is quantised to round(p * 65536) / 65536.  Supported: d in {32, 64}, sk <= 448 (toist_attention_supported). */
+typedef struct toist_attn_desc {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  float* lse;
+  const uint8_t* key_mask;
+  const uint64_t* seed;
+  int64_t q_ss, q_sb, k_ss, k_sb, v_ss, v_sb, o_ss, o_sb;
+  int32_t sq, sk, b, h, d;
+  float p_drop;
+  uint32_t site;
+  int32_t reserved;
+} toist_attn_desc;
+
+typedef struct toist_attn_bwd_desc {
+  toist_attn_desc fwd; /* the forward call's descriptor (out and lse as the forward wrote them) */
+  const void* dout;
+  void* dq;
+  void* dk;
+  void* dv;
+  void* workspace; /* toist_attention_bwd_workspace() bytes, f32 partial dQ per 128-key tile */
+  int64_t do_ss, do_sb, dq_ss, dq_sb, dk_ss, dk_sb, dv_ss, dv_sb;
+} toist_attn_bwd_desc;
+
+size_t toist_sizeof_attn_desc(void);
+size_t toist_sizeof_attn_bwd_desc(void);
+int toist_attention_supported(int32_t sq, int32_t sk, int32_t d);
+int toist_attention_fwd(const toist_attn_desc* a, void* stream);
+int64_t toist_attention_bwd_workspace(int32_t sq, int32_t sk, int32_t b, int32_t h, int32_t d);
+int toist_attention_bwd(const toist_attn_bwd_desc* a, void* stream);
+/* keep[b, h, sq, sk] in {0, 1}: the dropout decisions of the fused kernels for (seed, site) - test support */
+int toist_attention_dropout_mask(uint8_t* keep, int32_t b, int32_t h, int32_t sq, int32_t sk, float p_drop,
+                                 const uint64_t* seed, uint32_t site, void* stream);
+
 int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t batch, int32_t h, int32_t w,
                    int32_t num_pos_feats, float temperature, void* stream);
 /* ids [batch, len]; rows of out / pos_ids / dx are b*len + l, or l*batch + b when seq_first != 0 */

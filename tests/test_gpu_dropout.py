@@ -64,7 +64,7 @@ def test_attention_dropout_forward_backward():
     qq, kk, vv = rnd(sq, b, e).to(BF), rnd(sk, b, e).to(BF), rnd(sk, b, e).to(BF)
     km = torch.zeros(b, sk, dtype=torch.uint8, device=DEV)
     km[1, sk - 7:] = 1
-    ctx, probs = K.attention_fwd(qq, kk, vv, km, h, drop=drop)
+    ctx, probs = K.attention_fwd(qq, kk, vv, km, h, drop=drop, fused=False)  # the unfused path keeps P and dropout(P)
     P, Pd = probs
     ld = P.shape[-1]
     mask = mask_of((b, h, sq, ld), drop)[..., :sk]

@@ -204,14 +204,15 @@ def test_roberta_embeddings(K):
 
 
 # ------------------------------------------------------------------------------------------------ attention (composite)
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("sq,sk,b,h,d", [(416, 416, 2, 8, 32), (100, 233, 2, 8, 32), (16, 16, 3, 12, 64)])
-def test_attention_core(K, sq, sk, b, h, d):
+def test_attention_core(K, sq, sk, b, h, d, fused):
     torch.manual_seed(10)
     e = h * d
     q, k, v = rn(sq, b, e, dtype=BF), rn(sk, b, e, dtype=BF), rn(sk, b, e, dtype=BF)
     km = torch.zeros(b, sk, dtype=torch.uint8, device=DEV)
     km[0, sk - 3:] = 1
-    ctx, probs = K.attention_fwd(q, k, v, km, h)
+    ctx, probs = K.attention_fwd(q, k, v, km, h, fused=fused)
 
     def heads(t, s):
         return t.float().view(s, b, h, d).permute(1, 2, 0, 3)

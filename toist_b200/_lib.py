@@ -59,6 +59,26 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p), ("lse", C.c_void_p),
+        ("key_mask", C.c_void_p), ("seed", C.c_void_p),
+        ("q_ss", C.c_int64), ("q_sb", C.c_int64), ("k_ss", C.c_int64), ("k_sb", C.c_int64),
+        ("v_ss", C.c_int64), ("v_sb", C.c_int64), ("o_ss", C.c_int64), ("o_sb", C.c_int64),
+        ("sq", C.c_int32), ("sk", C.c_int32), ("b", C.c_int32), ("h", C.c_int32), ("d", C.c_int32),
+        ("p_drop", C.c_float), ("site", C.c_uint32), ("reserved", C.c_int32),
+    ]
+
+
+class AttnBwdDesc(C.Structure):
+    _fields_ = [
+        ("fwd", AttnDesc),
+        ("dout", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("workspace", C.c_void_p),
+        ("do_ss", C.c_int64), ("do_sb", C.c_int64), ("dq_ss", C.c_int64), ("dq_sb", C.c_int64),
+        ("dk_ss", C.c_int64), ("dk_sb", C.c_int64), ("dv_ss", C.c_int64), ("dv_sb", C.c_int64),
+    ]
+
+
 _lib = None
 
 
@@ -82,6 +102,8 @@ def load() -> C.CDLL:
         raise ToistError("libtoist_b200.so ABI version mismatch; rebuild")
     if lib.toist_sizeof_gemm_desc() != C.sizeof(GemmDesc):
         raise ToistError("toist_gemm_desc layout mismatch between _lib.py and libtoist_b200.so; rebuild")
+    if lib.toist_sizeof_attn_desc() != C.sizeof(AttnDesc) or lib.toist_sizeof_attn_bwd_desc() != C.sizeof(AttnBwdDesc):
+        raise ToistError("toist_attn_desc layout mismatch between _lib.py and libtoist_b200.so; rebuild")
     _lib = lib
     return lib
 
@@ -105,7 +127,7 @@ def parse_header():
     text = _HEADER.read_text()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(int|size_t|const char\*)\s+(toist_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"\b(int64_t|int|size_t|const char\*)\s+(toist_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         restype = C.c_char_p if ret == "const char*" else _SCALARS[ret]
         argtypes = []

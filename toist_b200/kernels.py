@@ -652,8 +652,95 @@ def _ld8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+FUSED_ATTENTION = os.environ.get("TOIST_FUSED_ATTN", "1") != "0"
+
+
+class FusedAttnSaved:
+    """What the fused forward keeps for its backward: the output, the row log-sum-exp and the key mask (the scores and
+    probabilities never leave the SM)."""
+    __slots__ = ("ctx", "lse", "key_mask")
+
+    def __init__(self, ctx, lse, key_mask):
+        self.ctx, self.lse, self.key_mask = ctx, lse, key_mask
+
+
+def fused_attention_ok(sq: int, sk: int, d: int) -> bool:
+    return FUSED_ATTENTION and _L().toist_attention_supported(sq, sk, d) == 1
+
+
+def _attn_desc(q, k, v, out, lse, key_mask_u8, nhead, drop) -> "_lib.AttnDesc":
+    sq, b, e = q.shape
+    a = _lib.AttnDesc()
+    for t in (q, k, v, out):
+        assert t.dtype == torch.bfloat16 and t.stride(2) == 1
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.lse = lse.data_ptr() if lse is not None else None
+    if key_mask_u8 is not None:
+        assert key_mask_u8.dtype == torch.uint8 and key_mask_u8.is_contiguous() and key_mask_u8.shape == (b, k.shape[0])
+        a.key_mask = key_mask_u8.data_ptr()
+    a.q_ss, a.q_sb, a.k_ss, a.k_sb = q.stride(0), q.stride(1), k.stride(0), k.stride(1)
+    a.v_ss, a.v_sb, a.o_ss, a.o_sb = v.stride(0), v.stride(1), out.stride(0), out.stride(1)
+    a.sq, a.sk, a.b, a.h, a.d = sq, k.shape[0], b, nhead, e // nhead
+    if drop is not None:
+        p_drop, seed, site = drop
+        a.p_drop, a.seed, a.site = float(p_drop), seed.data_ptr(), int(site)
+    return a
+
+
+def attention_fused_fwd(q, k, v, key_mask_u8, nhead: int, ctx: Optional[torch.Tensor] = None, drop=None,
+                        need_lse: bool = True):
+    """One launch: ctx = dropout(softmax(q k^T / sqrt(d) + mask)) v  (csrc/attention.cu).  Returns (ctx, lse)."""
+    sq, b, e = q.shape
+    sk = k.shape[0]
+    if ctx is None:
+        ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((b, nhead, sq), dtype=torch.float32, device=q.device) if need_lse else None
+    a = _attn_desc(q, k, v, ctx, lse, key_mask_u8, nhead, drop)
+    keep = (q, k, v, ctx, lse, key_mask_u8, drop)
+
+    def launch(a=a, keep=keep):
+        _lib.check(_L().toist_attention_fwd(C.addressof(a), _stream()))
+
+    with _prof("attn_core", 4.0 * sq * sk * (e // nhead) * nhead * b, ("attn_fwd", sq, sk, b, nhead, e, drop is not None),
+               launch):
+        launch()
+    _count()
+    return ctx, lse
+
+
+def attention_fused_bwd(dctx, q, k, v, saved: FusedAttnSaved, nhead: int, dq, dk, dv, drop=None) -> None:
+    sq, b, e = q.shape
+    sk = k.shape[0]
+    d = e // nhead
+    a = _lib.AttnBwdDesc()
+    a.fwd = _attn_desc(q, k, v, saved.ctx, saved.lse, saved.key_mask, nhead, drop)
+    for t in (dctx, dq, dk, dv):
+        assert t.dtype == torch.bfloat16 and t.stride(2) == 1
+    ws = torch.empty((_L().toist_attention_bwd_workspace(sq, sk, b, nhead, d) // 4,), dtype=torch.float32, device=q.device)
+    a.dout, a.dq, a.dk, a.dv, a.workspace = dctx.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr()
+    a.do_ss, a.do_sb, a.dq_ss, a.dq_sb = dctx.stride(0), dctx.stride(1), dq.stride(0), dq.stride(1)
+    a.dk_ss, a.dk_sb, a.dv_ss, a.dv_sb = dk.stride(0), dk.stride(1), dv.stride(0), dv.stride(1)
+    keep = (dctx, q, k, v, saved, dq, dk, dv, ws, drop)
+
+    def launch(a=a, keep=keep):
+        _lib.check(_L().toist_attention_bwd(C.addressof(a), _stream()))
+
+    with _prof("attn_core", 10.0 * sq * sk * d * nhead * b, ("attn_bwd", sq, sk, b, nhead, e, drop is not None), launch):
+        launch()
+    _count(2)
+
+
+def attention_dropout_mask(b: int, nhead: int, sq: int, sk: int, drop) -> torch.Tensor:
+    """uint8 [b, nhead, sq, sk]: 1 where the fused attention kernels keep the probability (test support)."""
+    p_drop, seed, site = drop
+    keep = torch.empty((b, nhead, sq, sk), dtype=torch.uint8, device=seed.device)
+    _ck(_L().toist_attention_dropout_mask(keep.data_ptr(), b, nhead, sq, sk, float(p_drop), seed.data_ptr(), int(site),
+                                          _stream()))
+    return keep
+
+
 def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8: Optional[torch.Tensor], nhead: int,
-                  need_probs: bool = True, ctx: Optional[torch.Tensor] = None, drop=None):
+                  need_probs: bool = True, ctx: Optional[torch.Tensor] = None, drop=None, fused: Optional[bool] = None):
     """Multi-head attention core on packed projections.
 
     q [Sq, B, E], k [Sk, B, E], v [Sk, B, E]: bf16 views whose last dim is contiguous (they may be column slices of a
@@ -664,6 +751,11 @@ def attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_mask_u8
     sq, b, e = q.shape
     sk = k.shape[0]
     d = e // nhead
+    if fused is None:
+        fused = fused_attention_ok(sq, sk, d)
+    if fused:  # one launch, scores and probabilities stay on the SM; `probs` is then the saved (ctx, lse, mask) record
+        ctx, lse = attention_fused_fwd(q, k, v, key_mask_u8, nhead, ctx=ctx, drop=drop, need_lse=need_probs)
+        return ctx, (FusedAttnSaved(ctx, lse, key_mask_u8) if need_probs else None)
     ld = _ld8(sk)
     dev = q.device
     scores = torch.empty((b, nhead, sq, ld), dtype=torch.float32, device=dev)
@@ -701,6 +793,9 @@ def attention_bwd(dctx: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch
                   dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, drop=None) -> None:
     """Backward of attention_fwd (`probs` exactly as it returned them, `drop` the same triple).  dq/dk/dv are bf16
     outputs with the same [S, B, E] indexing as q/k/v (they may be column slices of one packed gradient buffer)."""
+    if isinstance(probs, FusedAttnSaved):
+        attention_fused_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv, drop=drop)
+        return
     with gemm_tag("attn_core"):
         _attention_bwd(dctx, q, k, v, probs, nhead, dq, dk, dv, drop)
 
