@@ -113,8 +113,14 @@ def test_encoder_layer_with_dropout_matches_masked_reference():
     dy = rnd(S * B, E)
     dx = Bk.encoder_layer_bwd(split_w(sd), g, set(sd), dy.to(BF), saved, H, B, drop)
     # reference with the recovered masks
-    ld = (S + 7) // 8 * 8
-    m_att = mask_of((B, H, S, ld), drop.site(0))[..., :S]
+    from toist_b200 import kernels as K
+
+    if K.fused_attention_ok(S, S, dh):  # the fused kernel draws its own (paired 16-bit) decisions
+        p_att, seed_att, site_att = drop.site(0)
+        m_att = K.attention_dropout_mask(B, H, S, S, drop.site(0)).float() / (1.0 - round(p_att * 65536) / 65536.0)
+    else:
+        ld = (S + 7) // 8 * 8
+        m_att = mask_of((B, H, S, ld), drop.site(0))[..., :S]
     m1 = mask_of((S * B, E), drop.site(1))
     mh = mask_of((S * B, 2048), drop.site(2))
     m2 = mask_of((S * B, E), drop.site(3))

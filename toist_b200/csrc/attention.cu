@@ -31,7 +31,8 @@
 
 namespace toist {
 
-constexpr int kAttNP = 3;  // depth of the P ring (forward)
+constexpr int kAttNP = 4;  // depth of the P ring (forward)
+constexpr int kFwdThreads = 320;
 constexpr int kAttMaxKB = 7;
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
@@ -62,7 +63,7 @@ struct AttnFwdParams {
 };
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -72,7 +73,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sK = sQ + 16384;
   uint8_t* sV = sK + kb * 8192;
   uint8_t* sP = sV + kb * 8192;
-  uint32_t* sBits = reinterpret_cast<uint32_t*>(sP + kAttNP * 16384);  // one mask word per 32 keys
+  float* sRed = reinterpret_cast<float*>(sP + kAttNP * 16384);  // [2][128] row maxima, [2][128] row sums
+  uint32_t* sBits = reinterpret_cast<uint32_t*>(sRed + 512);    // one mask word per 32 keys
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBits + 16);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
@@ -157,34 +159,52 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
     }
   } else {
+    // 8 softmax warps: thread (r, hf) owns query row r = TMEM lane r and the 64-key blocks j with j % 2 == hf
     const int quad = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const int qrow = q0 + r;
+    const bool warp_valid = q0 + quad * 32 < p.sq;  // warp-uniform: rows past the last query do no arithmetic
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     // key mask as one bit per key (1 = masked or past the last key)
-    for (int w = quad; w < kb * 2; w += 4) {
+    for (int w = warp - 2; w < kb * 2; w += 8) {
       const int key = w * 32 + lane;
       const bool m = key >= p.sk || (p.kmask != nullptr && p.kmask[(long long)b * p.sk + key] != 0);
       const uint32_t bits = __ballot_sync(0xffffffffu, m);
       if (lane == 0) sBits[w] = bits;
     }
-    named_barrier_sync(1, 128);
+    named_barrier_sync(1, 256);
     // ---- pass 1: row maximum of the raw scores over the unmasked keys
     float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      mbar_wait(&bar_s[c], 0);
-      tc_fence_after();
-      const int n = min(256, ncols - c * 256);
-      for (int c0 = 0; c0 < n; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(lane_addr + (uint32_t)(c * 256 + c0), raw);
-        tmem_ld_wait();
-        const uint32_t bits = sBits[(c * 256 + c0) >> 5];
+    int s_ready = 0;
+    if (warp_valid) {
+      for (int j = hf; j < kb; j += 2) {
+        while (s_ready <= (j >> 2)) {
+          mbar_wait(&bar_s[s_ready], 0);
+          ++s_ready;
+        }
+        tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (!((bits >> i) & 1u)) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = j * 64 + half * 32;
+          uint32_t raw[32];
+          tmem_ld_32x32(lane_addr + (uint32_t)c0, raw);
+          tmem_ld_wait();
+          const uint32_t bits = sBits[c0 >> 5];
+          if (bits == 0u) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!((bits >> i) & 1u)) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          }
+        }
       }
     }
+    sRed[hf * 128 + r] = mx;
+    named_barrier_sync(1, 256);
+    mx = fmaxf(sRed[r], sRed[128 + r]);
     // ---- pass 2: e = exp(scale * (s - max)), dropout, bf16 operand tiles for the PV product
     const float m2 = mx * p.scale_log2;
     const bool drop = p.seed != nullptr;
@@ -194,54 +214,85 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       k0 = (uint32_t)key;
       k1 = (uint32_t)(key >> 32);
     }
-    const uint32_t pair_base = (uint32_t)(((long long)(b * p.h + h) * p.sq + qrow) * (kb * 32));
+    const uint32_t pair_base = (uint32_t)(((long long)(b * p.h + h) * p.sq + qrow) * (kb * 32)) + k0;
     const uint32_t rx = (uint32_t)(r & 7);
     float l = 0.f;
-    for (int j = 0; j < kb; ++j) {
+    for (int j = hf; j < kb; j += 2) {
       const int slot = j % kAttNP;
       mbar_wait(&p_empty[slot], (uint32_t)(((j / kAttNP) & 1) ^ 1));
-      uint8_t* prow = sP + slot * 16384 + r * 128;
+      if (warp_valid) {
+        while (s_ready <= (j >> 2)) {
+          mbar_wait(&bar_s[s_ready], 0);
+          ++s_ready;
+        }
+        tc_fence_after();
+        uint8_t* prow = sP + slot * 16384 + r * 128;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int c0 = j * 64 + half * 32;
-        uint32_t raw[32];
-        tmem_ld_32x32(lane_addr + (uint32_t)c0, raw);
-        tmem_ld_wait();
-        const uint32_t bits = sBits[c0 >> 5];
-        uint32_t pk[16];
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = j * 64 + half * 32;
+          uint32_t raw[32];
+          tmem_ld_32x32(lane_addr + (uint32_t)c0, raw);
+          tmem_ld_wait();
+          const uint32_t bits = sBits[c0 >> 5];
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0 = ((bits >> i) & 1u) ? 0.f : ex2_approx(__uint_as_float(raw[i]) * p.scale_log2 - m2);
-          float e1 = ((bits >> (i + 1)) & 1u) ? 0.f : ex2_approx(__uint_as_float(raw[i + 1]) * p.scale_log2 - m2);
-          l += e0 + e1;
-          if (drop) {
-            const uint32_t w = hash32(pair_base + (uint32_t)((c0 + i) >> 1) + k0) ^ k1;
-            if ((w & 0xffffu) < p.thr16) e0 = 0.f;
-            if ((w >> 16) < p.thr16) e1 = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            float e0 = ex2_approx(__uint_as_float(raw[i]) * p.scale_log2 - m2);
+            float e1 = ex2_approx(__uint_as_float(raw[i + 1]) * p.scale_log2 - m2);
+            if (bits != 0u) {  // warp-uniform
+              if ((bits >> i) & 1u) e0 = 0.f;
+              if ((bits >> (i + 1)) & 1u) e1 = 0.f;
+            }
+            l += e0 + e1;
+            if (drop) {
+              const uint32_t w = hash32(pair_base + (uint32_t)((c0 + i) >> 1)) ^ k1;
+              if ((w & 0xffffu) < p.thr16) e0 = 0.f;
+              if ((w >> 16) < p.thr16) e1 = 0.f;
+            }
+            pk[i >> 1] = pack_bf16(e0, e1);
           }
-          pk[i >> 1] = pack_bf16(e0, e1);
-        }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t chunk = (uint32_t)(half * 4 + g) ^ rx;
-          *reinterpret_cast<uint4*>(prow + (chunk << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t chunk = (uint32_t)(half * 4 + g) ^ rx;
+            *reinterpret_cast<uint4*>(prow + (chunk << 4)) =
+                make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+          }
         }
+        tc_fence_before();
+        fence_proxy_async();
       }
-      tc_fence_before();
-      fence_proxy_async();
       mbar_arrive(&p_full[slot]);
     }
     pdl_trigger();
-    // ---- epilogue: O * keep_scale / l -> bf16, log-sum-exp for the backward pass
+    sRed[256 + hf * 128 + r] = l;
+    named_barrier_sync(1, 256);
+    l = sRed[256 + r] + sRed[384 + r];
+    // ---- epilogue: O * keep_scale / l -> bf16 (this thread: d/2 columns), log-sum-exp for the backward pass
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const float inv = p.keep_scale / l;
-    for (int c0 = 0; c0 < p.d; c0 += 32) {
-      uint32_t raw[32];
-      tmem_ld_32x32(lane_addr + (uint32_t)(ncols + c0), raw);
+    const int hc = p.d >> 1;
+    __nv_bfloat16* op = p.out + (long long)qrow * p.o_ss + (long long)b * p.o_sb + h * p.d + hf * hc;
+    if (hc == 16) {
+      uint32_t raw[16];
+      tmem_ld_32x16(lane_addr + (uint32_t)(ncols + hf * 16), raw);
       tmem_ld_wait();
       if (qrow < p.sq) {
-        __nv_bfloat16* op = p.out + (long long)qrow * p.o_ss + (long long)b * p.o_sb + h * p.d + c0;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(raw[g * 8 + 0]) * inv, __uint_as_float(raw[g * 8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(raw[g * 8 + 2]) * inv, __uint_as_float(raw[g * 8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(raw[g * 8 + 4]) * inv, __uint_as_float(raw[g * 8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(raw[g * 8 + 6]) * inv, __uint_as_float(raw[g * 8 + 7]) * inv);
+          reinterpret_cast<uint4*>(op)[g] = u;
+        }
+      }
+    } else {
+      uint32_t raw[32];
+      tmem_ld_32x32(lane_addr + (uint32_t)(ncols + hf * 32), raw);
+      tmem_ld_wait();
+      if (qrow < p.sq) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
@@ -253,7 +304,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-    if (p.lse != nullptr && qrow < p.sq) p.lse[(long long)(b * p.h + h) * p.sq + qrow] = mx * p.scale + logf(l);
+    if (hf == 0 && p.lse != nullptr && qrow < p.sq)
+      p.lse[(long long)(b * p.h + h) * p.sq + qrow] = mx * p.scale + logf(l);
   }
 
   tc_fence_before();
@@ -270,6 +322,8 @@ struct AttnBwdParams {
   float scale, scale_log2;
   const __nv_bfloat16* o;
   long long o_ss, o_sb;
+  const __nv_bfloat16* dout;
+  long long do_ss, do_sb;
   const float* lse;
   const uint8_t* kmask;
   const unsigned long long* seed;
@@ -283,6 +337,7 @@ struct AttnBwdParams {
 };
 
 constexpr int kBwdThreads = 320;
+constexpr int kBwdMaxNQ = 8;  // query chunks of 128 (sq <= 1024)
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -295,9 +350,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sRing = sV + 16384;      // 2 x (Q chunk 16 KB | dO chunk 16 KB)
   uint8_t* sPd = sRing + 65536;     // Pd^T: 2 blocks of [128 keys][64 queries]
   uint8_t* sdS = sPd + 32768;       // dS^T: same layout
-  float* sLse = reinterpret_cast<float*>(sdS + 32768);  // [2][128] log2-domain lse (inf past the last query)
-  float* sDelta = sLse + 256;                            // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  float* sLse = reinterpret_cast<float*>(sdS + 32768);  // [nq <= 8][128] log2-domain lse (inf past the last query)
+  float* sDelta = sLse + kBwdMaxNQ * 128;                // [nq][128] rowsum(dO * O)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + kBwdMaxNQ * 128);
   uint64_t* bar_kv = bars + 0;
   uint64_t* full = bars + 1;    // [2]
   uint64_t* empty = bars + 3;   // [2]
@@ -408,34 +463,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     const uint32_t pairs_per_row = (uint32_t)(p.kb * 32);
     const uint32_t rx = (uint32_t)(r & 7);
+    const bool warp_keys = key0 + quad * 32 < p.sk;  // warp-uniform: at least one of this warp's 32 keys exists
     const float LOG2E = 1.4426950408889634f;
-    for (int c = 0; c < p.nq; ++c) {
-      const int st = c & 1;
-      const int qc0 = c * 128;
-      mbar_wait(&full[st], (uint32_t)((c >> 1) & 1));
-      if (half == 0) {  // delta[q] = sum_d dO[q, d] * O[q, d]; lse in the log2 domain
-        const int qrow = qc0 + r;
-        float dl = 0.f, ls = INFINITY;
-        if (qrow < p.sq) {
-          const uint8_t* drow = sRing + st * 32768 + 16384 + r * 128;
-          const __nv_bfloat16* orow = p.o + (long long)qrow * p.o_ss + (long long)b * p.o_sb + h * p.d;
-          for (int g = 0; g < (p.d >> 3); ++g) {
-            const uint4 ud = *reinterpret_cast<const uint4*>(drow + ((((uint32_t)g) ^ rx) << 4));
-            const uint4 uo = __ldg(reinterpret_cast<const uint4*>(orow) + g);
-            const uint32_t* pd_ = &ud.x;
-            const uint32_t* po_ = &uo.x;
+    // delta[q] = sum_d dO[q, d] * O[q, d] and the log2-domain lse of every query of this (b, h), once, straight from
+    // global memory: all loads are in flight together and overlap the K / V / Q tile loads and the first products
+    for (int qrow = (int)threadIdx.x - 64; qrow < p.nq * 128; qrow += 256) {
+      float dl = 0.f, ls = INFINITY;
+      if (qrow < p.sq) {
+        const __nv_bfloat16* orow = p.o + (long long)qrow * p.o_ss + (long long)b * p.o_sb + h * p.d;
+        const __nv_bfloat16* drow = p.dout + (long long)qrow * p.do_ss + (long long)b * p.do_sb + h * p.d;
+        for (int g = 0; g < (p.d >> 3); ++g) {
+          const uint4 ud = __ldg(reinterpret_cast<const uint4*>(drow) + g);
+          const uint4 uo = __ldg(reinterpret_cast<const uint4*>(orow) + g);
+          const uint32_t* pd_ = &ud.x;
+          const uint32_t* po_ = &uo.x;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 fd = unpack_bf16(pd_[k]), fo = unpack_bf16(po_[k]);
-              dl += fd.x * fo.x + fd.y * fo.y;
-            }
+          for (int k = 0; k < 4; ++k) {
+            const float2 fd = unpack_bf16(pd_[k]), fo = unpack_bf16(po_[k]);
+            dl += fd.x * fo.x + fd.y * fo.y;
           }
-          ls = p.lse[(long long)(b * p.h + h) * p.sq + qrow] * LOG2E;
         }
-        sDelta[st * 128 + r] = dl;
-        sLse[st * 128 + r] = ls;
+        ls = p.lse[(long long)(b * p.h + h) * p.sq + qrow] * LOG2E;
       }
-      named_barrier_sync(1, 256);
+      sDelta[qrow] = dl;
+      sLse[qrow] = ls;
+    }
+    named_barrier_sync(1, 256);
+    for (int c = 0; c < p.nq; ++c) {
+      const int st = c;
+      const int qc0 = c * 128;
       mbar_wait(bar_st, (uint32_t)(c & 1));
       tc_fence_after();
       uint8_t* pd_row = sPd + half * 16384 + r * 128;
@@ -443,35 +499,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll 1
       for (int g = 0; g < 2; ++g) {
         const int qi0 = half * 64 + g * 32;
+        if (!warp_keys || qc0 + qi0 >= p.sq) {
+          // warp-uniform: no valid key in this warp's 32 rows, or no valid query in these 32 columns -> exact zeros
+          // (rows of keys past the end are written once, in the first chunk that reaches here, and stay zero)
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t chunk = (uint32_t)(g * 4 + q4) ^ rx;
+            *reinterpret_cast<uint4*>(pd_row + (chunk << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(ds_row + (chunk << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
         uint32_t st_raw[32], dp_raw[32];
         tmem_ld_32x32(lane_addr + kColST + (uint32_t)qi0, st_raw);
         tmem_ld_32x32(lane_addr + kColDP + (uint32_t)qi0, dp_raw);
         tmem_ld_wait();
         uint32_t ppk[16], dpk[16];
-        const uint32_t row0 = (uint32_t)((b * p.h + h) * p.sq + qc0 + qi0);
+        // pair index of (query row0 + i, this key) = (row0 + i) * pairs_per_row + key / 2; lanes 2m and 2m+1 hold the
+        // two keys of one pair, so each computes the hash of one of two consecutive queries and they swap
+        const uint32_t hbase = (uint32_t)((b * p.h + h) * p.sq + qc0 + qi0) * pairs_per_row + (uint32_t)(key >> 1) + k0;
+        const float4* lse4 = reinterpret_cast<const float4*>(sLse + st * 128 + qi0);
+        const float4* del4 = reinterpret_cast<const float4*>(sDelta + st * 128 + qi0);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2], dsv[2];
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 ls4 = lse4[i4], dl4 = del4[i4];
+          const float lsv[4] = {ls4.x, ls4.y, ls4.z, ls4.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int qi = qi0 + i + e;
-            const float ls = sLse[st * 128 + qi];
-            const float dl = sDelta[st * 128 + qi];
-            float pr = key_ok ? ex2_approx(__uint_as_float(st_raw[i + e]) * p.scale_log2 - ls) : 0.f;
-            float dp = __uint_as_float(dp_raw[i + e]);
-            float pdv = pr;
+          for (int i2 = 0; i2 < 2; ++i2) {
+            const int i = i4 * 4 + i2 * 2;
+            bool keep0 = true, keep1 = true;
             if (drop) {
-              const uint32_t w = hash32((row0 + (uint32_t)(i + e)) * pairs_per_row + (uint32_t)(key >> 1) + k0) ^ k1;
-              const uint32_t v16 = (key & 1) ? (w >> 16) : (w & 0xffffu);
-              const bool keep = v16 >= p.thr16;
-              pdv = keep ? pr * p.keep_scale : 0.f;
-              dp = keep ? dp * p.keep_scale : 0.f;
+              const uint32_t mine = hash32(hbase + (uint32_t)(i + (lane & 1)) * pairs_per_row) ^ k1;
+              const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+              const uint32_t w0 = (lane & 1) ? other : mine, w1 = (lane & 1) ? mine : other;
+              keep0 = ((lane & 1) ? (w0 >> 16) : (w0 & 0xffffu)) >= p.thr16;
+              keep1 = ((lane & 1) ? (w1 >> 16) : (w1 & 0xffffu)) >= p.thr16;
             }
-            pv[e] = pdv;
-            dsv[e] = pr * (dp - dl) * p.scale;
+            float pr0 = ex2_approx(__uint_as_float(st_raw[i]) * p.scale_log2 - lsv[i2 * 2]);
+            float pr1 = ex2_approx(__uint_as_float(st_raw[i + 1]) * p.scale_log2 - lsv[i2 * 2 + 1]);
+            if (!key_ok) pr0 = pr1 = 0.f;
+            const float dp0 = keep0 ? __uint_as_float(dp_raw[i]) * p.keep_scale : 0.f;
+            const float dp1 = keep1 ? __uint_as_float(dp_raw[i + 1]) * p.keep_scale : 0.f;
+            ppk[i >> 1] = pack_bf16(keep0 ? pr0 * p.keep_scale : 0.f, keep1 ? pr1 * p.keep_scale : 0.f);
+            dpk[i >> 1] = pack_bf16(pr0 * p.scale * (dp0 - dlv[i2 * 2]), pr1 * p.scale * (dp1 - dlv[i2 * 2 + 1]));
           }
-          ppk[i >> 1] = pack_bf16(pv[0], pv[1]);
-          dpk[i >> 1] = pack_bf16(dsv[0], dsv[1]);
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -645,7 +716,7 @@ extern "C" size_t toist_sizeof_attn_desc(void) { return sizeof(toist_attn_desc);
 extern "C" size_t toist_sizeof_attn_bwd_desc(void) { return sizeof(toist_attn_bwd_desc); }
 
 extern "C" int toist_attention_supported(int32_t sq, int32_t sk, int32_t d) {
-  return (d == 32 || d == 64) && sk >= 1 && sk <= kAttMaxKB * 64 && sq >= 1 ? 1 : 0;
+  return (d == 32 || d == 64) && sk >= 1 && sk <= kAttMaxKB * 64 && sq >= 1 && sq <= kBwdMaxNQ * 128 ? 1 : 0;
 }
 
 extern "C" int toist_attention_fwd(const toist_attn_desc* a, void* stream_v) {
@@ -680,15 +751,15 @@ extern "C" int toist_attention_fwd(const toist_attn_desc* a, void* stream_v) {
   if ((rc = make_qkv_map(&mq, a->q, a->d, a->sq, a->h, a->b, a->q_ss, a->q_sb, 128)) != TOIST_OK) return rc;
   if ((rc = make_qkv_map(&mk, a->k, a->d, a->sk, a->h, a->b, a->k_ss, a->k_sb, 64)) != TOIST_OK) return rc;
   if ((rc = make_qkv_map(&mv, a->v, a->d, a->sk, a->h, a->b, a->v_ss, a->v_sb, 64)) != TOIST_OK) return rc;
-  const int smem = 16384 + 2 * p.kb * 8192 + kAttNP * 16384 + 64 + 16 * 8 + 16 + 1024;
+  const int smem = 16384 + 2 * p.kb * 8192 + kAttNP * 16384 + 2048 + 64 + 16 * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          16384 + 2 * kAttMaxKB * 8192 + kAttNP * 16384 + 64 + 16 * 8 + 16 + 1024));
+                                          16384 + 2 * kAttMaxKB * 8192 + kAttNP * 16384 + 2048 + 64 + 16 * 8 + 16 + 1024));
     configured = true;
   }
   dim3 grid((unsigned)((a->sq + 127) / 128), (unsigned)a->h, (unsigned)a->b);
-  TOIST_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(192), (size_t)smem, stream, mq, mk, mv, p));
+  TOIST_CHECK_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(kFwdThreads), (size_t)smem, stream, mq, mk, mv, p));
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -709,7 +780,7 @@ extern "C" int toist_attention_bwd(const toist_attn_bwd_desc* a, void* stream_v)
                 "toist_attention_bwd: dropout needs a seed and 0 < p < 1");
   const int e = f->h * f->d;
   TOIST_REQUIRE(a->dq_ss % 8 == 0 && a->dq_sb % 8 == 0 && a->dk_ss % 8 == 0 && a->dk_sb % 8 == 0 && a->dv_ss % 8 == 0 &&
-                    a->dv_sb % 8 == 0 && f->o_ss % 8 == 0 && f->o_sb % 8 == 0,
+                    a->dv_sb % 8 == 0 && f->o_ss % 8 == 0 && f->o_sb % 8 == 0 && a->do_ss % 8 == 0 && a->do_sb % 8 == 0,
                 "toist_attention_bwd: strides must be multiples of 8 elements");
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
@@ -720,6 +791,8 @@ extern "C" int toist_attention_bwd(const toist_attn_bwd_desc* a, void* stream_v)
   p.scale_log2 = p.scale * 1.4426950408889634f;
   p.o = reinterpret_cast<const __nv_bfloat16*>(f->out);
   p.o_ss = f->o_ss; p.o_sb = f->o_sb;
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(a->dout);
+  p.do_ss = a->do_ss; p.do_sb = a->do_sb;
   p.lse = f->lse;
   p.kmask = f->key_mask;
   p.keep_scale = 1.f;
@@ -738,7 +811,7 @@ extern "C" int toist_attention_bwd(const toist_attn_bwd_desc* a, void* stream_v)
   if ((rc = make_qkv_map(&mk, f->k, f->d, f->sk, f->h, f->b, f->k_ss, f->k_sb, 128)) != TOIST_OK) return rc;
   if ((rc = make_qkv_map(&mv, f->v, f->d, f->sk, f->h, f->b, f->v_ss, f->v_sb, 128)) != TOIST_OK) return rc;
   if ((rc = make_qkv_map(&mdo, a->dout, f->d, f->sq, f->h, f->b, a->do_ss, a->do_sb, 128)) != TOIST_OK) return rc;
-  const int smem = 32768 + 65536 + 65536 + 2048 + 8 * 8 + 16 + 1024;
+  const int smem = 32768 + 65536 + 65536 + 2 * kBwdMaxNQ * 512 + 8 * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
