@@ -395,7 +395,7 @@ int toist_box_loss(const float* boxes, const int32_t* match_q, const int32_t* tg
 int toist_cardinality(const float* logits, int32_t* card, int32_t n_layers, int32_t batch, int32_t n_queries,
                       int32_t n_classes, void* stream) {
   TOIST_REQUIRE(logits && card, "toist_cardinality: null pointer");
-  launch_pdl(cardinality_kernel, dim3(n_layers * batch), dim3(128), 0, (cudaStream_t)stream, logits, card, n_queries, n_classes);
+  launch_pdl(cardinality_kernel, dim3(n_layers * batch), dim3(1024), 0, (cudaStream_t)stream, logits, card, n_queries, n_classes);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -414,7 +414,7 @@ int toist_contrastive_align(const float* proj_queries, const float* proj_tokens,
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(contrastive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  launch_pdl(contrastive_kernel, dim3(n_layers * batch), dim3(128), smem, (cudaStream_t)stream, 
+  launch_pdl(contrastive_kernel, dim3(n_layers * batch), dim3(512), smem, (cudaStream_t)stream, 
       proj_queries, proj_tokens, match_q, tgt_count, tok_pos, num_boxes, img_loss, dpq, dpt, batch, n_queries,
       n_tokens, dim, t_max, 1.f / temperature);
   TOIST_CHECK_CUDA(cudaGetLastError());

@@ -10,10 +10,11 @@
 #include "host_util.h"
 #include "boxmath.cuh"
 #include "lsap.h"
+#include "lsap_warp.cuh"
 
 namespace toist {
 
-// grid = (L*B), block = 128 (4 warps); warp w handles queries w, w+4, ...
+// grid = (L*B, ceil(Q / 4)), block = 128 (4 warps): one query per warp (48 x 25 CTAs instead of 48 long-running ones)
 // cost[l][b][q][t] for t < count[b]; padding columns are written as 0.
 __global__ void match_cost_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                   const float* __restrict__ tgt_boxes, const int* __restrict__ tgt_count,
@@ -26,7 +27,7 @@ __global__ void match_cost_kernel(const float* __restrict__ logits, const float*
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   extern __shared__ float prob[];  // [nwarps][C]
   float* myprob = prob + warp * C;
-  for (int q = warp; q < Q; q += nwarps) {
+  for (int q = blockIdx.y * nwarps + warp; q < Q; q += nwarps * gridDim.y) {
     const float* lg = logits + ((size_t)lb * Q + q) * C;
     float mx = -INFINITY;
     for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lg[c]);
@@ -115,6 +116,42 @@ __global__ void lsap_kernel(const float* __restrict__ cost, const int* __restric
   if (rc != 0) atomicOr(flags, 1);
 }
 
+// One warp per problem (lsap_warp.cuh: the column scan of every augmentation step runs on 32 lanes, same scan order,
+// tie rule and float64 arithmetic as the sequential solver above).  Used when max(Q, T) <= kLsapMax.
+__global__ void lsap_warp_kernel(const float* __restrict__ cost, const int* __restrict__ tgt_count,
+                                 int* __restrict__ match_q, int* __restrict__ flags, int B, int Q, int Tmax) {
+  pdl_prologue();
+  __shared__ LsapShared w;
+  const int p = blockIdx.x, lane = threadIdx.x;
+  const int b = p % B;
+  const int T = min(tgt_count[b], Tmax);
+  const float* c = cost + (size_t)p * Q * Tmax;
+  int* mq = match_q + (size_t)p * Tmax;
+  for (int t = lane; t < Tmax; t += 32) mq[t] = -1;
+  if (T == 0) return;
+  int bad = 0;
+  for (int i = lane; i < Q * T; i += 32) {
+    const float v = c[(i / T) * Tmax + (i % T)];
+    if (isnan(v) || v == -INFINITY) bad = 1;
+  }
+  if (__any_sync(0xffffffffu, bad)) {
+    if (lane == 0) atomicOr(flags, 1);
+    return;
+  }
+  __syncwarp();
+  int rc;
+  if (T <= Q) {  // scipy transposes when rows (queries) > cols (targets): rows of the solved problem are targets
+    rc = lsap_warp(c, 1, Tmax, T, Q, w);
+    if (rc == 0)
+      for (int t = lane; t < T; t += 32) mq[t] = w.col4row[t];
+  } else {
+    rc = lsap_warp(c, Tmax, 1, Q, T, w);
+    if (rc == 0)
+      for (int q = lane; q < Q; q += 32) mq[w.col4row[q]] = q;
+  }
+  if (rc != 0 && lane == 0) atomicOr(flags, 1);
+}
+
 }  // namespace toist
 
 using namespace toist;
@@ -128,7 +165,7 @@ int toist_match_cost(const float* logits, const float* boxes, const float* tgt_b
   TOIST_REQUIRE(n_layers > 0 && batch > 0 && n_queries > 0 && n_classes > 0 && t_max > 0, "toist_match_cost: bad sizes");
   const int threads = 128;
   const size_t smem = (size_t)(threads / 32) * n_classes * sizeof(float);
-  launch_pdl(match_cost_kernel, dim3(n_layers * batch), dim3(threads), smem, (cudaStream_t)stream, 
+  launch_pdl(match_cost_kernel, dim3(n_layers * batch, (n_queries + threads / 32 - 1) / (threads / 32)), dim3(threads), smem, (cudaStream_t)stream, 
       logits, boxes, tgt_boxes, tgt_count, posmap, cost, batch, n_queries, n_classes, t_max, w_class, w_bbox, w_giou);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
@@ -139,6 +176,12 @@ int toist_lsap_device(const float* cost, const int32_t* tgt_count, int32_t* matc
   TOIST_REQUIRE(cost && tgt_count && match_q && flags, "toist_lsap_device: null pointer");
   TOIST_REQUIRE(n_problems > 0 && batch > 0 && n_queries > 0 && t_max > 0, "toist_lsap_device: bad sizes");
   const int nmax = n_queries > t_max ? n_queries : t_max;
+  if (nmax <= kLsapMax) {
+    launch_pdl(lsap_warp_kernel, dim3(n_problems), dim3(32), 0, (cudaStream_t)stream, cost, tgt_count, match_q, flags,
+               batch, n_queries, t_max);
+    TOIST_CHECK_CUDA(cudaGetLastError());
+    return TOIST_OK;
+  }
   const size_t smem = (size_t)nmax * (3 * sizeof(double) + 4 * sizeof(int) + 2) + 64;
   TOIST_REQUIRE(smem <= 200 * 1024, "toist_lsap_device: problem too large for shared memory (%zu bytes)", smem);
   static bool configured = false;

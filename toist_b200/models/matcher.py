@@ -13,6 +13,7 @@ import torch
 from torch import nn
 
 from .. import kernels as K
+from ..util.misc import h2d
 
 
 class PackedTargets(NamedTuple):
@@ -38,11 +39,11 @@ def pack_targets(targets: Sequence[dict], positive_map: torch.Tensor, device, t_
     pp = torch.zeros((B * tm, C), dtype=torch.float32, device=device)
     if sum(counts):
         rows = [b * tm + t for b, n in enumerate(counts) for t in range(n)]
-        idx = torch.tensor(rows, dtype=torch.int64).to(device, non_blocking=True)
-        cat = torch.cat([t["boxes"].reshape(-1, 4) for t in targets]).to(device=device, dtype=torch.float32)
+        idx = h2d(torch.tensor(rows, dtype=torch.int64), device)
+        cat = h2d(torch.cat([t["boxes"].reshape(-1, 4) for t in targets]), device, torch.float32)
         tb.index_copy_(0, idx, cat)
-        pp.index_copy_(0, idx, positive_map.to(device=device, dtype=torch.float32))
-    cnt = torch.tensor(counts, dtype=torch.int32).to(device, non_blocking=True)
+        pp.index_copy_(0, idx, h2d(positive_map, device, torch.float32))
+    cnt = h2d(torch.tensor(counts, dtype=torch.int32), device)
     return PackedTargets(tb.view(B, tm, 4), cnt, pp.view(B, tm, C), counts, tm)
 
 

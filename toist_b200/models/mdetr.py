@@ -17,7 +17,7 @@ from torch import nn
 from .. import kernels as K
 from ..runtime import (BACKBONE, DECODER, ENCODER, HEADS, TEXT, Call, GraphCache, ShadowBank, Spec, Stage, run_stage)
 from ..util import dist
-from ..util.misc import NestedTensor
+from ..util.misc import NestedTensor, h2d
 from .backbone import build_backbone
 from .matcher import PackedTargets, build_matcher, indices_from_match, match_layers, pack_targets
 from .transformer import build_transformer
@@ -99,9 +99,9 @@ class ModelRuntime:
         """Draws the dropout seed of this step from torch's CPU generator (reproducible under torch.manual_seed)."""
         s = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
         if self.seed is None or self.seed.device != device:
-            self.seed = s.to(device)
+            self.seed = h2d(s, device)
         else:
-            self.seed.copy_(s, non_blocking=True)
+            self.seed.copy_(s.pin_memory(), non_blocking=True)
 
 
 class MDETR(nn.Module):
@@ -449,7 +449,7 @@ class SetCriterion(nn.Module):
         """Global mean number of target boxes, clamped to >= 1, kept on the device (models/mdetr.py:997-1001 does an
         all-reduce followed by a blocking .item())."""
         n = sum(len(t["labels"]) for t in targets)
-        nb = torch.as_tensor([n], dtype=torch.float, device=device)
+        nb = h2d(torch.as_tensor([n], dtype=torch.float), device)
         if dist.is_dist_avail_and_initialized():
             torch.distributed.all_reduce(nb)
         return torch.clamp(nb / dist.get_world_size(), min=1)
@@ -476,8 +476,7 @@ class SetCriterion(nn.Module):
         pq = ptok = tok_pos = None
         if "contrastive_align" in self.losses:
             pq, ptok = st["proj_queries"], st["proj_tokens"]
-            tok_pos = build_token_positive(outputs["tokenized"], targets, packed.t_max, ptok.shape[1]).to(
-                dev, non_blocking=True)
+            tok_pos = h2d(build_token_positive(outputs["tokenized"], targets, packed.t_max, ptok.shape[1]), dev)
         save = torch.is_grad_enabled() and (logits.requires_grad or boxes.requires_grad)
         call = Call(self._stage, {}, save, graphs=self._graphs, w_class=float(self.matcher.cost_class),
                     w_bbox=float(self.matcher.cost_bbox), w_giou=float(self.matcher.cost_giou),

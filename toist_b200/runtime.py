@@ -257,6 +257,8 @@ class GraphCache:
     launches issued from Python.  Inputs are copied into static buffers; outputs (including everything saved for
     the backward graph) live in the graph's private memory pool and are overwritten by the next replay."""
 
+    timing = None  # list collecting (phase, stage signature, launches, start event, end event) when profiling
+
     def __init__(self):
         self.entries: Dict[tuple, _GraphEntry] = {}
         self.pool = None
@@ -274,7 +276,14 @@ class GraphCache:
             for s_, t in zip(e.static_in, inputs):
                 if s_ is not None:
                     s_.copy_(t)
-            e.graph.replay()
+            if GraphCache.timing is None:
+                e.graph.replay()
+            else:  # tools/stage_times.py: CUDA events around every replay (current stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                e.graph.replay()
+                e1.record()
+                GraphCache.timing.append((key[0], str(key[1])[:60], e.launches, e0, e1))
             K._count(e.launches)
             return e.outputs
         static_in = [None if t is None else t.detach().clone() for t in inputs]

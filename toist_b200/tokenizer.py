@@ -30,7 +30,9 @@ class TokenBatch(dict):
             raise AttributeError(item) from e
 
     def to(self, device) -> "TokenBatch":
-        return TokenBatch({k: v.to(device) for k, v in self.items()}, self._lengths)
+        from .util.misc import h2d
+
+        return TokenBatch({k: h2d(v, device) for k, v in self.items()}, self._lengths)
 
     def char_to_token(self, batch_or_char_index: int, char_index: Optional[int] = None) -> Optional[int]:
         if char_index is None:

@@ -44,3 +44,19 @@ class NestedTensor(object):
 
     def __repr__(self) -> str:
         return repr(self.tensors)
+
+
+def h2d(t: torch.Tensor, device, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Host -> device copy that does not stall the host.  A copy from pageable memory makes the CUDA runtime drain the
+    stream first (the host then waits for every kernel queued so far, once per small tensor, several times per step);
+    staging through the caching pinned allocator keeps it asynchronous, so the host keeps issuing the next stage while
+    the GPU works.  Tensors already on `device` are returned (converted) as they are."""
+    device = torch.device(device)
+    if t.device.type != "cpu" or device.type != "cuda":
+        return t.to(device=device, dtype=dtype) if dtype is not None else t.to(device)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_pinned():
+        t = t.contiguous().pin_memory()
+    return t.to(device, non_blocking=True)
+
