@@ -116,6 +116,155 @@ __global__ void layernorm_bwd_kernel(const TDy* __restrict__ dy, const TDy* __re
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ LayerNorm, bf16 fast path
+// Rows of N = 256 * K bf16 elements (the transformer's 256, RoBERTa's 768): lane l owns the 8 contiguous columns
+// 256 * k + 8 * l .. + 7 of every 256-wide slice, so a row is K 16-byte loads per lane (full 512-byte warp
+// transactions), the statistics are two shuffle reductions and nothing is guarded.  The backward keeps the
+// dgamma / dbeta partial sums of the lane's own columns in registers across the rows of a grid-stride loop; the CTA
+// reduces them once through shared memory and issues one global atomic per column (the generic kernel above spends
+// two shared-memory atomics per ELEMENT).
+template <int K>
+__global__ void __launch_bounds__(128)
+layernorm_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                         float* __restrict__ rstd, long long rows, float eps) {
+  constexpr int N = 256 * K;
+  const int lane = threadIdx.x & 31;
+  float ga[K][8], be[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {  // parameters do not depend on the previous kernel: load before the PDL wait
+    const float4* g4 = reinterpret_cast<const float4*>(gamma + 256 * k + 8 * lane);
+    const float4* b4 = reinterpret_cast<const float4*>(beta + 256 * k + 8 * lane);
+    const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+    ga[k][0] = g0.x; ga[k][1] = g0.y; ga[k][2] = g0.z; ga[k][3] = g0.w;
+    ga[k][4] = g1.x; ga[k][5] = g1.y; ga[k][6] = g1.z; ga[k][7] = g1.w;
+    be[k][0] = b0.x; be[k][1] = b0.y; be[k][2] = b0.z; be[k][3] = b0.w;
+    be[k][4] = b1.x; be[k][5] = b1.y; be[k][6] = b1.z; be[k][7] = b1.w;
+  }
+  pdl_prologue();
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * N;
+  float v[K][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + 256 * k + 8 * lane);
+    const uint32_t* pu = &u.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16(pu[j]);
+      v[k][2 * j] = f.x;
+      v[k][2 * j + 1] = f.y;
+      s += f.x + f.y;
+    }
+  }
+  const float mu = warp_sum(s) * (1.f / N);
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[k][j] - mu;
+      sq += d * d;
+    }
+  const float rs = rsqrtf(warp_sum(sq) * (1.f / N) + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mu) * rs * ga[k][j] + be[k][j];
+    uint4 u;
+    u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(y + row * N + 256 * k + 8 * lane) = u;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+layernorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy2,
+                         const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, const float* __restrict__ gamma,
+                         __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         long long rows) {
+  constexpr int N = 256 * K;
+  __shared__ float red[4][2][N];  // per warp: [dgamma | dbeta] partials of the CTA's rows
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float ga[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float4* g4 = reinterpret_cast<const float4*>(gamma + 256 * k + 8 * lane);
+    const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1);
+    ga[k][0] = g0.x; ga[k][1] = g0.y; ga[k][2] = g0.z; ga[k][3] = g0.w;
+    ga[k][4] = g1.x; ga[k][5] = g1.y; ga[k][6] = g1.z; ga[k][7] = g1.w;
+  }
+  pdl_prologue();
+  float ag[K][8], ab[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = 0.f;
+  for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[K][8], g[K][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const long long off = row * N + 256 * k + 8 * lane;
+      const uint4 ud = *reinterpret_cast<const uint4*>(dy + off);
+      const uint4 ux = *reinterpret_cast<const uint4*>(x + off);
+      uint4 u2 = make_uint4(0u, 0u, 0u, 0u);
+      if (dy2 != nullptr) u2 = *reinterpret_cast<const uint4*>(dy2 + off);
+      const uint32_t* pd = &ud.x;
+      const uint32_t* px = &ux.x;
+      const uint32_t* p2 = &u2.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fd = unpack_bf16(pd[j]), fx = unpack_bf16(px[j]), f2 = unpack_bf16(p2[j]);
+        const float d0 = fd.x + f2.x, d1 = fd.y + f2.y;
+        const float h0 = (fx.x - mu) * rs, h1 = (fx.y - mu) * rs;
+        xh[k][2 * j] = h0; xh[k][2 * j + 1] = h1;
+        g[k][2 * j] = d0 * ga[k][2 * j]; g[k][2 * j + 1] = d1 * ga[k][2 * j + 1];
+        s1 += g[k][2 * j] + g[k][2 * j + 1];
+        s2 += g[k][2 * j] * h0 + g[k][2 * j + 1] * h1;
+        ag[k][2 * j] += d0 * h0; ag[k][2 * j + 1] += d1 * h1;
+        ab[k][2 * j] += d0; ab[k][2 * j + 1] += d1;
+      }
+    }
+    s1 = warp_sum(s1) * (1.f / N);
+    s2 = warp_sum(s2) * (1.f / N);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rs * (g[k][j] - s1 - xh[k][j] * s2);
+      uint4 u;
+      u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + row * N + 256 * k + 8 * lane) = u;
+    }
+  }
+  if (dgamma == nullptr) return;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[warp][0][256 * k + 8 * lane + j] = ag[k][j];
+      red[warp][1][256 * k + 8 * lane + j] = ab[k][j];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+    const int which = i / N, c = i - which * N;
+    float t = 0.f;
+    for (int w = 0; w < wpb; ++w) t += red[w][which][c];
+    atomicAdd((which == 0 ? dgamma : dbeta) + c, t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ L2 normalise
 // y = x / max(||x||, eps) per row (fp32); bwd: dx = (dy - y * (y . dy)) / max(||x||, eps)
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ nrm,
@@ -307,6 +456,21 @@ int toist_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, cons
   TOIST_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "toist_layernorm_fwd: null pointer");
   TOIST_REQUIRE(n >= 1 && n <= 32 * kMaxPerLane, "toist_layernorm_fwd: width %d unsupported (max 1024)", n);
   if (rows == 0) return TOIST_OK;
+  if (x_dtype == TOIST_BF16 && y_bf16 != nullptr && y_f32 == nullptr && n % 256 == 0 && n <= 768 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y_bf16) | reinterpret_cast<uintptr_t>(gamma) |
+        reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    const unsigned g4 = (unsigned)((rows + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LN_FWD_VEC(KK)                                                                                               \
+  launch_pdl((layernorm_fwd_vec_kernel<KK>), dim3(g4), dim3(128), 0, st, (const __nv_bfloat16*)x, gamma, beta,       \
+             (__nv_bfloat16*)y_bf16, mean, rstd, rows, eps)
+    if (n == 256) LN_FWD_VEC(1);
+    else if (n == 512) LN_FWD_VEC(2);
+    else LN_FWD_VEC(3);
+#undef LN_FWD_VEC
+    TOIST_CHECK_CUDA(cudaGetLastError());
+    return TOIST_OK;
+  }
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (x_dtype == TOIST_F32)
     launch_pdl((layernorm_fwd_kernel<float>), dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)x, gamma, beta,
@@ -326,10 +490,26 @@ int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const
   TOIST_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "toist_layernorm_bwd: pass both dgamma and dbeta or neither");
   TOIST_REQUIRE(n >= 1 && n <= 32 * kMaxPerLane, "toist_layernorm_bwd: width %d unsupported (max 1024)", n);
   if (rows == 0) return TOIST_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == TOIST_BF16 && dy_dtype == TOIST_BF16 && dx_dtype == TOIST_BF16 && n % 256 == 0 && n <= 768 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) |
+        reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(gamma)) & 15) == 0) {
+    unsigned g4 = (unsigned)((rows + 3) / 4);
+    if (g4 > 592) g4 = 592;  // 4 CTAs of 4 warps per SM; each warp then walks rows with its column sums in registers
+#define LN_BWD_VEC(KK)                                                                                               \
+  launch_pdl((layernorm_bwd_vec_kernel<KK>), dim3(g4), dim3(128), 0, st, (const __nv_bfloat16*)dy,                   \
+             (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, dgamma,      \
+             dbeta, rows)
+    if (n == 256) LN_BWD_VEC(1);
+    else if (n == 512) LN_BWD_VEC(2);
+    else LN_BWD_VEC(3);
+#undef LN_BWD_VEC
+    TOIST_CHECK_CUDA(cudaGetLastError());
+    return TOIST_OK;
+  }
   unsigned grid = (unsigned)((rows + 7) / 8);
   if (grid > 296) grid = 296;
   const size_t smem = 2 * (size_t)n * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
 #define LN_BWD(TX, TDY, TDX)                                                                                      \
   launch_pdl((layernorm_bwd_kernel<TX, TDY, TDX>), dim3(grid), dim3(256), smem, st, (const TDY*)dy, (const TDY*)dy2, (const TX*)x, mean, \
                                                               rstd, gamma, (TDX*)dx, dgamma, dbeta, rows, n)

@@ -311,6 +311,31 @@ def _criterion_bwd(c: Call, saved, needs, gout, *unused):
 CRITERION = Spec("criterion", 9, _criterion_fwd, _criterion_bwd, nondiff=(1, 2))
 
 
+class _LossTerms(torch.autograd.Function):
+    """out [5, L] -> its 5 * L scalars as separate 0-dim tensors (the reference's loss dict holds one tensor per term
+    and layer, engine.py:70-76 sums them with their weights).  Indexing `out[row, l]` thirty times would hand autograd
+    thirty SelectBackward nodes, each materialising a zero [5, L] tensor that is then accumulated pairwise (~90 tiny
+    launches in front of the backward pass); here the thirty incoming scalar gradients are gathered by ONE stack."""
+
+    @staticmethod
+    def forward(ctx, out):
+        ctx.shape = out.shape
+        return tuple(out.detach().reshape(-1).unbind(0))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ref = next(g for g in grads if g is not None)
+        zero = None
+        cols = []
+        for g in grads:
+            if g is None:
+                if zero is None:
+                    zero = torch.zeros((), dtype=ref.dtype, device=ref.device)
+                g = zero
+            cols.append(g.reshape(()))
+        return torch.stack(cols).view(ctx.shape)
+
+
 def _mask_loss_fwd(c: Call, pred_masks, tgt_masks, match_q, tgt_count, num_boxes):
     """loss_masks (models/mdetr.py:827-853): matched predictions, bilinear upsample to the padded target size,
     sigmoid focal + dice, fused in one pass; returns [loss_mask, loss_dice]."""
@@ -496,18 +521,19 @@ class SetCriterion(nn.Module):
             mcall = Call(self._stage_mask, {}, msave, graphs=self._graphs)
             mask_out = run_stage(MASKLOSS, mcall, pm_, tgt_masks, match_q[L - 1].contiguous(), packed.count, nb)[0]
         losses = {}
+        cells = _LossTerms.apply(out) if out.requires_grad else tuple(out.reshape(-1).unbind(0))
         for name, row in terms:
             if name == "loss_contrastive_align" and mask_out is not None:
                 losses[prefix + "loss_mask"], losses[prefix + "loss_dice"] = mask_out[0], mask_out[1]
                 mask_out = None
-            v = out[row, L - 1]
+            v = cells[row * L + L - 1]
             losses[prefix + name] = v.detach() if row >= 3 else v
         if mask_out is not None:
             losses[prefix + "loss_mask"], losses[prefix + "loss_dice"] = mask_out[0], mask_out[1]
         if use_aux:
             for i in range(L - 1):
                 for name, row in terms:
-                    v = out[row, i]
+                    v = cells[row * L + i]
                     losses[f"{prefix}{name}_{i}"] = v.detach() if row >= 3 else v
         return losses, (st, match_q, packed, flags)
 
