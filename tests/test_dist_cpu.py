@@ -65,3 +65,22 @@ def test_two_rank_gloo_host_logic():
         assert nb0 == 1.0
         assert not same_shard
     assert res[1][4] is None  # the reference arm does no work on rank != 0
+
+
+def test_memory_cache_survives_ddp_argument_mapping():
+    """DistributedDataParallel maps every (nested) dict among the forward arguments through `type(obj)(items)`
+    (torch/distributed/utils.py:_recursive_to).  `memory_cache` is such an argument in phase B (engine.py:66) and
+    carries the tokenizer output: it must come out with its caption lengths intact (char_to_token feeds the
+    contrastive-alignment loss, models/mdetr.py:614-645)."""
+    import torch
+    from torch.distributed.utils import _to_kwargs
+
+    from toist_b200.tokenizer import CharTokenizer
+
+    tok = CharTokenizer()(["open something", "cut"])
+    mc = {"tokenized": tok, "mask": torch.zeros(2, 4, dtype=torch.bool), "nested": {"t": tok}}
+    _, kw = _to_kwargs((), {"memory_cache": mc, "encode_and_save": False}, torch.device("cpu"), False)
+    out = kw[0]["memory_cache"]
+    for t in (out["tokenized"], out["nested"]["t"]):
+        assert t.char_to_token(0, 3) == 4 and t.char_to_token(1, 2) == 3 and t.char_to_token(1, 3) is None
+        assert torch.equal(t["input_ids"], tok["input_ids"]) and torch.equal(t.attention_mask, tok.attention_mask)

@@ -35,14 +35,6 @@ constexpr int kAttNP = 4;  // depth of the P ring (forward)
 constexpr int kFwdThreads = 320;
 constexpr int kAttMaxKB = 7;
 
-__device__ __forceinline__ uint32_t hash32(uint32_t x) {
-  x ^= x >> 16;
-  x *= 0x7feb352dU;
-  x ^= x >> 15;
-  x *= 0x846ca68bU;
-  x ^= x >> 16;
-  return x;
-}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

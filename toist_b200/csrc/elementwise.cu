@@ -106,24 +106,58 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 
 // ------------------------------------------------------------------------------------------------ stem im2col
 // images fp32 NCHW [N,3,H,W] -> patches bf16 [N*Ho*Wo, ldk] for the 7x7/2 pad-3 stem conv; column = (ky*7+kx)*3+c.
-__global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W,
-                                   int Ho, int Wo, int ldk) {
-  pdl_prologue();
-  const long long pix = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (pix >= (long long)N * Ho * Wo) return;
-  const int ox = (int)(pix % Wo);
-  const int oy = (int)((pix / Wo) % Ho);
-  const int n = (int)(pix / ((long long)Wo * Ho));
-  __nv_bfloat16* o = out + pix * ldk;
-  for (int col = lane; col < ldk; col += 32) {
-    float v = 0.f;
+// One CTA per strip of 64 output pixels of one output row: the 7 input rows x 133 input columns x 3 channels the strip
+// touches are staged in shared memory with coalesced fp32 reads (converted to bf16 once), then every thread assembles
+// 16-byte chunks (8 patch columns) of the output rows from a column -> shared-offset table and stores them coalesced.
+constexpr int kStemStrip = 64;
+constexpr int kStemCols = 2 * kStemStrip + 5;  // input columns touched by a strip (stride 2, 7 taps)
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W, int Ho, int Wo,
+                   int ldk) {
+  __shared__ __nv_bfloat16 tile[3 * 7 * (kStemCols + 3)];
+  __shared__ short lut[256];
+  constexpr int kPitch = kStemCols + 3;
+  const int strips = (Wo + kStemStrip - 1) / kStemStrip;
+  int t = blockIdx.x;
+  const int sx = t % strips;
+  t /= strips;
+  const int oy = t % Ho;
+  const int n = t / Ho;
+  const int ox0 = sx * kStemStrip;
+  for (int col = threadIdx.x; col < ldk && col < 256; col += blockDim.x) {
+    short off = -1;
     if (col < 147) {
       const int c = col % 3, kx = (col / 3) % 7, ky = col / 21;
-      const int iy = oy * 2 + ky - 3, ix = ox * 2 + kx - 3;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((long long)n * 3 + c) * H + iy) * W + ix];
+      off = (short)((c * 7 + ky) * kPitch + kx);
     }
-    o[col] = __float2bfloat16_rn(v);
+    lut[col] = off;
+  }
+  pdl_prologue();
+  const int ix0 = ox0 * 2 - 3, iy0 = oy * 2 - 3;
+  for (int i = threadIdx.x; i < 21 * kStemCols; i += blockDim.x) {
+    const int r = i / kStemCols, dx = i - r * kStemCols;  // r = c * 7 + ky
+    const int c = r / 7, ky = r - c * 7;
+    const int iy = iy0 + ky, ix = ix0 + dx;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((long long)n * 3 + c) * H + iy) * W + ix);
+    tile[r * kPitch + dx] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int chunks = ldk >> 3;
+  const int npx = min(kStemStrip, Wo - ox0);
+  __nv_bfloat16* obase = out + (((long long)n * Ho + oy) * Wo + ox0) * ldk;
+  const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+  for (int i = threadIdx.x; i < npx * chunks; i += blockDim.x) {
+    const int px = i / chunks, ch = i - px * chunks;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const short o0 = lut[ch * 8 + 2 * j], o1 = lut[ch * 8 + 2 * j + 1];
+      const uint32_t lo = o0 >= 0 ? tl[o0 + 2 * px] : 0u;
+      const uint32_t hi = o1 >= 0 ? tl[o1 + 2 * px] : 0u;
+      w[j] = lo | (hi << 16);
+    }
+    *reinterpret_cast<uint4*>(obase + (long long)px * ldk + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -341,6 +375,33 @@ __global__ void dropout_kernel(const T* __restrict__ x, const T* __restrict__ re
   if constexpr (sizeof(T) == 2) out[i] = __float2bfloat16_rn(v); else out[i] = v;
 }
 
+// bf16, 16-byte aligned, n % 8 == 0: 8 elements and 4 hashes per thread, 16-byte loads and stores
+__global__ void dropout_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                        __nv_bfloat16* __restrict__ out, long long n8,
+                                        const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thr,
+                                        float scale) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint64_t key = dropout_key(seed, site);
+  const uint32_t thr16 = thr >> 16;
+  const uint4 ux = *reinterpret_cast<const uint4*>(x + i * 8);
+  uint4 ur = make_uint4(0u, 0u, 0u, 0u);
+  if (res != nullptr) ur = *reinterpret_cast<const uint4*>(res + i * 8);
+  const uint32_t* px = &ux.x;
+  const uint32_t* pr = &ur.x;
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w = dropout_word((uint64_t)i * 4 + j, key);
+    const float2 f = unpack_bf16(px[j]), r = unpack_bf16(pr[j]);
+    const float a = ((w & 0xffffu) >= thr16 ? f.x * scale : 0.f) + r.x;
+    const float b = ((w >> 16) >= thr16 ? f.y * scale : 0.f) + r.y;
+    o[j] = pack_bf16(a, b);
+  }
+  *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // dst[a, c, b] = src[a, b, c]  (fp32) — conv weight gradients come out of the WGRAD engine as [Cout][taps][Cin]
 __global__ void permute_021_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int B, int C) {
   pdl_prologue();
@@ -426,8 +487,11 @@ int toist_stem_im2col(const float* images, void* patches, int32_t n, int32_t h, 
   TOIST_REQUIRE(images && patches && ldk >= 147 && ldk % 8 == 0, "toist_stem_im2col: bad arguments");
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
   const long long pix = (long long)n * ho * wo;
-  launch_pdl(stem_im2col_kernel, dim3(nblk(pix, 8)), dim3(256), 0, (cudaStream_t)stream, images, (__nv_bfloat16*)patches, n, h, w, ho, wo,
-                                                                     ldk);
+  TOIST_REQUIRE(ldk <= 256, "toist_stem_im2col: ldk %d too wide", ldk);
+  (void)pix;
+  const long long blocks = (long long)n * ho * ((wo + kStemStrip - 1) / kStemStrip);
+  launch_pdl(stem_im2col_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, images,
+             (__nv_bfloat16*)patches, n, h, w, ho, wo, ldk);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -550,7 +614,12 @@ int toist_dropout(const void* x, const void* res, void* out, int64_t n, int32_t 
   if (n == 0) return TOIST_OK;
   const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
   const float scale = 1.f / (1.f - p);
-  if (dtype == TOIST_BF16)
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(out);
+  if (dtype == TOIST_BF16 && n % 8 == 0 && (al & 15) == 0)
+    launch_pdl(dropout_bf16_vec_kernel, dim3(nblk(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream,
+               (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, n / 8,
+               (const unsigned long long*)seed, site, thr, scale);
+  else if (dtype == TOIST_BF16)
     launch_pdl((dropout_kernel<__nv_bfloat16>), dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, n, (const unsigned long long*)seed, site, thr, scale);
   else

@@ -8,6 +8,7 @@ benchmark, the oracle and the golden fixtures use: a caption of n characters yie
 """
 from __future__ import annotations
 
+from collections import UserDict
 from typing import Dict, List, Optional
 
 import torch
@@ -16,16 +17,21 @@ BOS, PAD, EOS = 0, 1, 2
 _CHAR_BASE = 4
 
 
-class TokenBatch(dict):
-    """Minimal BatchEncoding work-alike: mapping of tensors + `.to()`, attribute access and `char_to_token`."""
+class TokenBatch(UserDict):
+    """Minimal BatchEncoding work-alike: mapping of tensors + `.to()`, attribute access and `char_to_token`.
+    A UserDict like transformers.BatchEncoding, NOT a dict subclass: DistributedDataParallel rebuilds every dict it
+    finds among the forward arguments (`type(obj)(items)`), which would drop the caption lengths that `char_to_token`
+    needs when `memory_cache["tokenized"]` travels through the wrapped model (engine.py:66)."""
 
     def __init__(self, data: Dict[str, torch.Tensor], lengths: List[int]):
         super().__init__(data)
         self._lengths = list(lengths)
 
     def __getattr__(self, item):
+        if item == "data":  # UserDict storage, not yet set during construction / unpickling
+            raise AttributeError(item)
         try:
-            return self[item]
+            return self.data[item]
         except KeyError as e:  # pragma: no cover
             raise AttributeError(item) from e
 
