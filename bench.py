@@ -297,7 +297,7 @@ def run_ours(a):
     # include host launch gaps) and neither is a step-level difference (the step overlaps streams).
     peaks = _peaks()
     roof = attn = None
-    if rank == 0:
+    if True:  # every rank runs the instrumented step: it contains the gradient all-reduce and the num_boxes all-reduce
         model.enable_cuda_graphs(False)
         criterion.enable_cuda_graphs(False)
         prof = GemmProfiler()
@@ -307,7 +307,7 @@ def run_ours(a):
         K.set_gemm_profiler(None)
         iso = prof.isolated_times()
         agg = prof.summary(iso)
-        if a.dump_shapes:  # per distinct launch shape: count, algorithmic FLOPs, isolated duration (tools/shape_table.py)
+        if a.dump_shapes and rank == 0:  # per distinct launch shape: count, algorithmic FLOPs, isolated duration (tools/shape_table.py)
             cnt = {}
             for tag, f, sg, _ in prof.rec:
                 if sg is not None:
