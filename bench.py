@@ -224,8 +224,16 @@ def run_ours(a):
         criterion.enable_cuda_graphs(True)
     ddp = None
     if world > 1:
-        # the reference wraps the model exactly like this (main.py:336); gradients are all-reduced in buckets over NCCL
-        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+        # main.py:336 wraps the model in DistributedDataParallel(model, device_ids=[gpu], find_unused_parameters=True).
+        # toist_b200.util.dist.DistributedDataParallel is the drop-in with the same signature: one flat NCCL
+        # all-reduce per backward stage straight on the stage's gradient arena (--torch-ddp runs torch's wrapper, whose
+        # per-parameter hooks, bucket copies, buffer broadcasts and unused-parameter search cost ~14 ms/step of host time)
+        if a.torch_ddp:
+            ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+        else:
+            from toist_b200.util.dist import DistributedDataParallel as FlatDDP
+
+            ddp = FlatDDP(model, device_ids=[local], find_unused_parameters=True)
     net = ddp if ddp is not None else model
 
     images, mask, captions, targets, pm = make_batch(BATCH, SIZE, TOKENS, seed=1234 + rank)
@@ -354,7 +362,9 @@ def run_ours(a):
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": a.dropout,
                        "cuda_graphs": not a.no_graphs,
                        "l2": "320 MB buffer rewritten between steps (> 126 MB L2)",
-                       "parallelism": f"dp{world}" + (" (DDP bucketed NCCL all-reduce)" if world > 1 else "")},
+                       "parallelism": f"dp{world}" + ((" (torch DDP bucketed NCCL all-reduce)" if a.torch_ddp else
+                                                              " (flat NCCL all-reduce per backward stage, side stream)")
+                                                             if world > 1 else "")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * a.steps,
             "gpu_launches_per_step": int(launches), "roofline": roof, "attention_roofline": attn,
             "step_tensor_frac": STEP_FLOPS_PER_IMAGE * BATCH / (ms * 1e-3 / a.steps) / 1e12 / peaks["tf_sustained"],
@@ -373,6 +383,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1, help="transformer dropout (reference default 0.1, main.py:137)")
+    ap.add_argument("--torch-ddp", action="store_true", help="N > 1: wrap with torch's DistributedDataParallel instead of "
+                                                             "toist_b200.util.dist.DistributedDataParallel")
     ap.add_argument("--dump-shapes", default="", help="write one JSON line per distinct tensor-core launch shape")
     ap.add_argument("--no-graphs", action="store_true", help="issue every kernel launch from Python (no CUDA graphs)")
     a = ap.parse_args()

@@ -40,12 +40,25 @@ def _worker(rank: int, world: int, port: int, q):
     img = make_batch(1, 8, 8, seed=1234 + rank)[0]
     gathered = [torch.zeros_like(img) for _ in range(world)]
     dist.all_gather(gathered, img)
+    # flat gradient exchange (util/dist.py): a stage's arena and one gradient living outside of it
+    from toist_b200.util.dist import FlatGradSync
+
+    arena = torch.arange(8, dtype=torch.float32) * (rank + 1)
+    views = (arena[:4].view(2, 2), None, arena[4:8])
+    stray = torch.full((3,), float(rank + 1))
+    sync = FlatGradSync()
+    sync.reduce("stage", arena, views + (stray,))
+    sync.enabled = False
+    untouched = torch.ones(2) * (rank + 1)
+    sync.reduce("stage", untouched, (untouched,))
+    flat_ok = bool(torch.equal(arena, torch.arange(8, dtype=torch.float32) * 1.5) and torch.equal(stray, torch.full((3,), 1.5))
+                   and torch.equal(views[0], arena[:4].view(2, 2)) and torch.equal(untouched, torch.ones(2) * (rank + 1)))
     import argparse
 
     import bench
 
     out = bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=1)) if rank != 0 else "skipped-on-rank0"
-    q.put((rank, float(nb), float(nb0), bool(torch.equal(gathered[0], gathered[1])), out))
+    q.put((rank, float(nb), float(nb0), bool(torch.equal(gathered[0], gathered[1])), out, flat_ok))
     dist.destroy_process_group()
 
 
@@ -60,7 +73,8 @@ def test_two_rank_gloo_host_logic():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, nb, nb0, same_shard, ref in res:
+    for rank, nb, nb0, same_shard, ref, flat_ok in res:
+        assert flat_ok  # averaged in place, views intact, no_sync() leaves gradients alone
         assert nb == 3.5
         assert nb0 == 1.0
         assert not same_shard

@@ -152,6 +152,7 @@ def t4(t: torch.Tensor, dims: Sequence[int], strides: Sequence[int], offset: int
     """A 4-D bf16 view (dim[0] innermost) over `t`'s storage, starting `offset` elements after t.data_ptr()."""
     assert t.dtype == torch.bfloat16, "GEMM operands must be bf16"
     r = Tensor4()
+    r._keep = t  # the profiler's relaunch closures must keep the operand storage alive (see gemm())
     r.ptr = t.data_ptr() + 2 * offset
     for i in range(4):
         r.dim[i] = int(dims[i])
@@ -238,7 +239,7 @@ def gemm(mode: int, a: Tensor4, b: Tensor4, out: torch.Tensor, *, ext: Tuple[int
                tuple(batch), act, d.out_dtype, res is not None, mask is not None, aux is not None, bool(accumulate),
                bool(b_batched), tuple(out_strides))
         dcopy = GemmDesc.from_buffer_copy(d)
-        keep = (out, res, mask, aux, col_scale, col_shift, row_scale)
+        keep = (out, res, mask, aux, col_scale, col_shift, row_scale, getattr(a, "_keep", None), getattr(b, "_keep", None))
 
         def relaunch(dcopy=dcopy, keep=keep):
             _lib.check(_lib.load().toist_gemm(C.byref(dcopy), _stream()))

@@ -44,6 +44,7 @@ class ModelRuntime:
         self.graphs: Optional[GraphCache] = None
         self.graphs_text: Optional[GraphCache] = None
         self.seed: Optional[torch.Tensor] = None  # device int64 [1]: dropout seed of the current step
+        self.grad_sync = None  # set by util.dist.DistributedDataParallel
         self.dirty = True  # parameters may have moved / been reloaded since the shadow bank was built
 
     def __deepcopy__(self, memo):  # the EMA copy (main.py:322) rebuilds its own
@@ -92,8 +93,10 @@ class ModelRuntime:
         # the text stage replays concurrently with the backbone: graphs that may overlap in time must not share a
         # memory pool (a pool is only safe for graphs replayed one after the other)
         graphs = self.graphs_text if (name == "text" and self.text_stream_enabled) else self.graphs
-        return Call(self.stages[name], self.bank.w, save, graphs=graphs, drop_p=drop_p,
-                    seed=self.seed, **kw)
+        c = Call(self.stages[name], self.bank.w, save, graphs=graphs, drop_p=drop_p,
+                 seed=self.seed, **kw)
+        c.grad_sync = self.grad_sync  # util.dist.FlatGradSync when wrapped for data-parallel training, else None
+        return c
 
     def new_step_seed(self, device) -> None:
         """Draws the dropout seed of this step from torch's CPU generator (reproducible under torch.manual_seed)."""

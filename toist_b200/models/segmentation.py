@@ -131,6 +131,7 @@ class DETRsegm(nn.Module):
         mem = memory_cache["img_memory"]
         save = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         call = Call(rt.stage, rt.bank.w, save, graphs=rt.graphs, n_dec_layers=int(hs.shape[0]), seq_len=int(mem.shape[0]))
+        call.grad_sync = getattr(rt, "grad_sync", None)
         pred = run_stage(MASKHEAD, call, hs, mem, memory_cache["_b200_src_proj"], feats[2], feats[1], feats[0],
                          memory_cache["_b200_small_mask"])[0]
         out["pred_masks"] = pred

@@ -353,21 +353,30 @@ class StageFn(torch.autograd.Function):
         numel = sum((_numel(shp) + 63) // 64 * 64 for n, shp in zip(c.stage.names, c.stage.shapes) if n in c.req)
 
         def body(*g):
-            with Bk.zero_arena(numel, dev), K.wgrad_lanes():
-                return spec.bwd(c, saved, needs, *g)
+            with Bk.zero_arena(numel, dev) as arena, K.wgrad_lanes():
+                gi, gr = spec.bwd(c, saved, needs, *g)
+            return gi, gr, arena.buf
 
+        sync = getattr(c, "grad_sync", None)
+        fresh = all(p.grad is None for p in c.stage.params)
         if c.graphs is None:
-            gin, grads = body(*gouts)
+            gin, grads, abuf = body(*gouts)
             pg = _grads_for(c.stage.names, grads, c.stage.shapes)
+            if sync is not None and c.req:
+                sync.reduce(c.stage.name, abuf, pg, blocking=not fresh)
         else:
             key = ("bwd", ctx.fkey, needs, _sig(gouts))
-            gin, grads = c.graphs.run(key, body, gouts)
+            gin, grads, abuf = c.graphs.run(key, body, gouts)
             pg = _grads_for(c.stage.names, grads, c.stage.shapes)
+            # data parallel: one in-place all-reduce of the stage's gradient arena on a side stream (util/dist.py);
+            # with accumulated gradients the copies below must see the reduced values, so that case waits
+            if sync is not None and c.req:
+                sync.reduce(c.stage.name, abuf, pg, blocking=not fresh)
             # The gradient buffers are static memory of the backward graph.  When no parameter holds a gradient yet
             # (the usual zero_grad(set_to_none=True) loop) hand autograd fresh aliases: AccumulateGrad then adopts them
             # without a copy.  With gradients already present (accumulation over several backward passes) the next
             # replay would overwrite what was accumulated, so copies are returned instead.
-            if all(p.grad is None for p in c.stage.params):
+            if fresh:
                 pg = tuple(None if t is None else t.detach() for t in pg)
             else:
                 pg = tuple(None if t is None else t.clone() for t in pg)

@@ -14,3 +14,98 @@ def get_world_size() -> int:
 
 def get_rank() -> int:
     return dist.get_rank() if is_dist_avail_and_initialized() else 0
+
+
+# ------------------------------------------------------------------------------------------------ gradient all-reduce
+import contextlib
+from typing import Optional
+
+import torch
+from torch import nn
+
+
+class FlatGradSync:
+    """Gradient exchange of data-parallel training (reference main.py:336: DistributedDataParallel's bucketed
+    all-reduce).  Every backward stage of the model (heads, decoder, encoder, backbone, text) already writes ALL of its
+    parameter gradients into one flat fp32 arena (blocks.zero_arena) and `param.grad` are views of it, so the exchange
+    is one in-place NCCL all-reduce (average) per stage on a side stream, issued the moment the stage's backward has
+    been queued: it overlaps the backward of the stages that follow, needs no per-parameter hooks, no bucket copies and
+    no autograd-graph traversal.  The calling stream waits for the side stream at the end of the backward pass."""
+
+    def __init__(self, process_group=None):
+        self.group = process_group
+        self.stream: Optional[torch.cuda.Stream] = None
+        self.enabled = True
+        self._pending = False
+        self._outside = {}
+
+    def reduce(self, stage_name: str, flat: torch.Tensor, grads, blocking: bool = False) -> None:
+        if not self.enabled or not is_dist_avail_and_initialized() or get_world_size() == 1:
+            return
+        if not flat.is_cuda:  # host tensors (gloo, used by the CPU tests of this logic): SUM then divide, in line
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            for t in [flat] + [g for g in grads if g is not None and not (lo <= g.data_ptr() < hi)]:
+                dist.all_reduce(t, group=self.group)
+                t /= get_world_size()
+            return
+        cur = torch.cuda.current_stream(flat.device)
+        if self.stream is None or self.stream.device != flat.device:
+            self.stream = torch.cuda.Stream(device=flat.device)
+        # gradients that were not served from the arena (none today) are exchanged one by one; checked once per stage
+        key = (stage_name, flat.data_ptr(), flat.numel())
+        if key not in self._outside:
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+            self._outside[key] = [i for i, t in enumerate(grads) if t is not None and not (lo <= t.data_ptr() < hi)]
+        extra = [grads[i] for i in self._outside[key]]
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            for t in extra:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        if blocking:
+            cur.wait_stream(self.stream)
+        elif not self._pending:
+            self._pending = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._join)
+
+    def _join(self) -> None:
+        self._pending = False
+        if self.stream is not None:
+            torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
+
+
+class DistributedDataParallel(nn.Module):
+    """Drop-in for `torch.nn.parallel.DistributedDataParallel(model, device_ids=[gpu], find_unused_parameters=True)`
+    at reference main.py:336,345 for toist_b200 models: same constructor keywords, `.module`, `no_sync()`, state dict
+    with the `module.` prefix.  Parameters and buffers are broadcast from rank 0 once at construction (as torch's
+    wrapper does); gradients are averaged by FlatGradSync.  Parameters that receive no gradient in a step (RoBERTa's
+    pooler) simply keep `grad = None` on every rank: there is nothing to find or to wait for."""
+
+    def __init__(self, module: nn.Module, device_ids=None, output_device=None, find_unused_parameters: bool = False,
+                 process_group=None, broadcast_buffers: bool = True, **_unused):
+        super().__init__()
+        self.module = module
+        self.process_group = process_group
+        self.grad_sync = FlatGradSync(process_group)
+        inner = getattr(module, "detr", module)  # DETRsegm wraps the detector (models/segmentation.py:29)
+        rt = getattr(inner, "_rt", None)
+        if rt is None or not hasattr(rt, "grad_sync"):
+            raise TypeError("toist_b200.util.dist.DistributedDataParallel wraps toist_b200 models (MDETR / DETRsegm)")
+        rt.grad_sync = self.grad_sync
+        if inner is not module:  # the mask branch is a stage of its own
+            module._rt.grad_sync = self.grad_sync
+        if is_dist_avail_and_initialized() and get_world_size() > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t, src=0, group=process_group)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        prev, self.grad_sync.enabled = self.grad_sync.enabled, False
+        try:
+            yield
+        finally:
+            self.grad_sync.enabled = prev
