@@ -52,11 +52,13 @@ class FlatGradSync:
         if self.stream is None or self.stream.device != flat.device:
             self.stream = torch.cuda.Stream(device=flat.device)
         # gradients that were not served from the arena (none today) are exchanged one by one; checked once per stage
-        key = (stage_name, flat.data_ptr(), flat.numel())
-        if key not in self._outside:
-            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
-            self._outside[key] = [i for i, t in enumerate(grads) if t is not None and not (lo <= t.data_ptr() < hi)]
-        extra = [grads[i] for i in self._outside[key]]
+        extra = []
+        if grads:
+            key = (stage_name, flat.data_ptr(), flat.numel())
+            if key not in self._outside:
+                lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+                self._outside[key] = [i for i, t in enumerate(grads) if t is not None and not (lo <= t.data_ptr() < hi)]
+            extra = [grads[i] for i in self._outside[key]]
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
@@ -92,8 +94,19 @@ class DistributedDataParallel(nn.Module):
         if rt is None or not hasattr(rt, "grad_sync"):
             raise TypeError("toist_b200.util.dist.DistributedDataParallel wraps toist_b200 models (MDETR / DETRsegm)")
         rt.grad_sync = self.grad_sync
+        covered = ()
         if inner is not module:  # the mask branch is a stage of its own
             module._rt.grad_sync = self.grad_sync
+            covered = ("bbox_attention.", "mask_head.")
+        # parameters that no stage owns (query_embed: its gradient comes out of plain torch autograd) are exchanged
+        # one by one from a post-accumulate hook, on the same side stream
+        if rt.stages is None:
+            rt.build(inner)
+        staged = {id(p) for st in rt.stages.values() for p in st.params}
+        self._loose = [(n, p) for n, p in module.named_parameters()
+                       if id(p) not in staged and not n.startswith(covered) and p.requires_grad]
+        for n, p in self._loose:
+            p.register_post_accumulate_grad_hook(lambda q, n=n: self.grad_sync.reduce(n, q.grad, ()))
         if is_dist_avail_and_initialized() and get_world_size() > 1:
             with torch.no_grad():
                 for t in list(module.parameters()) + list(module.buffers()):

@@ -29,7 +29,7 @@ def main():
 
     torch.manual_seed(rank)  # different initial weights per rank: the wrapper must broadcast rank 0's
     model, criterion, _, wd = build_model(make_args("resnet50", dropout=0.0))
-    model.to(dev).train()
+    model.to(dev).eval()  # no dropout anywhere (RoBERTa keeps its own 0.1 in train mode): two passes are comparable
     graphs = os.environ.get("DDP_CHECK_GRAPHS", "1") != "0"
     if graphs:
         model.enable_cuda_graphs(True)
@@ -59,6 +59,7 @@ def main():
         synced = step()
         assert local_g.keys() == synced.keys()
         worst = 0.0
+        devs = []
         for n in sorted(synced):
             parts = [torch.empty_like(local_g[n]) for _ in range(world)]
             dist.all_gather(parts, local_g[n])
@@ -68,7 +69,13 @@ def main():
             assert all(torch.equal(other[0], o) for o in other), f"{n}: ranks disagree after the all-reduce"
             den = float(mean.abs().max())
             if den > 0:
-                worst = max(worst, float((synced[n] - mean).abs().max()) / den)
+                dv = float((synced[n] - mean).abs().max()) / den
+                devs.append((dv, n, float((synced[n] - parts[rank]).abs().max()) / den))
+                worst = max(worst, dv)
+        devs.sort(reverse=True)
+        if rank == 0:
+            print("[ddp_check] largest deviations (vs mean, name, vs own local):", devs[:6], "median", devs[len(devs) // 2][0],
+                  flush=True)
         # the matcher / atomics make two backward passes of the same batch agree to ~1e-3, not bit for bit
         assert worst < 2e-2, worst
         if rank == 0:
