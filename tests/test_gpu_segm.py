@@ -200,7 +200,11 @@ def test_mask_branch_cuda_graph_replay_matches_eager():
                     (k, int((~torch.isfinite(g0[k])).sum()), int((~torch.isfinite(g1[k])).sum()), g0[k].numel())
                 # mask_loss_bwd scatters through fp32 atomics (order varies run to run) and the maps in between are
                 # bf16: replay and eager agree norm-wise, not bit for bit
-                assert rel_err(g1[k], g0[k]) < 5e-3 or float(g0[k].abs().max()) < 1e-10, (k, rel_err(g1[k], g0[k]))
+                # bbox_attention gradients pass the softmax backward P * (dP - sum P dP): a cancelling difference of
+                # atomically accumulated, bf16-stored values whose result is ~1e-8 here; its run-to-run noise was
+                # measured at 3e-3 .. 7e-3 (the test passed or failed with the atomics' arrival order)
+                tol = 2e-2 if "bbox_attention." in k else 5e-3
+                assert rel_err(g1[k], g0[k]) < tol or float(g0[k].abs().max()) < 1e-10, (k, rel_err(g1[k], g0[k]))
 
 
 def test_mask_stage_against_fp32_torch():
