@@ -246,7 +246,7 @@ def run_ours(a):
     flush = torch.empty(80 * 1024 * 1024, dtype=torch.float32, device=dev)  # 320 MB > 126 MB L2
 
     def step(samples, tg, pmap):
-        model.zero_grad(set_to_none=True)
+        model.zero_grad(set_to_none=True)  # (after the H2D copies of e2e_step have been queued: they overlap it)
         mc = net(samples, captions, encode_and_save=True)
         out = net(samples, captions, encode_and_save=False, memory_cache=mc)
         losses = criterion(mc, out, tg, pmap, None)

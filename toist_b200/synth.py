@@ -70,4 +70,6 @@ def make_batch(batch: int, size: int, n_tokens: int, seed: int = 1234, pad: bool
 
 
 def targets_to(targets: List[dict], device) -> List[dict]:
-    return [{k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in t.items()} for t in targets]
+    from .util.misc import h2d  # pinned staging: a pageable copy would drain the stream once per tensor
+
+    return [{k: (h2d(v, device) if isinstance(v, torch.Tensor) else v) for k, v in t.items()} for t in targets]
