@@ -245,12 +245,12 @@ def run_ours(a):
     d_pm = pm.to(dev)
     flush = torch.empty(80 * 1024 * 1024, dtype=torch.float32, device=dev)  # 320 MB > 126 MB L2
 
-    def step(samples, tg, pmap):
-        model.zero_grad(set_to_none=True)  # (after the H2D copies of e2e_step have been queued: they overlap it)
+    def step(samples, tg, pmap):  # the order of engine.py:63-88
         mc = net(samples, captions, encode_and_save=True)
         out = net(samples, captions, encode_and_save=False, memory_cache=mc)
         losses = criterion(mc, out, tg, pmap, None)
         total = sum(losses[k] * weight_dict[k] for k in losses.keys() if k in weight_dict)
+        model.zero_grad(set_to_none=True)  # optimizer.zero_grad() sits right before backward() (engine.py:86-87)
         total.backward()
         return total
 

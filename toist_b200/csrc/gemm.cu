@@ -8,6 +8,8 @@
 // See include/toist_b200.h for the three traversal modes (FWD / DGRAD / WGRAD) and the epilogue contract.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -251,9 +253,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         // in the SWIZZLE_128B layout (16-byte chunk index XOR row % 8), which makes the per-row accesses of the 128
         // epilogue threads bank-conflict free and lets TMA move whole tiles with full-line transactions.
         const bool has_res = p.res != nullptr, has_mask = p.mask != nullptr;
+        // The output tile is written IN PLACE over the residual tile (or over the mask tile when there is no
+        // residual): every thread reads its 64-byte pieces of res / mask before it writes the same addresses of out,
+        // and nobody else touches them.  Staging is therefore max(1, res + mask) tiles, which lets short reductions
+        // run with a 2-deep ring (dispatch_bn) and three CTAs per SM.
         uint8_t* st_out = smem;
-        uint8_t* st_res = smem + BN * 256;
-        uint8_t* st_mask = st_res + (has_res ? BN * 256 : 0);
+        uint8_t* st_res = smem;
+        uint8_t* st_mask = smem + (has_res ? BN * 256 : 0);
         const bool leader = (warp == 2 && lane == 0);
         if (has_res || has_mask) {
           if (leader) {
@@ -626,13 +632,32 @@ static int dispatch_epi(const CUtensorMap* maps, const GemmKParams& kp, dim3 gri
   }
 }
 
+static int short_k_stages() {  // TOIST_GEMM_SHORTK_STAGES: ring depth for reductions of <= 4 k-blocks (A/B knob, 0 = off)
+  static const int v = []() {
+    const char* e = getenv("TOIST_GEMM_SHORTK_STAGES");
+    return e ? atoi(e) : 2;
+  }();
+  return v;
+}
+
 template <int MODE>
-static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 grid, cudaStream_t stream) {
-  // ring depth: 2 CTAs per SM for BN <= 128 (one tile's epilogue overlaps the other's main loop)
+static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 grid, cudaStream_t stream, int k_iters) {
+  // ring depth: 2 CTAs per SM for BN <= 128 (one tile's epilogue overlaps the other's main loop).  A reduction of at
+  // most 4 k-blocks (the 1x1 convolutions with Cin <= 256, the attention projections) never has more than 4 stages in
+  // flight anyway and is bound by the latency chain of one short-lived CTA (prologue -> loads -> 4 MMAs -> residual
+  // tile -> epilogue -> store): a 2-deep ring halves the shared memory per CTA so that twice as many CTAs are resident
+  // and overlap each other's chains.
+  int sk = short_k_stages();
+  const bool short_k = sk > 0 && k_iters <= 4;
+  if (short_k && kp.epi == 0) {  // the bf16 epilogue stages [res = out | mask] tiles of BN * 256 bytes in the idle ring
+    const int stage_bytes = kABytes + bn * 128;
+    const int staging = bn * 256 * std::max(1, (kp.res != nullptr ? 1 : 0) + (kp.mask != nullptr ? 1 : 0));
+    sk = std::max(sk, (staging + stage_bytes - 1) / stage_bytes);
+  }
   switch (bn) {
-    case 256: kp.stages = 4; return dispatch_epi<256, MODE>(maps, kp, grid, stream);
-    case 128: kp.stages = 3; return dispatch_epi<128, MODE>(maps, kp, grid, stream);
-    default:  kp.stages = 4; return dispatch_epi<64, MODE>(maps, kp, grid, stream);
+    case 256: kp.stages = short_k ? std::min(sk, 4) : 4; return dispatch_epi<256, MODE>(maps, kp, grid, stream);
+    case 128: kp.stages = short_k ? std::min(sk, 3) : 3; return dispatch_epi<128, MODE>(maps, kp, grid, stream);
+    default:  kp.stages = short_k ? std::min(sk, 4) : 4; return dispatch_epi<64, MODE>(maps, kp, grid, stream);
   }
 }
 
@@ -755,8 +780,8 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
                                   d->mode == TOIST_GEMM_FWD ? bbox_fwd : bbox_dg, ones)) != TOIST_OK)
       return rc;
     dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, 1);
-    if (d->mode == TOIST_GEMM_FWD) return dispatch_bn<TOIST_GEMM_FWD>(bn, maps, kp, grid, stream);
-    return dispatch_bn<TOIST_GEMM_DGRAD>(bn, maps, kp, grid, stream);
+    if (d->mode == TOIST_GEMM_FWD) return dispatch_bn<TOIST_GEMM_FWD>(bn, maps, kp, grid, stream, (int)k_iters);
+    return dispatch_bn<TOIST_GEMM_DGRAD>(bn, maps, kp, grid, stream, (int)k_iters);
   }
   TOIST_REQUIRE(tile_rows == kBK, "toist_gemm: WGRAD pixel tile must hold 64 rows (got %d)", tile_rows);
   TOIST_REQUIRE(d->m_rows >= 1, "toist_gemm: WGRAD needs m_rows");
@@ -785,5 +810,5 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
     }
   }
   dim3 grid((unsigned)m_tiles, (unsigned)(n_tiles * d->n_taps), (unsigned)(kp.batch_y * kp.batch_n * kp.splits));
-  return dispatch_bn<TOIST_GEMM_WGRAD>(bn, maps, kp, grid, stream);
+  return dispatch_bn<TOIST_GEMM_WGRAD>(bn, maps, kp, grid, stream, 1 << 20);
 }
