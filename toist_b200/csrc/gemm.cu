@@ -47,6 +47,7 @@ struct GemmKParams {
   int vec_ok;   // 1: every row base and column tile is 16-byte aligned for all epilogue pointers
   int stages;   // depth of the TMA -> MMA shared-memory ring
   int epi;      // epilogue flavour (template parameter EPI of the kernel)
+  int cluster;  // 2: CTA pairs share the B tile by TMA multicast (template parameter CL)
   toist_tap taps[TOIST_MAX_TAPS];
 };
 
@@ -62,7 +63,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 //      2 = generic direct path (any dtype, aux output, every activation, unaligned shapes)
 // One epilogue per instantiation keeps the SASS small: the tiles are short-lived and instruction fetch of a
 // 100+ KB kernel showed up as the second largest stall reason (profiles/r01_ncu_gemm_notes.md).
-template <int BN, int MODE, int EPI>
+// CL = 2: the two CTAs of a cluster compute neighbouring M tiles of the same N tile; each loads its own A tile and
+// HALF of the shared B tile, multicast to both (the B = weight traffic from L2 per SM halves: the layer3 convolutions
+// are bound by the ~50 B/clk an SM can pull from L2, two thirds of which was B).
+template <int BN, int MODE, int EPI, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
@@ -125,7 +129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // every CTA that received the stage's multicast B releases it
     }
     mbar_init(accum_bar, 1);
     mbar_init(epi_bar, 1);
@@ -137,8 +141,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync();  // the peer's barriers exist before anything is multicast to or signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t cl_rank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
   pdl_wait();  // barrier init, descriptor prefetch and the TMEM allocation above overlap the previous kernel's tail
 
   if (warp == 0) {
@@ -159,7 +166,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                       i0 + tp.dn);
           const int cy = p.b_batched ? y0 : 0;
           const int cn = p.b_batched ? i0 : 0;
-          if constexpr (MODE == TOIST_GEMM_FWD) {
+          if constexpr (CL > 1) {  // this CTA fetches 1/CL of the B tile for the whole cluster
+            if constexpr (MODE == TOIST_GEMM_FWD) {
+              constexpr int kRows = BN / CL;  // tma_b's box holds BN / CL rows
+              tma_load_4d_mc(sb + cl_rank * kRows * 128, &tma_b, &full_bar[stage], tp.col + kb * kBK,
+                             n0 + (int)cl_rank * kRows, cy, cn, kClMask);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64 / CL; ++j) {
+                const int jj = (int)cl_rank * (BN / 64 / CL) + j;
+                tma_load_4d_mc(sb + jj * 8192, &tma_b, &full_bar[stage], tp.col + n0 + jj * 64, kb * kBK, cy, cn, kClMask);
+              }
+            }
+          } else if constexpr (MODE == TOIST_GEMM_FWD) {
             tma_load_4d(sb, &tma_b, &full_bar[stage], tp.col + kb * kBK, n0, cy, cn);
           } else {
 #pragma unroll
@@ -205,7 +224,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint64_t db = kBMN ? umma_smem_desc(sb + ks * 2048, 8192, 1024) : umma_smem_desc(sb + ks * 32, 16, 1024);
           umma_f16(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);                 // frees the smem stage once these MMAs retire
+        if constexpr (CL > 1) umma_commit_mc(&empty_bar[stage], kClMask);  // ... in every CTA that fills it
+        else umma_commit(&empty_bar[stage]);            // frees the smem stage once these MMAs retire
         if (it == n_iters - 1) umma_commit(accum_bar);  // accumulator complete
       }
       __syncwarp();
@@ -598,20 +618,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
   }
+  if constexpr (CL > 1) cluster_sync();  // the peer may still signal this CTA's empty barriers: keep the smem alive
 }
 
-template <int BN, int MODE, int EPI>
+template <int BN, int MODE, int EPI, int CL = 1>
 static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
   constexpr int kMaxStages = (BN == 128) ? 3 : 4;
   constexpr int max_smem = kMaxStages * (kABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
   const int smem = kp.stages * (kABytes + BN * 128) + 1024 + 256;
   static bool configured = false;
-  auto kfn = gemm_kernel<BN, MODE, EPI>;
+  auto kfn = gemm_kernel<BN, MODE, EPI, CL>;
   if (!configured) {
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
-  launch_pdl(kfn, dim3(grid), dim3(kThreads), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  if constexpr (CL > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = CL;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    TOIST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, maps[0], maps[1], maps[2], maps[3], maps[4], kp));
+  } else {
+    launch_pdl(kfn, dim3(grid), dim3(kThreads), smem, stream, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+  }
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }
@@ -624,6 +663,9 @@ static int dispatch_epi(const CUtensorMap* maps, const GemmKParams& kp, dim3 gri
     if (kp.epi == 1) return launch_gemm<BN, MODE, 1>(maps, kp, grid, stream);
     return launch_gemm<BN, MODE, 2>(maps, kp, grid, stream);
   } else {
+    if constexpr (BN >= 128) {
+      if (kp.epi == 0 && kp.cluster == 2) return launch_gemm<BN, MODE, 0, 2>(maps, kp, grid, stream);
+    }
     switch (kp.epi) {
       case 0: return launch_gemm<BN, MODE, 0>(maps, kp, grid, stream);
       case 1: return launch_gemm<BN, MODE, 1>(maps, kp, grid, stream);
@@ -662,6 +704,14 @@ static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 gr
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static bool cluster_enabled() {  // TOIST_GEMM_CLUSTER=0 disables the CTA-pair / multicast variant (A/B runs)
+  static const bool on = []() {
+    const char* e = getenv("TOIST_GEMM_CLUSTER");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return on;
+}
 
 static bool reduce_epilogue_enabled() {  // TOIST_GEMM_ATOMIC_WGRAD=1 selects the scattered-atomics epilogue (A/B runs)
   static const bool on = []() {
@@ -774,7 +824,9 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
                         (uint32_t)d->tile_n};
     uint32_t aes[4] = {1, (uint32_t)d->stride_x, (uint32_t)d->stride_y, 1};
     if ((rc = encode_tmap_bf16_4d(&ma, d->a.ptr, d->a.dim, d->a.stride, abox, aes)) != TOIST_OK) return rc;
-    uint32_t bbox_fwd[4] = {64, (uint32_t)bn, 1, 1};
+    // CTA pairs with a multicast B tile for the long, L2-feed-bound reductions (see gemm_kernel)
+    kp.cluster = (cluster_enabled() && kp.epi == 0 && !d->b_batched && bn >= 128 && m_tiles % 2 == 0 && k_iters >= 8) ? 2 : 1;
+    uint32_t bbox_fwd[4] = {64, (uint32_t)(bn / kp.cluster), 1, 1};
     uint32_t bbox_dg[4] = {64, 64, 1, 1};
     if ((rc = encode_tmap_bf16_4d(&mb, d->b.ptr, d->b.dim, d->b.stride,
                                   d->mode == TOIST_GEMM_FWD ? bbox_fwd : bbox_dg, ones)) != TOIST_OK)
