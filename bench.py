@@ -305,7 +305,7 @@ def run_ours(a):
     # include host launch gaps) and neither is a step-level difference (the step overlaps streams).
     peaks = _peaks()
     roof = attn = None
-    if True:  # every rank runs the instrumented step: it contains the gradient all-reduce and the num_boxes all-reduce
+    if not a.no_roofline:  # every rank runs the instrumented step: it contains the gradient all-reduce and the num_boxes all-reduce
         model.enable_cuda_graphs(False)
         criterion.enable_cuda_graphs(False)
         prof = GemmProfiler()
@@ -346,6 +346,50 @@ def run_ours(a):
                     "frac": f / t / 1e12 / peaks["tf_sustained"], "flops_per_step": f, "seconds_per_step": t,
                     "launches": n, "method": "same isolated-replay timing, attention-core launches only"}
 
+    # ---- optimizer side of the step, reported separately (BASELINE metric: "optimizer/EMA reported separately"):
+    # clip_grad_norm_(0.1) + AdamW over the three parameter groups of main.py:351-392 + update_ema (engine.py:89-107)
+    optim = None
+    if not a.no_optimizer:
+        import copy
+
+        from toist_b200.util import optim as FO
+
+        def groups():
+            named = list(model.named_parameters())
+            return [{"params": [p for n, p in named if "backbone" not in n and "text_encoder" not in n and p.requires_grad]},
+                    {"params": [p for n, p in named if "backbone" in n and p.requires_grad], "lr": 1e-5},
+                    {"params": [p for n, p in named if "text_encoder" in n and p.requires_grad], "lr": 5e-5}]
+
+        model.enable_cuda_graphs(True)
+        criterion.enable_cuda_graphs(True)
+        step(d_samples, d_targets, d_pm)  # fresh gradients
+        ema = copy.deepcopy(model)
+        params = [p for p in model.parameters()]
+
+        def ours_opt(o):
+            FO.clip_grad_norm_(params, 0.1)
+            o.step()
+            FO.update_ema(model, ema, 0.9998)
+
+        def torch_opt(o):
+            torch.nn.utils.clip_grad_norm_(params, 0.1)
+            o.step()
+            with torch.no_grad():  # util/optim.py:9-26 as written
+                msd = model.state_dict()
+                for k, ema_v in ema.state_dict().items():
+                    ema_v.copy_(ema_v * 0.9998 + (1.0 - 0.9998) * msd[k].detach())
+
+        res = {}
+        for name, fn, o in (("ours", ours_opt, FO.FusedAdamW(groups(), lr=1e-4, weight_decay=1e-4)),
+                            ("torch", torch_opt, torch.optim.AdamW(groups(), lr=1e-4, weight_decay=1e-4))):
+            fn(o)
+            fn(o)
+            res[name] = timed(lambda: fn(o), 5) / 5
+        n_par = sum(p.numel() for p in params if p.grad is not None)
+        optim = {"ms": res["ours"], "torch_ms": res["torch"], "what": "clip_grad_norm_(0.1) + AdamW (3 groups) + update_ema, "
+                 "toist_b200.util.optim vs torch.optim.AdamW + the reference's update_ema loop",
+                 "params_with_grad": n_par, "hbm_gbs": (n_par * 40 + sum(p.numel() for p in params) * 12) / (res["ours"] * 1e-3) / 1e9}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -368,7 +412,7 @@ def run_ours(a):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * a.steps,
             "gpu_launches_per_step": int(launches), "roofline": roof, "attention_roofline": attn,
             "step_tensor_frac": STEP_FLOPS_PER_IMAGE * BATCH / (ms * 1e-3 / a.steps) / 1e12 / peaks["tf_sustained"],
-            "cpu_baseline": cpu,
+            "optimizer": optim, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -385,6 +429,8 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.1, help="transformer dropout (reference default 0.1, main.py:137)")
     ap.add_argument("--torch-ddp", action="store_true", help="N > 1: wrap with torch's DistributedDataParallel instead of "
                                                              "toist_b200.util.dist.DistributedDataParallel")
+    ap.add_argument("--no-optimizer", action="store_true", help="skip the separate optimizer-side measurement")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-launch roofline pass (quick A/B runs)")
     ap.add_argument("--dump-shapes", default="", help="write one JSON line per distinct tensor-core launch shape")
     ap.add_argument("--no-graphs", action="store_true", help="issue every kernel launch from Python (no CUDA graphs)")
     a = ap.parse_args()

@@ -375,6 +375,27 @@ int toist_mse_rows(const float* a, const float* b, const uint8_t* use, float* lo
 /* out [n, m] = torch.cdist(a [n, dim], b [m, dim], p=1)   (mdetr.py:98) */
 int toist_cdist_l1(const float* a, const float* b, float* out, int32_t n, int32_t m, int32_t dim, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer side of the step (csrc/optim.cu), multi-tensor: `items` is a DEVICE array of 48-byte records
+ *   { float* a; float* b; float* c; float* d; int64_t n; int32_t first_block; int32_t group; }
+ * (toist_sizeof_opt_item()), first_block = running sum of ceil(n / 2048) over the preceding records, total_blocks the
+ * sum over all of them.  All tensors are contiguous f32.
+ *   toist_grad_sqnorm      a = grad.  partial: f32 [total_blocks] scratch.  norm_and_coef[0] = L2 norm over all items,
+ *                          [1] = min(1, max_norm / (norm + 1e-6))   -- torch.nn.utils.clip_grad_norm_ (engine.py:89-90)
+ *   toist_grad_clip_scale  a = grad, scaled in place by norm_and_coef[1]
+ *   toist_adamw_step       a = param, b = grad, c = exp_avg, d = exp_avg_sq, group = parameter group; hyper (HOST) holds 8
+ *                          floats per group {lr, beta1, beta2, eps, weight_decay, lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t), 0}
+ *                          -- torch.optim.AdamW.step (main.py:351-392, engine.py:91)
+ *   toist_ema_update       a = ema tensor, b = model tensor: a = a * decay + (1 - decay) * b  (util/optim.py:9-26) */
+size_t toist_sizeof_opt_item(void);
+int toist_grad_sqnorm(const void* items_dev, int32_t n_items, int32_t total_blocks, float* partial, float max_norm,
+                      float* norm_and_coef, void* stream);
+int toist_grad_clip_scale(const void* items_dev, int32_t n_items, int32_t total_blocks, const float* norm_and_coef,
+                          void* stream);
+int toist_adamw_step(const void* items_dev, int32_t n_items, int32_t total_blocks, const float* hyper_host,
+                     int32_t n_groups, void* stream);
+int toist_ema_update(const void* items_dev, int32_t n_items, int32_t total_blocks, float decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,3 +161,33 @@ def test_lsap_restatement_matches_scipy():
         O.lsap(np.array([[np.nan, 0.0]]))
     with pytest.raises(ValueError):
         O.lsap(np.full((2, 2), np.inf))
+
+
+def test_lr_schedule_matches_reference():
+    """toist_b200.util.optim.adjust_learning_rate against the reference's util/optim.py:29-90 for all four schedules."""
+    import argparse
+    import importlib.util
+    import random
+
+    from toist_b200.util import optim as ours
+
+    spec = importlib.util.spec_from_file_location("_ref_optim", "/root/reference/util/optim.py")
+    refmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refmod)
+
+    class Opt:
+        def __init__(self):
+            self.param_groups = [{"lr": 0.0}, {"lr": 0.0}, {"lr": 0.0}]
+
+    rng = random.Random(0)
+    for schedule in ("step", "multistep", "linear_with_warmup", "all_linear_with_warmup"):
+        for _ in range(50):
+            a = argparse.Namespace(fraction_warmup_steps=rng.choice([0.0, 0.01, 0.1]), schedule=schedule,
+                                   lr_drop=rng.choice([5, 10, 35]), epochs=rng.choice([30, 120, 200]), lr=1e-4,
+                                   lr_backbone=1e-5, text_encoder_lr=5e-5)
+            total = rng.choice([1, 100, 12345])
+            epoch, step = rng.randrange(0, a.epochs), rng.randrange(0, total + 1)
+            o1, o2 = Opt(), Opt()
+            refmod.adjust_learning_rate(o1, epoch, step, total, a)
+            ours.adjust_learning_rate(o2, epoch, step, total, a)
+            assert o1.param_groups == o2.param_groups, (schedule, epoch, step, total)

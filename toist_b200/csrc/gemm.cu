@@ -690,7 +690,11 @@ static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 gr
   // tile -> epilogue -> store): a 2-deep ring halves the shared memory per CTA so that twice as many CTAs are resident
   // and overlap each other's chains.
   int sk = short_k_stages();
-  const bool short_k = sk > 0 && k_iters <= 4;
+  static const int short_max = []() {  // TOIST_GEMM_SHORTK_MAX: longest reduction (k-blocks) given the shallow ring
+    const char* e = getenv("TOIST_GEMM_SHORTK_MAX");
+    return e ? atoi(e) : 4;
+  }();
+  const bool short_k = sk > 0 && k_iters <= short_max;
   if (short_k && kp.epi == 0) {  // the bf16 epilogue stages [res = out | mask] tiles of BN * 256 bytes in the idle ring
     const int stage_bytes = kABytes + bn * 128;
     const int staging = bn * 256 * std::max(1, (kp.res != nullptr ? 1 : 0) + (kp.mask != nullptr ? 1 : 0));
@@ -778,7 +782,7 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   const int cands[3] = {256, 128, 64};
   static const int min_ctas = []() {  // tuning knob: smallest grid for which a wider column tile is preferred
     const char* e = getenv("TOIST_GEMM_MIN_CTAS");
-    return e ? atoi(e) : 96;
+    return e ? atoi(e) : 160;  // measured on the bench step: 96 -> 9.55, 130 -> 9.47, 160 -> 9.32, 210 -> 9.83 ms
   }();
   // short reductions are epilogue bound: keep two CTAs per SM (BN <= 128) so epilogues overlap main loops
   const int64_t k_iters = (d->mode == TOIST_GEMM_WGRAD) ? 1 << 20 : (int64_t)ceil_div(d->k_per_tap, kBK) * d->n_taps;

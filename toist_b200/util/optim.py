@@ -1,0 +1,196 @@
+"""Optimizer side of the training step on the multi-tensor kernels of csrc/optim.cu.
+
+Drop-ins, same call signatures as what the reference uses:
+  * `FusedAdamW(param_dicts, lr=..., weight_decay=...)`   for `torch.optim.AdamW` (main.py:351-392), one launch per step
+  * `clip_grad_norm_(parameters, max_norm)`               for `torch.nn.utils.clip_grad_norm_` (engine.py:89-90), three launches
+  * `update_ema(model, model_ema, decay)`                 for util/optim.py:9-26, one launch
+  * `adjust_learning_rate(optimizer, epoch, curr_step, num_training_steps, args)`  util/optim.py:29-90 (host arithmetic)
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from bisect import bisect_right
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .misc import h2d
+
+_CHUNK = 2048
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Table:
+    """Device array of OptItem records for a fixed list of tensor tuples; rebuilt only when a pointer changes (the
+    gradient arenas of the CUDA-graph backward are static, parameters and optimizer state never move)."""
+
+    def __init__(self):
+        self.key = None
+        self.dev = None
+        self.blocks = 0
+        self.n = 0
+
+    def get(self, cols: Sequence[Sequence[Optional[torch.Tensor]]], groups: Optional[Sequence[int]] = None):
+        """cols: up to four parallel lists (a, b, c, d) of contiguous fp32 CUDA tensors of equal numel per row."""
+        ptrs = [[0 if t is None else t.data_ptr() for t in col] for col in cols]
+        numel = [t.numel() for t in cols[0]]
+        key = (tuple(map(tuple, ptrs)), tuple(numel), None if groups is None else tuple(groups))
+        if key != self.key:
+            n = len(numel)
+            rec = np.zeros((n, 6), dtype=np.int64)
+            for j, col in enumerate(ptrs):
+                rec[:, j] = col
+            rec[:, 4] = numel
+            blocks = 0
+            for i, ne in enumerate(numel):
+                g = 0 if groups is None else int(groups[i])
+                rec[i, 5] = blocks | (g << 32)  # {int32 first_block, int32 group}, little endian
+                blocks += -(-ne // _CHUNK)
+            for col in cols:
+                for t in col:
+                    if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                        raise RuntimeError("toist_b200.util.optim works on contiguous fp32 CUDA tensors (no CPU path)")
+            assert _lib.load().toist_sizeof_opt_item() == 48
+            self.dev = h2d(torch.from_numpy(rec.view(np.uint8).reshape(-1)), cols[0][0].device)
+            self.key, self.blocks, self.n = key, blocks, n
+        return self.dev, self.n, self.blocks
+
+
+_clip_tables = {}
+
+
+def clip_grad_norm_(parameters, max_norm: float, norm_type: float = 2.0) -> torch.Tensor:
+    """Clips the global L2 norm of the gradients in place; returns the total norm (a 0-dim CUDA tensor, no host sync)."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    if float(norm_type) != 2.0:
+        raise NotImplementedError("only the L2 norm the reference uses (engine.py:90) is implemented")
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return torch.zeros(())
+    key = id(grads[0].device), len(grads)
+    tab = _clip_tables.setdefault(key, (_Table(), {}))
+    items, n, blocks = tab[0].get([grads])
+    dev = grads[0].device
+    scratch = tab[1].get(blocks)
+    if scratch is None:
+        scratch = tab[1][blocks] = (torch.empty(blocks, dtype=torch.float32, device=dev),)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    L = _lib.load()
+    _lib.check(L.toist_grad_sqnorm(items.data_ptr(), n, blocks, scratch[0].data_ptr(), float(max_norm), out.data_ptr(),
+                                   _stream()))
+    _lib.check(L.toist_grad_clip_scale(items.data_ptr(), n, blocks, out.data_ptr(), _stream()))
+    return out[0]
+
+
+_ema_tables = {}
+
+
+def update_ema(model, model_ema, decay: float) -> None:
+    """w_ema = w_ema * decay + (1 - decay) * w for every floating-point entry of the state dict (util/optim.py:9-26);
+    integer buffers are copied."""
+    with torch.no_grad():
+        if hasattr(model, "module"):
+            model = model.module
+        key = (id(model), id(model_ema))
+        ent = _ema_tables.get(key)
+        if ent is None:
+            msd = model.state_dict()
+            pairs, copies = [], []
+            for k, ema_v in model_ema.state_dict().items():
+                mv = msd[k].detach()
+                if ema_v.dtype == torch.float32 and mv.dtype == torch.float32 and ema_v.is_contiguous() and mv.is_contiguous():
+                    pairs.append((ema_v, mv))
+                else:
+                    copies.append((ema_v, mv))
+            ent = _ema_tables[key] = (_Table(), pairs, copies)
+        tab, pairs, copies = ent
+        if pairs:
+            items, n, blocks = tab.get([[a for a, _ in pairs], [b for _, b in pairs]])
+            _lib.check(_lib.load().toist_ema_update(items.data_ptr(), n, blocks, float(decay), _stream()))
+        for ema_v, mv in copies:
+            ema_v.copy_(ema_v * decay + (1.0 - decay) * mv)
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction, no amsgrad) with the whole step of all
+    parameter groups in ONE launch.  State (`step`, `exp_avg`, `exp_avg_sq`) uses torch's key names."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        if len(self.param_groups) > 8:
+            raise ValueError("FusedAdamW supports up to 8 parameter groups")
+        self._table = _Table()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        ps, gs, ms, vs, grp = [], [], [], [], []
+        rows = {}  # (group index, step count) -> hyper-parameter row: parameters skipped in some steps lag behind
+        hyper = []
+        for gi, group in enumerate(self.param_groups):
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                t = int(st["step"])
+                row = rows.get((gi, t))
+                if row is None:
+                    row = rows[(gi, t)] = len(hyper)
+                    bc1, bc2 = 1.0 - b1 ** t, 1.0 - b2 ** t
+                    hyper.append((group["lr"], b1, b2, group["eps"], group["weight_decay"], group["lr"] / bc1,
+                                  1.0 / math.sqrt(bc2), 0.0))
+                ps.append(p)
+                gs.append(p.grad)
+                ms.append(st["exp_avg"])
+                vs.append(st["exp_avg_sq"])
+                grp.append(row)
+        if len(hyper) > 8:
+            raise RuntimeError("FusedAdamW: more than 8 distinct (parameter group, step count) combinations in one step")
+        hyper = np.asarray(hyper, dtype=np.float32).reshape(-1, 8)
+        if ps:
+            items, n, blocks = self._table.get([ps, gs, ms, vs], grp)
+            _lib.check(_lib.load().toist_adamw_step(items.data_ptr(), n, blocks, hyper.ctypes.data_as(C.c_void_p),
+                                                    int(hyper.shape[0]), _stream()))
+        return loss
+
+
+def adjust_learning_rate(optimizer, epoch: int, curr_step: int, num_training_steps: int, args) -> None:
+    """The four schedules of util/optim.py:29-90: a decay factor for (transformer, backbone) and one for the text encoder."""
+    warm = round(args.fraction_warmup_steps * num_training_steps)
+
+    def linear():
+        if curr_step < warm:
+            return float(curr_step) / float(max(1, warm))
+        return max(0.0, float(num_training_steps - curr_step) / float(max(1, num_training_steps - warm)))
+
+    if args.schedule == "step":
+        gamma = text_gamma = 0.1 ** (epoch // args.lr_drop)
+    elif args.schedule == "multistep":
+        gamma = text_gamma = 0.5 ** bisect_right(list(range(args.lr_drop, args.epochs, 50)), epoch)
+    elif args.schedule == "linear_with_warmup":
+        gamma, text_gamma = 0.1 ** (epoch // args.lr_drop), linear()
+    elif args.schedule == "all_linear_with_warmup":
+        gamma = text_gamma = linear()
+    else:
+        raise NotImplementedError(args.schedule)
+    base = [args.lr, args.lr_backbone, args.text_encoder_lr]
+    assert len(optimizer.param_groups) == len(base)
+    for group, lr, g in zip(optimizer.param_groups, base, [gamma, gamma, text_gamma]):
+        group["lr"] = lr * g
