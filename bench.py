@@ -214,6 +214,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints "NCCL version ..." on STDOUT at debug level VERSION: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     args = make_args("resnet101", device="cuda", dropout=a.dropout)
     torch.manual_seed(0)

@@ -384,9 +384,10 @@ int toist_cdist_l1(const float* a, const float* b, float* out, int32_t n, int32_
  *                          [1] = min(1, max_norm / (norm + 1e-6))   -- torch.nn.utils.clip_grad_norm_ (engine.py:89-90)
  *   toist_grad_clip_scale  a = grad, scaled in place by norm_and_coef[1]
  *   toist_adamw_step       a = param, b = grad, c = exp_avg, d = exp_avg_sq, group = parameter group; hyper (HOST) holds 8
- *                          floats per group {lr, beta1, beta2, eps, weight_decay, lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t), 0}
+ *                          floats per group {1 - lr * wd, 1 - beta1, beta2, 1 - beta2, eps, lr / (1 - beta1^t), sqrt(1 - beta2^t), 0},
+ *                          each formed in double precision as torch's Python code does and rounded once
  *                          -- torch.optim.AdamW.step (main.py:351-392, engine.py:91)
- *   toist_ema_update       a = ema tensor, b = model tensor: a = a * decay + (1 - decay) * b  (util/optim.py:9-26) */
+ *   toist_ema_update       a = ema tensor, b = model tensor: a = a * decay + one_minus_decay * b  (util/optim.py:9-26) */
 size_t toist_sizeof_opt_item(void);
 int toist_grad_sqnorm(const void* items_dev, int32_t n_items, int32_t total_blocks, float* partial, float max_norm,
                       float* norm_and_coef, void* stream);
@@ -394,7 +395,8 @@ int toist_grad_clip_scale(const void* items_dev, int32_t n_items, int32_t total_
                           void* stream);
 int toist_adamw_step(const void* items_dev, int32_t n_items, int32_t total_blocks, const float* hyper_host,
                      int32_t n_groups, void* stream);
-int toist_ema_update(const void* items_dev, int32_t n_items, int32_t total_blocks, float decay, void* stream);
+int toist_ema_update(const void* items_dev, int32_t n_items, int32_t total_blocks, float decay, float one_minus_decay,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -96,8 +96,17 @@ __global__ void __launch_bounds__(256) grad_scale_kernel(const OptItem* __restri
   }
 }
 
+// Scalars are prepared on the host in double precision exactly as torch's Python code forms them (1 - beta2 evaluated
+// in fp32 is off by 5e-5 relative, which shows in exp_avg_sq), then rounded to fp32 once.
 struct AdamHyper {
-  float lr, beta1, beta2, eps, weight_decay, step_size, inv_bc2_sqrt, pad;
+  float decay;        // 1 - lr * weight_decay
+  float omb1;         // 1 - beta1
+  float beta2;
+  float omb2;         // 1 - beta2
+  float eps;
+  float step_size;    // lr / (1 - beta1^t)
+  float bc2_sqrt;     // sqrt(1 - beta2^t)
+  float pad;
 };
 struct AdamGroups {
   AdamHyper g[8];
@@ -105,10 +114,10 @@ struct AdamGroups {
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamHyper& h) {
   // torch.optim.AdamW (_single_tensor_adamw): decoupled decay, lerp, mul + addcmul, sqrt / bias correction + eps, addcdiv
-  p *= 1.f - h.lr * h.weight_decay;
-  m += (g - m) * (1.f - h.beta1);
-  v = v * h.beta2 + (1.f - h.beta2) * g * g;
-  const float denom = sqrtf(v) * h.inv_bc2_sqrt + h.eps;
+  p *= h.decay;
+  m += (g - m) * h.omb1;
+  v = v * h.beta2 + h.omb2 * g * g;
+  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
   p -= h.step_size * (m / denom);
 }
 
@@ -141,11 +150,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const OptItem* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(256) ema_kernel(const OptItem* __restrict__ items, int n_items, float decay) {
+__global__ void __launch_bounds__(256) ema_kernel(const OptItem* __restrict__ items, int n_items, float decay,
+                                                  float w) {
   pdl_prologue();
   const OptItem it = find_item(items, n_items, blockIdx.x);
   const long long i = (long long)(blockIdx.x - it.first_block) * kOptChunk + (long long)threadIdx.x * 8;
-  const float w = 1.f - decay;
   const uintptr_t al = reinterpret_cast<uintptr_t>(it.a) | reinterpret_cast<uintptr_t>(it.b);
   if (i + 8 <= it.n && (al & 15) == 0) {
 #pragma unroll
@@ -188,7 +197,7 @@ int toist_grad_clip_scale(const void* items_dev, int32_t n_items, int32_t total_
   return TOIST_OK;
 }
 
-// hyper: n_groups x 8 floats {lr, beta1, beta2, eps, weight_decay, lr / bias_correction1, 1 / sqrt(bias_correction2), 0}
+// hyper: n_groups x 8 floats {1 - lr * wd, 1 - beta1, beta2, 1 - beta2, eps, lr / (1 - beta1^t), sqrt(1 - beta2^t), 0}
 int toist_adamw_step(const void* items_dev, int32_t n_items, int32_t total_blocks, const float* hyper_host,
                      int32_t n_groups, void* stream) {
   TOIST_REQUIRE(items_dev && hyper_host && n_items > 0 && total_blocks > 0, "toist_adamw_step: bad arguments");
@@ -201,10 +210,11 @@ int toist_adamw_step(const void* items_dev, int32_t n_items, int32_t total_block
   return TOIST_OK;
 }
 
-int toist_ema_update(const void* items_dev, int32_t n_items, int32_t total_blocks, float decay, void* stream) {
+int toist_ema_update(const void* items_dev, int32_t n_items, int32_t total_blocks, float decay, float one_minus_decay,
+                     void* stream) {
   TOIST_REQUIRE(items_dev && n_items > 0 && total_blocks > 0, "toist_ema_update: bad arguments");
   TOIST_CHECK_CUDA(launch_pdl(ema_kernel, dim3(total_blocks), dim3(256), 0, (cudaStream_t)stream,
-                              reinterpret_cast<const OptItem*>(items_dev), n_items, decay));
+                              reinterpret_cast<const OptItem*>(items_dev), n_items, decay, one_minus_decay));
   return TOIST_OK;
 }
 

@@ -114,7 +114,7 @@ def update_ema(model, model_ema, decay: float) -> None:
         tab, pairs, copies = ent
         if pairs:
             items, n, blocks = tab.get([[a for a, _ in pairs], [b for _, b in pairs]])
-            _lib.check(_lib.load().toist_ema_update(items.data_ptr(), n, blocks, float(decay), _stream()))
+            _lib.check(_lib.load().toist_ema_update(items.data_ptr(), n, blocks, float(decay), 1.0 - float(decay), _stream()))
         for ema_v, mv in copies:
             ema_v.copy_(ema_v * decay + (1.0 - decay) * mv)
 
@@ -154,8 +154,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 if row is None:
                     row = rows[(gi, t)] = len(hyper)
                     bc1, bc2 = 1.0 - b1 ** t, 1.0 - b2 ** t
-                    hyper.append((group["lr"], b1, b2, group["eps"], group["weight_decay"], group["lr"] / bc1,
-                                  1.0 / math.sqrt(bc2), 0.0))
+                    hyper.append((1.0 - group["lr"] * group["weight_decay"], 1.0 - b1, b2, 1.0 - b2, group["eps"],
+                                  group["lr"] / bc1, math.sqrt(bc2), 0.0))
                 ps.append(p)
                 gs.append(p.grad)
                 ms.append(st["exp_avg"])
