@@ -211,3 +211,32 @@ def test_no_cpu_fallback_in_product_path():
         model(NestedTensor(images, mask), captions, encode_and_save=True)
     with pytest.raises(RuntimeError):
         criterion({}, {"pred_logits": torch.zeros(1, 100, 256), "pred_boxes": torch.zeros(1, 100, 4)}, targets, pm, None)
+
+
+def test_loss_terms_node_matches_indexing():
+    """The criterion hands out its [5, L] loss tensor as 5 * L scalars through one autograd node (models/mdetr.py
+    _LossTerms): values and the gradient of any weighted sum must equal plain `out[row, l]` indexing, including unused
+    and detached entries (cardinality / contrastive rows are logging-only in the reference)."""
+    from toist_b200.models.mdetr import _LossTerms
+
+    torch.manual_seed(0)
+    out = torch.randn(5, 6, requires_grad=True)
+    w = torch.rand(5, 6)
+    ref = torch.randn(5, 6).detach().copy_(out.detach()).requires_grad_(True)
+    cells = _LossTerms.apply(out)
+    assert len(cells) == 30 and all(c.dim() == 0 for c in cells)
+    used = [(r, l) for r in range(3) for l in range(6) if (r + l) % 4 != 0]
+    total = sum(cells[r * 6 + l] * float(w[r, l]) for r, l in used) + cells[3 * 6 + 2].detach() * 7.0
+    total_ref = sum(ref[r, l] * float(w[r, l]) for r, l in used) + ref[3, 2].detach() * 7.0
+    assert torch.allclose(total, total_ref, rtol=1e-6, atol=1e-6)
+    total.backward()
+    total_ref.backward()
+    assert torch.allclose(out.grad, ref.grad, rtol=0, atol=1e-7)
+
+
+def test_h2d_keeps_values_and_is_a_no_op_without_cuda():
+    from toist_b200.util.misc import h2d
+
+    t = torch.arange(12, dtype=torch.int64).view(3, 4)
+    assert torch.equal(h2d(t, "cpu"), t)
+    assert h2d(t, "cpu", torch.float32).dtype == torch.float32

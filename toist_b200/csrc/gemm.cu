@@ -786,10 +786,14 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   }();
   // short reductions are epilogue bound: keep two CTAs per SM (BN <= 128) so epilogues overlap main loops
   const int64_t k_iters = (d->mode == TOIST_GEMM_WGRAD) ? 1 << 20 : (int64_t)ceil_div(d->k_per_tap, kBK) * d->n_taps;
+  static const int bn256_min_k = []() {  // TOIST_GEMM_BN256_MINK: shortest reduction (k-blocks) that may use 256-wide tiles
+    const char* e = getenv("TOIST_GEMM_BN256_MINK");
+    return e ? atoi(e) : 8;
+  }();
   for (int c = 0; c < 3; ++c) {
     const int cand = cands[c];
     if (cand > 64 && d->n_cols <= cand / 2) continue;  // more than half the tile would be padding
-    if (cand == 256 && k_iters < 8) continue;
+    if (cand == 256 && k_iters < bn256_min_k) continue;
     const int64_t ctas = m_tiles * ceil_div(d->n_cols, cand) * z_mult;
     if (ctas >= min_ctas || cand == 64) {
       bn = cand;

@@ -282,9 +282,12 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, mask: Optional[torch.Tens
     return out
 
 
+_WGRAD_CTAS = int(os.environ.get("TOIST_WGRAD_CTAS", "296"))  # split-K target: CTAs per weight-gradient launch
+
+
 def _wgrad_splits(m_rows: int, n_cols: int, n_taps: int, pixel_tiles: int, batch: int = 1) -> int:
     base = -(-m_rows // 128) * -(-n_cols // 128) * n_taps * batch
-    want = max(1, 296 // max(base, 1))
+    want = max(1, _WGRAD_CTAS // max(base, 1))
     return max(1, min(want, pixel_tiles // 4 if pixel_tiles >= 8 else 1))
 
 
