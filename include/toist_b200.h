@@ -240,7 +240,9 @@ int toist_attn_softmax_bwd(const float* dprobs, const void* probs, void* dscores
  * q, k, v, out, dout, dq, dk, dv are bf16 with element (s, b, head * d + i) at ptr[s * ss + b * sb + head * d + i]
  * (ss, sb in elements, multiples of 8; bases 16-byte aligned): the reference's [S, B, E] layout, or column slices of
  * a packed projection.  key_mask: uint8 [b, sk], non-zero = key ignored (key_padding_mask), may be null.
- * lse: f32 [b, h, sq] row log-sum-exp, written by the forward when non-null and required by the backward.
+ * lse: f32 [b, h, sq, 2] row statistics (m2, l): the row maximum of the scaled scores in the log2 domain and the softmax
+ * denominator sum_k exp2(s_k * scale * log2(e) - m2); written by the forward when non-null, required by the backward
+ * (natural log-sum-exp = m2 * ln 2 + ln l; kept apart because their sum loses the softmax for very large logits).
  * Dropout (p_drop > 0): decisions are a hash of (seed[0], site, row, key pair) regenerated in the backward;
  * p is quantised to round(p * 65536) / 65536.  Supported: d in {32, 64}, sk <= 448 (toist_attention_supported). */
 typedef struct toist_attn_desc {

@@ -77,7 +77,10 @@ def test_fused_attention_matches_fp32_torch(sq, sk, b, h, d, p_drop):
     # row log-sum-exp
     att = (heads(q, sq, b, h, d) @ heads(k, sk, b, h, d).transpose(-1, -2)) * d ** -0.5
     att = att.masked_fill(km.bool()[:, None, None, :], float("-inf"))
-    assert rel_err(saved.lse, torch.logsumexp(att, -1)) < 1e-4
+    import math
+
+    assert saved.lse.shape == (b, h, sq, 2)  # (row maximum in the log2 domain, softmax denominator)
+    assert rel_err(saved.lse[..., 0] * math.log(2.0) + saved.lse[..., 1].log(), torch.logsumexp(att, -1)) < 1e-4
     dctx = torch.randn(sq, b, e, device=DEV).to(BF)
     ref.backward(dctx.float())
     dqk = torch.full((max(sq, sk), b, 2 * e), float("nan"), device=DEV, dtype=BF)
@@ -128,3 +131,26 @@ def test_unsupported_shapes_use_the_unfused_path():
     assert not isinstance(saved, K.FusedAttnSaved)
     ref, _ = reference(q, k, v, None, h)
     assert rel_err(ctx.float(), ref) < 5e-3
+
+
+def test_fused_attention_backward_is_finite_for_huge_logits():
+    """Random-initialised ResNet-101 features reach 1e5, the first encoder layer's logits 1e10 (one ulp = 1e3): the
+    softmax is then one-hot, the reference's gradients w.r.t. q and k vanish and w.r.t. v route dO to the winning key.
+    The flash-style recompute must not turn rounding differences of such numbers into inf / NaN."""
+    from toist_b200 import kernels as K
+
+    torch.manual_seed(5)
+    sq, sk, b, h, d = 416, 416, 1, 8, 32
+    e = h * d
+    q, k = (torch.randn(s, b, e, device=DEV) * 2.0e4).to(BF), (torch.randn(sk, b, e, device=DEV) * 2.0e4).to(BF)
+    v = (torch.randn(sk, b, e, device=DEV) * 1.0e3).to(BF)
+    ctx, saved = K.attention_fwd(q, k, v, None, h, fused=True)
+    assert torch.isfinite(ctx.float()).all()
+    ref, (qr, kr, vr) = reference(q, k, v, None, h)
+    assert rel_err(ctx.float(), ref) < 2e-2
+    dctx = torch.randn(sq, b, e, device=DEV).to(BF)
+    ref.backward(dctx.float())
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    K.attention_bwd(dctx, q, k, v, saved, h, dq, dk, dv)
+    for t in (dq, dk, dv):
+        assert torch.isfinite(t.float()).all()

@@ -16,7 +16,7 @@
 //               reads it again, exponentiates (ex2.approx), applies the dropout decision, sums, packs bf16 and writes
 //               the K-major operand tile for the PV product; the epilogue scales O by keep_scale / l.
 // Backward, one CTA per (128-key tile, head, batch), 320 threads, loop over 128-query chunks:
-//   S^T = K Q^T and dP^T = V dO^T (TMEM) -> 8 compute warps: p = exp(s - lse), dropout decision regenerated,
+//   S^T = K Q^T and dP^T = V dO^T (TMEM) -> 8 compute warps: p = exp2(s * scale - m2) / l, dropout decision regenerated,
 //   Pd^T and dS^T (bf16, K-major in shared memory) -> dV += Pd^T dO, dK += dS^T Q (accumulated in TMEM over the
 //   chunks), dQ_chunk = dS K (TMEM -> fp32 partial per key tile; attn_dq_reduce_kernel sums the key tiles in a fixed
 //   order and writes bf16).  Nothing is atomic: results are deterministic run to run.
@@ -229,8 +229,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float e0 = ex2_approx(__uint_as_float(raw[i]) * p.scale_log2 - m2);
-            float e1 = ex2_approx(__uint_as_float(raw[i + 1]) * p.scale_log2 - m2);
+            // exactly this expression is re-evaluated by the backward pass (same operands, one rounding)
+            float e0 = ex2_approx(__fmaf_rn(__uint_as_float(raw[i]), p.scale_log2, -m2));
+            float e1 = ex2_approx(__fmaf_rn(__uint_as_float(raw[i + 1]), p.scale_log2, -m2));
             if (bits != 0u) {  // warp-uniform
               if ((bits >> i) & 1u) e0 = 0.f;
               if ((bits >> (i + 1)) & 1u) e1 = 0.f;
@@ -296,8 +297,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
+    // Row statistics for the backward pass: (m2, l) = (scaled row maximum in the log2 domain, softmax denominator), kept
+    // as two numbers.  Folding them into one log-sum-exp loses the softmax when |logit| is large: at random
+    // initialisation the first encoder layer sees logits of ~1e10 (ulp 1e3), the backward recomputed exp(s - lse) from
+    // two differently rounded large numbers and produced inf -> NaN gradients for the whole backbone.
     if (hf == 0 && p.lse != nullptr && qrow < p.sq)
-      p.lse[(long long)(b * p.h + h) * p.sq + qrow] = mx * p.scale + logf(l);
+      reinterpret_cast<float2*>(p.lse)[(long long)(b * p.h + h) * p.sq + qrow] = make_float2(m2, l);
   }
 
   tc_fence_before();
@@ -342,9 +347,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sRing = sV + 16384;      // 2 x (Q chunk 16 KB | dO chunk 16 KB)
   uint8_t* sPd = sRing + 65536;     // Pd^T: 2 blocks of [128 keys][64 queries]
   uint8_t* sdS = sPd + 32768;       // dS^T: same layout
-  float* sLse = reinterpret_cast<float*>(sdS + 32768);  // [nq <= 8][128] log2-domain lse (inf past the last query)
+  float* sLse = reinterpret_cast<float*>(sdS + 32768);  // [nq <= 8][128] log2-domain row maximum m2 (inf past the last query)
   float* sDelta = sLse + kBwdMaxNQ * 128;                // [nq][128] rowsum(dO * O)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + kBwdMaxNQ * 128);
+  float* sInvL = sDelta + kBwdMaxNQ * 128;               // [nq][128] 1 / softmax denominator (0 past the last query)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sInvL + kBwdMaxNQ * 128);
   uint64_t* bar_kv = bars + 0;
   uint64_t* full = bars + 1;    // [2]
   uint64_t* empty = bars + 3;   // [2]
@@ -456,11 +462,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t pairs_per_row = (uint32_t)(p.kb * 32);
     const uint32_t rx = (uint32_t)(r & 7);
     const bool warp_keys = key0 + quad * 32 < p.sk;  // warp-uniform: at least one of this warp's 32 keys exists
-    const float LOG2E = 1.4426950408889634f;
-    // delta[q] = sum_d dO[q, d] * O[q, d] and the log2-domain lse of every query of this (b, h), once, straight from
+    // delta[q] = sum_d dO[q, d] * O[q, d] and the softmax statistics of every query of this (b, h), once, straight from
     // global memory: all loads are in flight together and overlap the K / V / Q tile loads and the first products
     for (int qrow = (int)threadIdx.x - 64; qrow < p.nq * 128; qrow += 256) {
-      float dl = 0.f, ls = INFINITY;
+      float dl = 0.f, ls = INFINITY, il = 0.f;
       if (qrow < p.sq) {
         const __nv_bfloat16* orow = p.o + (long long)qrow * p.o_ss + (long long)b * p.o_sb + h * p.d;
         const __nv_bfloat16* drow = p.dout + (long long)qrow * p.do_ss + (long long)b * p.do_sb + h * p.d;
@@ -475,10 +480,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             dl += fd.x * fo.x + fd.y * fo.y;
           }
         }
-        ls = p.lse[(long long)(b * p.h + h) * p.sq + qrow] * LOG2E;
+        const float2 st2 = reinterpret_cast<const float2*>(p.lse)[(long long)(b * p.h + h) * p.sq + qrow];
+        ls = st2.x;
+        il = 1.f / st2.y;
       }
       sDelta[qrow] = dl;
       sLse[qrow] = ls;
+      sInvL[qrow] = il;
     }
     named_barrier_sync(1, 256);
     for (int c = 0; c < p.nq; ++c) {
@@ -512,10 +520,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t hbase = (uint32_t)((b * p.h + h) * p.sq + qc0 + qi0) * pairs_per_row + (uint32_t)(key >> 1) + k0;
         const float4* lse4 = reinterpret_cast<const float4*>(sLse + st * 128 + qi0);
         const float4* del4 = reinterpret_cast<const float4*>(sDelta + st * 128 + qi0);
+        const float4* inv4 = reinterpret_cast<const float4*>(sInvL + st * 128 + qi0);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 ls4 = lse4[i4], dl4 = del4[i4];
+          const float4 ls4 = lse4[i4], dl4 = del4[i4], il4 = inv4[i4];
           const float lsv[4] = {ls4.x, ls4.y, ls4.z, ls4.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+          const float ilv[4] = {il4.x, il4.y, il4.z, il4.w};
 #pragma unroll
           for (int i2 = 0; i2 < 2; ++i2) {
             const int i = i4 * 4 + i2 * 2;
@@ -527,8 +537,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               keep0 = ((lane & 1) ? (w0 >> 16) : (w0 & 0xffffu)) >= p.thr16;
               keep1 = ((lane & 1) ? (w1 >> 16) : (w1 & 0xffffu)) >= p.thr16;
             }
-            float pr0 = ex2_approx(__uint_as_float(st_raw[i]) * p.scale_log2 - lsv[i2 * 2]);
-            float pr1 = ex2_approx(__uint_as_float(st_raw[i + 1]) * p.scale_log2 - lsv[i2 * 2 + 1]);
+            // p = e / l with e exactly as the forward formed it; a probability never exceeds 1 (the clamp only acts
+            // if S^T and S differ in the last bit at logit magnitudes where one ulp is worth many octaves)
+            float pr0 = fminf(ex2_approx(__fmaf_rn(__uint_as_float(st_raw[i]), p.scale_log2, -lsv[i2 * 2])) * ilv[i2 * 2], 1.f);
+            float pr1 = fminf(ex2_approx(__fmaf_rn(__uint_as_float(st_raw[i + 1]), p.scale_log2, -lsv[i2 * 2 + 1])) *
+                                  ilv[i2 * 2 + 1], 1.f);
             if (!key_ok) pr0 = pr1 = 0.f;
             const float dp0 = keep0 ? __uint_as_float(dp_raw[i]) * p.keep_scale : 0.f;
             const float dp1 = keep1 ? __uint_as_float(dp_raw[i + 1]) * p.keep_scale : 0.f;
@@ -803,7 +816,7 @@ extern "C" int toist_attention_bwd(const toist_attn_bwd_desc* a, void* stream_v)
   if ((rc = make_qkv_map(&mk, f->k, f->d, f->sk, f->h, f->b, f->k_ss, f->k_sb, 128)) != TOIST_OK) return rc;
   if ((rc = make_qkv_map(&mv, f->v, f->d, f->sk, f->h, f->b, f->v_ss, f->v_sb, 128)) != TOIST_OK) return rc;
   if ((rc = make_qkv_map(&mdo, a->dout, f->d, f->sq, f->h, f->b, a->do_ss, a->do_sb, 128)) != TOIST_OK) return rc;
-  const int smem = 32768 + 65536 + 65536 + 2 * kBwdMaxNQ * 512 + 8 * 8 + 16 + 1024;
+  const int smem = 32768 + 65536 + 65536 + 3 * kBwdMaxNQ * 512 + 8 * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

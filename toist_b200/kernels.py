@@ -660,8 +660,8 @@ FUSED_ATTENTION = os.environ.get("TOIST_FUSED_ATTN", "1") != "0"
 
 
 class FusedAttnSaved:
-    """What the fused forward keeps for its backward: the output, the row log-sum-exp and the key mask (the scores and
-    probabilities never leave the SM)."""
+    """What the fused forward keeps for its backward: the output, the row statistics `lse` = (log2-domain row maximum,
+    softmax denominator) and the key mask (the scores and probabilities never leave the SM)."""
     __slots__ = ("ctx", "lse", "key_mask")
 
     def __init__(self, ctx, lse, key_mask):
@@ -698,7 +698,7 @@ def attention_fused_fwd(q, k, v, key_mask_u8, nhead: int, ctx: Optional[torch.Te
     sk = k.shape[0]
     if ctx is None:
         ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=q.device)
-    lse = torch.empty((b, nhead, sq), dtype=torch.float32, device=q.device) if need_lse else None
+    lse = torch.empty((b, nhead, sq, 2), dtype=torch.float32, device=q.device) if need_lse else None  # (m2, l) per row
     a = _attn_desc(q, k, v, ctx, lse, key_mask_u8, nhead, drop)
     keep = (q, k, v, ctx, lse, key_mask_u8, drop)
 
