@@ -47,7 +47,7 @@ struct GemmKParams {
   int vec_ok;   // 1: every row base and column tile is 16-byte aligned for all epilogue pointers
   int stages;   // depth of the TMA -> MMA shared-memory ring
   int epi;      // epilogue flavour (template parameter EPI of the kernel)
-  int cluster;  // 2: CTA pairs share the B tile by TMA multicast (template parameter CL)
+  int cluster;  // 2: CTA pairs share the B tile by TMA multicast (PAIR 1); 3: cta_group::2 MMA over the pair (PAIR 2)
   toist_tap taps[TOIST_MAX_TAPS];
 };
 
@@ -66,13 +66,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // CL = 2: the two CTAs of a cluster compute neighbouring M tiles of the same N tile; each loads its own A tile and
 // HALF of the shared B tile, multicast to both (the B = weight traffic from L2 per SM halves: the layer3 convolutions
 // are bound by the ~50 B/clk an SM can pull from L2, two thirds of which was B).
-template <int BN, int MODE, int EPI, int CL>
+// PAIR = 2 (EXPERIMENTAL, TOIST_GEMM_2SM=1, written at the end of round 1 and not yet run on a GPU): the CTA pair issues
+// ONE tcgen05.mma.cta_group::2 per k-step over a 256 x BN tile; each CTA stages its own 128 A rows and only BN / 2 rows of
+// B, so an SM ingests 32 KB instead of 48 KB per 512 MMA clocks (BN = 256) - the measured bound of the layer3 convolutions.
+template <int BN, int MODE, int EPI, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
             const __grid_constant__ CUtensorMap tma_mask, const __grid_constant__ GemmKParams p) {
+  constexpr int CL = PAIR ? 2 : 1;          // CTAs per cluster
+  constexpr bool kTwoSm = (PAIR == 2);      // cta_group::2 MMA (PAIR == 1: independent MMAs, multicast B)
   const int STAGES = p.stages;
-  constexpr int kBBytes = BN * 128;
+  constexpr int kBBytes = (kTwoSm ? BN / 2 : BN) * 128;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr bool kAMN = (MODE == TOIST_GEMM_WGRAD);
   constexpr bool kBMN = (MODE != TOIST_GEMM_FWD);
@@ -124,20 +129,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int n_iters = it_end - it_begin;
 
   // ---------------- one-time setup
+  if constexpr (kTwoSm) cluster_sync();  // both CTAs of the pair are resident before the paired TMEM allocation
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);  // every CTA that received the stage's multicast B releases it
+      // PAIR 2: the leader's full barrier collects its own expect_tx arrival and the peer's "loads issued" arrival
+      mbar_init(&full_bar[s], kTwoSm ? 2 : 1);
+      // PAIR 1: every CTA that received the stage's multicast B releases it; PAIR 2: one multicast commit of the leader
+      mbar_init(&empty_bar[s], PAIR == 1 ? 2 : 1);
     }
     mbar_init(accum_bar, 1);
     mbar_init(epi_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
-    tmem_relinquish();
+    if constexpr (kTwoSm) {
+      tmem_alloc_2sm(tmem_slot, BN);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -157,8 +170,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStageBytes;
         uint8_t* sb = sa + kABytes;
-        mbar_expect_tx(&full_bar[stage], kStageBytes);
-        if constexpr (MODE != TOIST_GEMM_WGRAD) {
+        if constexpr (kTwoSm) {
+          if (cl_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);  // both CTAs' pieces land on this barrier
+        } else {
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+        }
+        if constexpr (kTwoSm) {
+          // every load completes on the LEADER's full barrier; this CTA stages its A rows and its half of B
+          const int t = it / p.kblocks;
+          const int kb = it - t * p.kblocks;
+          const toist_tap tp = p.taps[t];
+          tma_load_4d_2sm(sa, &tma_a, &full_bar[stage], kb * kBK, x0 * p.stride_x + tp.dx, y0 * p.stride_y + tp.dy,
+                          i0 + tp.dn);
+          if constexpr (MODE == TOIST_GEMM_FWD) {
+            tma_load_4d_2sm(sb, &tma_b, &full_bar[stage], tp.col + kb * kBK, n0 + (int)cl_rank * (BN / 2), 0, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_4d_2sm(sb + j * 8192, &tma_b, &full_bar[stage], tp.col + n0 + ((int)cl_rank * (BN / 128) + j) * 64,
+                              kb * kBK, 0, 0);
+          }
+          if (cl_rank != 0) mbar_arrive_leader(&full_bar[stage]);
+        } else if constexpr (MODE != TOIST_GEMM_WGRAD) {
           const int t = it / p.kblocks;
           const int kb = it - t * p.kblocks;
           const toist_tap tp = p.taps[t];
@@ -208,11 +241,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    constexpr uint32_t idesc = umma_idesc_bf16(BN, kAMN, kBMN);
+    // ======================= MMA issuer (PAIR 2: the leader CTA issues for both) =======================
+    constexpr uint32_t idesc = umma_idesc_bf16(BN, kAMN, kBMN, kTwoSm ? 256 : 128);
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < n_iters; ++it) {
+    const int mma_iters = (kTwoSm && cl_rank != 0) ? 0 : n_iters;
+    for (int it = 0; it < mma_iters; ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
@@ -222,11 +256,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         for (int ks = 0; ks < kBK / 16; ++ks) {
           const uint64_t da = kAMN ? umma_smem_desc(sa + ks * 2048, 8192, 1024) : umma_smem_desc(sa + ks * 32, 16, 1024);
           const uint64_t db = kBMN ? umma_smem_desc(sb + ks * 2048, 8192, 1024) : umma_smem_desc(sb + ks * 32, 16, 1024);
-          umma_f16(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          if constexpr (kTwoSm) umma_f16_2sm(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          else umma_f16(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
-        if constexpr (CL > 1) umma_commit_mc(&empty_bar[stage], kClMask);  // ... in every CTA that fills it
-        else umma_commit(&empty_bar[stage]);            // frees the smem stage once these MMAs retire
-        if (it == n_iters - 1) umma_commit(accum_bar);  // accumulator complete
+        if constexpr (kTwoSm) {
+          umma_commit_2sm(&empty_bar[stage], kClMask);                       // frees the stage in both CTAs
+          if (it == n_iters - 1) umma_commit_2sm(accum_bar, kClMask);        // both CTAs' epilogues may start
+        } else {
+          if constexpr (CL > 1) umma_commit_mc(&empty_bar[stage], kClMask);  // ... in every CTA that fills it
+          else umma_commit(&empty_bar[stage]);            // frees the smem stage once these MMAs retire
+          if (it == n_iters - 1) umma_commit(accum_bar);  // accumulator complete
+        }
       }
       __syncwarp();
       if (++stage == STAGES) {
@@ -614,20 +654,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+  if constexpr (kTwoSm) {
+    cluster_sync();  // both CTAs are done with the paired TMEM (and with each other's barriers) before it is freed
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc_2sm(tmem_base, BN);
+    }
+  } else {
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(tmem_base, BN);
+    }
+    if constexpr (CL > 1) cluster_sync();  // the peer may still signal this CTA's empty barriers: keep the smem alive
   }
-  if constexpr (CL > 1) cluster_sync();  // the peer may still signal this CTA's empty barriers: keep the smem alive
 }
 
-template <int BN, int MODE, int EPI, int CL = 1>
+template <int BN, int MODE, int EPI, int PAIR = 0>
 static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
-  constexpr int kMaxStages = (BN == 128) ? 3 : 4;
-  constexpr int max_smem = kMaxStages * (kABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
-  const int smem = kp.stages * (kABytes + BN * 128) + 1024 + 256;
+  constexpr int CL = PAIR ? 2 : 1;
+  constexpr int kStage = kABytes + (PAIR == 2 ? BN / 2 : BN) * 128;
+  constexpr int kMaxStages = PAIR == 2 ? 6 : ((BN == 128) ? 3 : 4);
+  constexpr int max_smem = kMaxStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int smem = kp.stages * kStage + 1024 + 256;
   static bool configured = false;
-  auto kfn = gemm_kernel<BN, MODE, EPI, CL>;
+  auto kfn = gemm_kernel<BN, MODE, EPI, PAIR>;
   if (!configured) {
     TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
@@ -664,7 +714,10 @@ static int dispatch_epi(const CUtensorMap* maps, const GemmKParams& kp, dim3 gri
     return launch_gemm<BN, MODE, 2>(maps, kp, grid, stream);
   } else {
     if constexpr (BN >= 128) {
-      if (kp.epi == 0 && kp.cluster == 2) return launch_gemm<BN, MODE, 0, 2>(maps, kp, grid, stream);
+      if (kp.epi == 0 && kp.cluster == 2) return launch_gemm<BN, MODE, 0, 1>(maps, kp, grid, stream);
+    }
+    if constexpr (BN == 256) {
+      if (kp.epi == 0 && kp.cluster == 3) return launch_gemm<BN, MODE, 0, 2>(maps, kp, grid, stream);
     }
     switch (kp.epi) {
       case 0: return launch_gemm<BN, MODE, 0>(maps, kp, grid, stream);
@@ -700,6 +753,10 @@ static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 gr
     const int staging = bn * 256 * std::max(1, (kp.res != nullptr ? 1 : 0) + (kp.mask != nullptr ? 1 : 0));
     sk = std::max(sk, (staging + stage_bytes - 1) / stage_bytes);
   }
+  if (kp.cluster == 3 && bn == 256) {  // 32 KB stages: six of them, the epilogue needs at most four (res + mask tiles)
+    kp.stages = 6;
+    return dispatch_epi<256, MODE>(maps, kp, grid, stream);
+  }
   switch (bn) {
     case 256: kp.stages = short_k ? std::min(sk, 4) : 4; return dispatch_epi<256, MODE>(maps, kp, grid, stream);
     case 128: kp.stages = short_k ? std::min(sk, 3) : 3; return dispatch_epi<128, MODE>(maps, kp, grid, stream);
@@ -712,6 +769,14 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 static bool cluster_enabled() {  // TOIST_GEMM_CLUSTER=0 disables the CTA-pair / multicast variant (A/B runs)
   static const bool on = []() {
     const char* e = getenv("TOIST_GEMM_CLUSTER");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return on;
+}
+
+static bool two_sm_enabled() {  // TOIST_GEMM_2SM=1: cta_group::2 MMA over CTA pairs (experimental, see gemm_kernel)
+  static const bool on = []() {
+    const char* e = getenv("TOIST_GEMM_2SM");
     return e ? atoi(e) != 0 : false;
   }();
   return on;
@@ -834,12 +899,17 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
     if ((rc = encode_tmap_bf16_4d(&ma, d->a.ptr, d->a.dim, d->a.stride, abox, aes)) != TOIST_OK) return rc;
     // CTA pairs with a multicast B tile for the long, L2-feed-bound reductions (see gemm_kernel)
     kp.cluster = (cluster_enabled() && kp.epi == 0 && !d->b_batched && bn >= 128 && m_tiles % 2 == 0 && k_iters >= 8) ? 2 : 1;
-    uint32_t bbox_fwd[4] = {64, (uint32_t)(bn / kp.cluster), 1, 1};
+    if (two_sm_enabled() && kp.epi == 0 && !d->b_batched && d->n_cols >= 256 && m_tiles % 2 == 0 && k_iters >= 8) {
+      kp.cluster = 3;  // cta_group::2 pairs, always with 256-wide tiles
+      bn = 256;
+      kp.n_tiles = (int)ceil_div(d->n_cols, bn);
+    }
+    uint32_t bbox_fwd[4] = {64, (uint32_t)(kp.cluster > 1 ? bn / 2 : bn), 1, 1};
     uint32_t bbox_dg[4] = {64, 64, 1, 1};
     if ((rc = encode_tmap_bf16_4d(&mb, d->b.ptr, d->b.dim, d->b.stride,
                                   d->mode == TOIST_GEMM_FWD ? bbox_fwd : bbox_dg, ones)) != TOIST_OK)
       return rc;
-    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, 1);
+    dim3 grid((unsigned)m_tiles, (unsigned)kp.n_tiles, 1);
     if (d->mode == TOIST_GEMM_FWD) return dispatch_bn<TOIST_GEMM_FWD>(bn, maps, kp, grid, stream, (int)k_iters);
     return dispatch_bn<TOIST_GEMM_DGRAD>(bn, maps, kp, grid, stream, (int)k_iters);
   }
