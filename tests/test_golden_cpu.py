@@ -240,3 +240,19 @@ def test_h2d_keeps_values_and_is_a_no_op_without_cuda():
     t = torch.arange(12, dtype=torch.int64).view(3, 4)
     assert torch.equal(h2d(t, "cpu"), t)
     assert h2d(t, "cpu", torch.float32).dtype == torch.float32
+
+
+def test_library_contains_tcgen05_and_tma_instructions():
+    """The hot kernels are hand-written sm_100a code: the built library must contain tcgen05.mma (SASS UTCHMMA), TMA loads /
+    stores (UTMALDG / UTMASTG), TMEM loads (LDTM) and mbarrier operations (SYNCS).  Needs cuobjdump (CUDA toolkit)."""
+    import shutil
+    import subprocess
+
+    from toist_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists() or not _lib.lib_path().exists():
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([cuobjdump, "-sass", str(_lib.lib_path())], capture_output=True, text=True, timeout=300).stdout
+    for mnemonic, at_least in (("UTCHMMA", 100), ("UTMALDG", 100), ("UTMASTG", 20), ("LDTM", 20), ("SYNCS", 500)):
+        assert sass.count(mnemonic) >= at_least, (mnemonic, sass.count(mnemonic))
