@@ -256,3 +256,23 @@ def test_library_contains_tcgen05_and_tma_instructions():
     sass = subprocess.run([cuobjdump, "-sass", str(_lib.lib_path())], capture_output=True, text=True, timeout=300).stdout
     for mnemonic, at_least in (("UTCHMMA", 100), ("UTMALDG", 100), ("UTMASTG", 20), ("LDTM", 20), ("SYNCS", 500)):
         assert sass.count(mnemonic) >= at_least, (mnemonic, sass.count(mnemonic))
+
+
+def test_bench_reference_arm_prints_one_valid_json_line():
+    """`bench.py --impl reference` (the oracle port on the host cores, a bounded 2-image sample of the bench workload)
+    must print exactly one JSON line with the contract's keys; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("images/sec") and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
