@@ -1,7 +1,12 @@
 """The two torch.distributed helpers the criterion needs (reference util/dist.py:150-170)."""
 from __future__ import annotations
 
+import contextlib
+from typing import Optional
+
+import torch
 import torch.distributed as dist
+from torch import nn
 
 
 def is_dist_avail_and_initialized() -> bool:
@@ -17,13 +22,6 @@ def get_rank() -> int:
 
 
 # ------------------------------------------------------------------------------------------------ gradient all-reduce
-import contextlib
-from typing import Optional
-
-import torch
-from torch import nn
-
-
 class FlatGradSync:
     """Gradient exchange of data-parallel training (reference main.py:336: DistributedDataParallel's bucketed
     all-reduce).  Every backward stage of the model (heads, decoder, encoder, backbone, text) already writes ALL of its
@@ -56,6 +54,8 @@ class FlatGradSync:
         if grads:
             key = (stage_name, flat.data_ptr(), flat.numel())
             if key not in self._outside:
+                if len(self._outside) > 64:  # eager mode allocates a new arena every step: do not grow without bound
+                    self._outside.clear()
                 lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
                 self._outside[key] = [i for i, t in enumerate(grads) if t is not None and not (lo <= t.data_ptr() < hi)]
             extra = [grads[i] for i in self._outside[key]]

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from bisect import bisect_right
 from typing import Iterable, List, Optional, Sequence
 
@@ -101,6 +102,8 @@ def update_ema(model, model_ema, decay: float) -> None:
             model = model.module
         key = (id(model), id(model_ema))
         ent = _ema_tables.get(key)
+        if ent is not None and (ent[3]() is not model or ent[4]() is not model_ema):
+            ent = None  # the ids were recycled by other objects
         if ent is None:
             msd = model.state_dict()
             pairs, copies = [], []
@@ -110,8 +113,8 @@ def update_ema(model, model_ema, decay: float) -> None:
                     pairs.append((ema_v, mv))
                 else:
                     copies.append((ema_v, mv))
-            ent = _ema_tables[key] = (_Table(), pairs, copies)
-        tab, pairs, copies = ent
+            ent = _ema_tables[key] = (_Table(), pairs, copies, weakref.ref(model), weakref.ref(model_ema))
+        tab, pairs, copies = ent[:3]
         if pairs:
             items, n, blocks = tab.get([[a for a, _ in pairs], [b for _, b in pairs]])
             _lib.check(_lib.load().toist_ema_update(items.data_ptr(), n, blocks, float(decay), 1.0 - float(decay), _stream()))
