@@ -102,8 +102,9 @@ def update_ema(model, model_ema, decay: float) -> None:
             model = model.module
         key = (id(model), id(model_ema))
         ent = _ema_tables.get(key)
-        if ent is not None and (ent[3]() is not model or ent[4]() is not model_ema):
-            ent = None  # the ids were recycled by other objects
+        probe = (next(model.parameters()).data_ptr(), next(model_ema.parameters()).data_ptr())
+        if ent is not None and (ent[3]() is not model or ent[4]() is not model_ema or ent[5] != probe):
+            ent = None  # the ids were recycled by other objects, or the parameters moved (.to(), .cuda())
         if ent is None:
             msd = model.state_dict()
             pairs, copies = [], []
@@ -113,7 +114,7 @@ def update_ema(model, model_ema, decay: float) -> None:
                     pairs.append((ema_v, mv))
                 else:
                     copies.append((ema_v, mv))
-            ent = _ema_tables[key] = (_Table(), pairs, copies, weakref.ref(model), weakref.ref(model_ema))
+            ent = _ema_tables[key] = (_Table(), pairs, copies, weakref.ref(model), weakref.ref(model_ema), probe)
         tab, pairs, copies = ent[:3]
         if pairs:
             items, n, blocks = tab.get([[a for a, _ in pairs], [b for _, b in pairs]])
