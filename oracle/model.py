@@ -584,9 +584,10 @@ def criterion(cfg: Config, out: dict, tokenized, targets, positive_map: Tensor, 
         if with_masks:
             res["loss_mask" + suffix], res["loss_dice" + suffix] = loss_masks(o["pred_masks"], targets, idx, nb)
         if cfg.contrastive_align_loss:
-            with torch.no_grad():  # the reference decorates this loss with @torch.no_grad() (models/mdetr.py:600)
-                res["loss_contrastive_align" + suffix] = loss_contrastive_align(
-                    o["proj_queries"], o["proj_tokens"], tokenized, targets, idx, nb, cfg.temperature_NCE)
+            # differentiable in the reference: models/mdetr.py:601 is a plain method (only softkd_matcher :520 and
+            # loss_cardinality :783 carry @torch.no_grad()); weight 1 per layer (:1068-1069), summed at engine.py:72
+            res["loss_contrastive_align" + suffix] = loss_contrastive_align(
+                o["proj_queries"], o["proj_tokens"], tokenized, targets, idx, nb, cfg.temperature_NCE)
         return res, idx
 
     nb = num_boxes

@@ -43,3 +43,16 @@ def max_err(got, ref) -> float:
     g = got.detach().double().cpu().flatten()
     r = ref.detach().double().cpu().flatten()
     return (g - r).abs().max().item() if g.numel() else 0.0
+
+
+GRAD_SAMPLE = 2048
+
+
+def strided_sample(t, n: int = GRAD_SAMPLE):
+    """Deterministic subsample of a tensor (at most n elements, evenly strided over the flattened tensor): lets a
+    small fixture pin a 170 M-element gradient set element by element (tools/make_golden.py, tests/test_gpu_golden.py)."""
+    f = t.detach().flatten()
+    if f.numel() <= n:
+        return f.clone()
+    step = f.numel() // n
+    return f[::step][:n].clone()

@@ -79,8 +79,9 @@ def test_fused_attention_matches_fp32_torch(sq, sk, b, h, d, p_drop):
     att = att.masked_fill(km.bool()[:, None, None, :], float("-inf"))
     import math
 
-    assert saved.lse.shape == (b, h, sq, 2)  # (row maximum in the log2 domain, softmax denominator)
-    assert rel_err(saved.lse[..., 0] * math.log(2.0) + saved.lse[..., 1].log(), torch.logsumexp(att, -1)) < 1e-4
+    assert saved.lse.shape == (b, h, sq, 2)  # (raw row maximum of q.k, softmax denominator)
+    assert float(saved.lse[..., 1].min()) >= 1.0 - 1e-6 and float(saved.lse[..., 1].max()) <= sk  # e <= 1, e_max = 1
+    assert rel_err(saved.lse[..., 0] * d ** -0.5 + saved.lse[..., 1].log(), torch.logsumexp(att, -1)) < 1e-4
     dctx = torch.randn(sq, b, e, device=DEV).to(BF)
     ref.backward(dctx.float())
     dqk = torch.full((max(sq, sk), b, 2 * e), float("nan"), device=DEV, dtype=BF)
@@ -133,8 +134,6 @@ def test_unsupported_shapes_use_the_unfused_path():
     assert rel_err(ctx.float(), ref) < 5e-3
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: the (m2, l) statistics it guards "
-                                        "passed the parity tests on B200, this extreme-magnitude case has not run yet")
 def test_fused_attention_backward_is_finite_for_huge_logits():
     """Random-initialised ResNet-101 features reach 1e5, the first encoder layer's logits 1e10 (one ulp = 1e3): the
     softmax is then one-hot, the reference's gradients w.r.t. q and k vanish and w.r.t. v route dO to the winning key.
@@ -152,5 +151,11 @@ def test_fused_attention_backward_is_finite_for_huge_logits():
     dctx = torch.randn(sq, b, e, device=DEV).to(BF)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     K.attention_bwd(dctx, q, k, v, saved, h, dq, dk, dv)
-    for t in (dq, dk, dv):
-        assert torch.isfinite(t.float()).all()
+    bad = {n: int((~torch.isfinite(t.float())).sum()) for n, t in (("dq", dq), ("dk", dk), ("dv", dv))}
+    assert not any(bad.values()), bad
+    # the softmax is one-hot here: dv routes every dO row to its winning key, so it matches fp32 torch closely
+    ref, (qr, kr, vr) = reference(q, k, v, None, h)
+    ref.backward(dctx.float())
+    # (a row whose two best logits are closer than the fp32 rounding of a 1e10 dot product may pick the other key)
+    assert rel_err(ctx.float(), ref.detach()) < 5e-2
+    assert rel_err(dv.float(), unheads(vr.grad, sk, b, e)) < 5e-2

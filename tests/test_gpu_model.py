@@ -79,7 +79,9 @@ def test_two_phase_protocol_and_autograd_link():
     assert model.backbone[0].body.layer1[0].conv1.weight.grad is None  # frozen (backbone.py:64-66)
     assert model.transformer.text_encoder.embeddings.word_embeddings.weight.grad is not None
     assert model.transformer.text_encoder.pooler.dense.weight.grad is None  # unused parameter
-    assert model.contrastive_align_projection_image.weight.grad is None  # loss is evaluated under no_grad
+    # loss_contrastive_align is differentiable (models/mdetr.py:601-666): both projections train
+    assert float(model.contrastive_align_projection_image.weight.grad.norm()) > 0
+    assert float(model.contrastive_align_projection_text.weight.grad.norm()) > 0
     assert model.query_embed.weight.grad is not None
     assert torch.isfinite(total)
 

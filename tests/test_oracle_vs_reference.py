@@ -191,3 +191,46 @@ def test_lr_schedule_matches_reference():
             refmod.adjust_learning_rate(o1, epoch, step, total, a)
             ours.adjust_learning_rate(o2, epoch, step, total, a)
             assert o1.param_groups == o2.param_groups, (schedule, epoch, step, total)
+
+
+def test_gradients_match_reference(ref):
+    """The oracle's backward is pinned too: gradient of the weighted loss sum (engine.py:72,88) w.r.t. EVERY trainable
+    tensor, reference vs oracle.  In particular loss_contrastive_align is differentiated (models/mdetr.py:601-666 has
+    no @torch.no_grad; weight 1 per layer at :1068-1069): both contrastive projections receive a gradient."""
+    images, mask, captions, targets, pm = ref["batch"]
+    model, criterion = ref["model"], ref["criterion"]
+    from util.misc import NestedTensor  # reference
+
+    weight_dict = shims.load_reference(ref["tok"]).build_model(ref["args"])[3]
+    model.zero_grad(set_to_none=True)
+    mc = model(NestedTensor(images, mask), captions, encode_and_save=True)
+    out = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc)
+    losses = criterion(mc, out, targets, pm, None)
+    assert losses["loss_contrastive_align"].requires_grad
+    total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+    total.backward()
+    rgrads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    assert float(rgrads["contrastive_align_projection_image.weight"].norm()) > 0
+    assert float(rgrads["contrastive_align_projection_text.weight"].norm()) > 0
+
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    cfg = O.Config(backbone="resnet50")
+    tokd = ref["tok"](captions)
+    omc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+    oout = O.decode(sd, cfg, omc)
+    olosses, _ = O.criterion(cfg, oout, tokd, targets, pm)
+    ototal = sum(olosses[k] * weight_dict[k] for k in olosses if k in weight_dict)
+    ototal.backward()
+    assert abs(float(ototal.detach()) - float(total.detach())) <= 2e-4 * abs(float(total.detach()))
+    missing = [k for k in rgrads if sd[k].grad is None]
+    assert not missing, missing
+    extra = [k for k in trainable if sd[k].grad is not None and k not in rgrads]
+    assert not extra, extra
+    # RoBERTa key biases: the softmax is invariant to them, their exact gradient is zero and what is left is rounding
+    errs = sorted(((rel_err(sd[k].grad, rgrads[k]), k) for k in rgrads
+                   if float(rgrads[k].norm()) > 0 and "key.bias" not in k), reverse=True)
+    assert errs[0][0] < 2e-3, errs[:5]

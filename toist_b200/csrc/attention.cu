@@ -16,7 +16,7 @@
 //               reads it again, exponentiates (ex2.approx), applies the dropout decision, sums, packs bf16 and writes
 //               the K-major operand tile for the PV product; the epilogue scales O by keep_scale / l.
 // Backward, one CTA per (128-key tile, head, batch), 320 threads, loop over 128-query chunks:
-//   S^T = K Q^T and dP^T = V dO^T (TMEM) -> 8 compute warps: p = exp2(s * scale - m2) / l, dropout decision regenerated,
+//   S^T = K Q^T and dP^T = V dO^T (TMEM) -> 8 compute warps: p = exp2((s - mx) * scale) / l, dropout decision regenerated,
 //   Pd^T and dS^T (bf16, K-major in shared memory) -> dV += Pd^T dO, dK += dS^T Q (accumulated in TMEM over the
 //   chunks), dQ_chunk = dS K (TMEM -> fp32 partial per key tile; attn_dq_reduce_kernel sums the key tiles in a fixed
 //   order and writes bf16).  Nothing is atomic: results are deterministic run to run.
@@ -197,8 +197,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     sRed[hf * 128 + r] = mx;
     named_barrier_sync(1, 256);
     mx = fmaxf(sRed[r], sRed[128 + r]);
-    // ---- pass 2: e = exp(scale * (s - max)), dropout, bf16 operand tiles for the PV product
-    const float m2 = mx * p.scale_log2;
+    // ---- pass 2: e = exp2((s - max) * scale * log2 e), dropout, bf16 operand tiles for the PV product.
+    // The subtraction comes first: s - mx is exactly 0 for the row maximum and <= 0 for every other key, so e <= 1 and
+    // 1 <= l <= Sk whatever the magnitude of the logits (random-init ResNet-101 features give logits of 1e10, where
+    // fma(s, c, -mx * c) is off by up to half an ulp of mx * c, i.e. by dozens of octaves).
     const bool drop = p.seed != nullptr;
     uint32_t k0 = 0, k1 = 0;
     if (drop) {
@@ -230,8 +232,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             // exactly this expression is re-evaluated by the backward pass (same operands, one rounding)
-            float e0 = ex2_approx(__fmaf_rn(__uint_as_float(raw[i]), p.scale_log2, -m2));
-            float e1 = ex2_approx(__fmaf_rn(__uint_as_float(raw[i + 1]), p.scale_log2, -m2));
+            float e0 = ex2_approx(__fmul_rn(__fsub_rn(__uint_as_float(raw[i]), mx), p.scale_log2));
+            float e1 = ex2_approx(__fmul_rn(__fsub_rn(__uint_as_float(raw[i + 1]), mx), p.scale_log2));
             if (bits != 0u) {  // warp-uniform
               if ((bits >> i) & 1u) e0 = 0.f;
               if ((bits >> (i + 1)) & 1u) e1 = 0.f;
@@ -297,12 +299,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-    // Row statistics for the backward pass: (m2, l) = (scaled row maximum in the log2 domain, softmax denominator), kept
-    // as two numbers.  Folding them into one log-sum-exp loses the softmax when |logit| is large: at random
-    // initialisation the first encoder layer sees logits of ~1e10 (ulp 1e3), the backward recomputed exp(s - lse) from
-    // two differently rounded large numbers and produced inf -> NaN gradients for the whole backbone.
+    // Row statistics for the backward pass: (mx, l) = (raw row maximum of q.k, softmax denominator), kept as two
+    // numbers.  Folding them into one log-sum-exp loses the softmax when |logit| is large: at random initialisation
+    // the first encoder layer sees logits of ~1e10 (ulp 1e3), the backward recomputed exp(s - lse) from two
+    // differently rounded large numbers and produced inf -> NaN gradients for the whole backbone.
     if (hf == 0 && p.lse != nullptr && qrow < p.sq)
-      reinterpret_cast<float2*>(p.lse)[(long long)(b * p.h + h) * p.sq + qrow] = make_float2(m2, l);
+      reinterpret_cast<float2*>(p.lse)[(long long)(b * p.h + h) * p.sq + qrow] = make_float2(mx, l);
   }
 
   tc_fence_before();
@@ -347,7 +349,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sRing = sV + 16384;      // 2 x (Q chunk 16 KB | dO chunk 16 KB)
   uint8_t* sPd = sRing + 65536;     // Pd^T: 2 blocks of [128 keys][64 queries]
   uint8_t* sdS = sPd + 32768;       // dS^T: same layout
-  float* sLse = reinterpret_cast<float*>(sdS + 32768);  // [nq <= 8][128] log2-domain row maximum m2 (inf past the last query)
+  float* sLse = reinterpret_cast<float*>(sdS + 32768);  // [nq <= 8][128] raw row maximum of q.k (inf past the last query)
   float* sDelta = sLse + kBwdMaxNQ * 128;                // [nq][128] rowsum(dO * O)
   float* sInvL = sDelta + kBwdMaxNQ * 128;               // [nq][128] 1 / softmax denominator (0 past the last query)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sInvL + kBwdMaxNQ * 128);
@@ -539,9 +541,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             // p = e / l with e exactly as the forward formed it; a probability never exceeds 1 (the clamp only acts
             // if S^T and S differ in the last bit at logit magnitudes where one ulp is worth many octaves)
-            float pr0 = fminf(ex2_approx(__fmaf_rn(__uint_as_float(st_raw[i]), p.scale_log2, -lsv[i2 * 2])) * ilv[i2 * 2], 1.f);
-            float pr1 = fminf(ex2_approx(__fmaf_rn(__uint_as_float(st_raw[i + 1]), p.scale_log2, -lsv[i2 * 2 + 1])) *
-                                  ilv[i2 * 2 + 1], 1.f);
+            float pr0 = fminf(ex2_approx(__fmul_rn(fminf(__fsub_rn(__uint_as_float(st_raw[i]), lsv[i2 * 2]), 0.f),
+                                                   p.scale_log2)) * ilv[i2 * 2], 1.f);
+            float pr1 = fminf(ex2_approx(__fmul_rn(fminf(__fsub_rn(__uint_as_float(st_raw[i + 1]), lsv[i2 * 2 + 1]), 0.f),
+                                                   p.scale_log2)) * ilv[i2 * 2 + 1], 1.f);
             if (!key_ok) pr0 = pr1 = 0.f;
             const float dp0 = keep0 ? __uint_as_float(dp_raw[i]) * p.keep_scale : 0.f;
             const float dp1 = keep1 ? __uint_as_float(dp_raw[i + 1]) * p.keep_scale : 0.f;

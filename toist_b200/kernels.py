@@ -660,7 +660,7 @@ FUSED_ATTENTION = os.environ.get("TOIST_FUSED_ATTN", "1") != "0"
 
 
 class FusedAttnSaved:
-    """What the fused forward keeps for its backward: the output, the row statistics `lse` = (log2-domain row maximum,
+    """What the fused forward keeps for its backward: the output, the row statistics `lse` = (raw row maximum of q.k,
     softmax denominator) and the key mask (the scores and probabilities never leave the SM)."""
     __slots__ = ("ctx", "lse", "key_mask")
 
@@ -698,7 +698,7 @@ def attention_fused_fwd(q, k, v, key_mask_u8, nhead: int, ctx: Optional[torch.Te
     sk = k.shape[0]
     if ctx is None:
         ctx = torch.empty((sq, b, e), dtype=torch.bfloat16, device=q.device)
-    lse = torch.empty((b, nhead, sq, 2), dtype=torch.float32, device=q.device) if need_lse else None  # (m2, l) per row
+    lse = torch.empty((b, nhead, sq, 2), dtype=torch.float32, device=q.device) if need_lse else None  # (raw row maximum, denominator) per row
     a = _attn_desc(q, k, v, ctx, lse, key_mask_u8, nhead, drop)
     keep = (q, k, v, ctx, lse, key_mask_u8, drop)
 
@@ -946,12 +946,13 @@ def criterion_reduce(row_loss, pl1, pgi, card, img_loss, tgt_count, num_boxes, f
     return out
 
 
-def scale_layers(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
-    """y[l] = x[l] * g[l] for x [L, ...] fp32, g [L] fp32."""
+def scale_layers(x: torch.Tensor, g: torch.Tensor, reduce: bool = False) -> torch.Tensor:
+    """y[l] = x[l] * g[l] for x [L, ...] fp32, g [L] fp32; with `reduce` y = sum_l x[l] * g[l] (shape x.shape[1:])."""
     L = x.shape[0]
-    assert x.is_contiguous() and g.is_contiguous() and g.numel() == L
-    y = torch.empty_like(x)
-    _ck(_L().toist_scale_layers(x.data_ptr(), g.data_ptr(), y.data_ptr(), L, x.numel() // L, 0, _stream()))
+    assert x.dtype == torch.float32 and x.is_contiguous() and g.is_contiguous() and g.numel() == L
+    y = torch.empty(x.shape[1:], dtype=x.dtype, device=x.device) if reduce else torch.empty_like(x)
+    _ck(_L().toist_scale_layers(x.data_ptr(), g.data_ptr(), y.data_ptr(), L, x.numel() // L, 1 if reduce else 0,
+                                _stream()))
     return y
 
 

@@ -288,30 +288,41 @@ class MDETR(nn.Module):
 
 
 # ====================================================================================================== criterion
-def _criterion_fwd(c: Call, logits, boxes, pq, ptok, tgt_boxes, tgt_count, posmap, tok_pos, num_boxes):
+def _criterion_fwd(c: Call, logits, boxes, pq, ptok, tgt_boxes, tgt_count, posmap, tok_pos, num_boxes, forced=None):
     """Matching + every detection loss term of every decoder layer in a handful of launches; returns out [5, L] (see
-    toist_criterion_reduce), the assignments and the error flag.  Gradients exist w.r.t. logits and boxes only (the
-    alignment loss is evaluated without gradient in the reference, models/mdetr.py:600)."""
+    toist_criterion_reduce), the assignments and the error flag.  Unit gradients w.r.t. logits, boxes and both
+    contrastive projections are produced by the same launches (loss_contrastive_align is differentiable in the
+    reference, models/mdetr.py:601-666; only loss_cardinality :783 is evaluated without gradient)."""
     pt = PackedTargets(tgt_boxes, tgt_count, posmap, (), tgt_boxes.shape[1])
-    match_q, flags, _ = match_layers(logits, boxes, pt, c.w_class, c.w_bbox, c.w_giou)
+    if forced is None:
+        match_q, flags, _ = match_layers(logits, boxes, pt, c.w_class, c.w_bbox, c.w_giou)
+    else:  # SetCriterion.force_match: differentiate a given assignment (parity tests against reference goldens)
+        match_q, flags = forced, torch.zeros(1, dtype=torch.int32, device=logits.device)
     row_loss, dlogits = K.token_ce(logits, match_q, tgt_count, posmap, num_boxes, c.eos_coef, c.save)
     pl1, pgi, d1, d2 = K.box_loss(boxes, match_q, tgt_count, tgt_boxes, num_boxes, c.save)
     card = K.cardinality(logits)
-    img_loss = None
+    img_loss = dpq = dpt = None
     if pq is not None:
-        img_loss, _, _ = K.contrastive_align(pq, ptok, match_q, tgt_count, tok_pos, num_boxes, c.temperature, False)
+        img_loss, dpq, dpt = K.contrastive_align(pq, ptok, match_q, tgt_count, tok_pos, num_boxes, c.temperature,
+                                                 c.save)
     out = K.criterion_reduce(row_loss, pl1, pgi, card, img_loss, tgt_count, num_boxes, flags)
-    return (out, match_q, flags), ((dlogits, d1, d2) if c.save else None)
+    return (out, match_q, flags), ((dlogits, d1, d2, dpq, dpt) if c.save else None)
 
 
 def _criterion_bwd(c: Call, saved, needs, gout, *unused):
-    dlogits, d1, d2 = saved
+    """gout [5, L]: the weight each (term, layer) cell carries in the caller's weighted sum (engine.py:72)."""
+    dlogits, d1, d2, dpq, dpt = saved
     gl = K.scale_layers(dlogits, gout[0]) if needs[0] else None
     gb = K.scale_layers2(d1, gout[1], d2, gout[2]) if needs[1] else None
-    return (gl, gb) + (None,) * 7, {}
+    gq = gt = None
+    if dpq is not None:
+        g4 = gout[4].contiguous()
+        gq = K.scale_layers(dpq, g4) if needs[2] else None
+        gt = K.scale_layers(dpt, g4, reduce=True) if needs[3] else None  # proj_tokens is shared by all decoder layers
+    return (gl, gb, gq, gt) + (None,) * 6, {}
 
 
-CRITERION = Spec("criterion", 9, _criterion_fwd, _criterion_bwd, nondiff=(1, 2))
+CRITERION = Spec("criterion", 10, _criterion_fwd, _criterion_bwd, nondiff=(1, 2))
 
 
 class _LossTerms(torch.autograd.Function):
@@ -447,6 +458,21 @@ class SetCriterion(nn.Module):
         self._stage_mask = Stage.empty("mask_loss")
         self._stage_kd = Stage.empty("softkd")
         self._graphs: Optional[GraphCache] = None
+        self._forced = None
+
+    def force_match(self, indices) -> None:
+        """Testing hook: `indices[l][b] = (query_idx, target_idx)` (the matcher's output format, one list per decoder
+        layer, first layer first) replaces the Hungarian assignment in the following forward calls; `None` restores
+        the matcher.  Lets a gradient-parity test differentiate exactly the assignment the reference chose when bf16
+        input noise would flip near-tie costs."""
+        self._forced = indices
+
+    def _forced_match(self, L: int, packed, dev) -> torch.Tensor:
+        mq = torch.full((L, len(packed.counts), packed.t_max), -1, dtype=torch.int32)
+        for l in range(L):
+            for b, (qi, ti) in enumerate(self._forced[l]):
+                mq[l, b, ti.to(torch.int64)] = qi.to(torch.int32)
+        return h2d(mq, dev)
 
     def enable_cuda_graphs(self, on: bool = True) -> "SetCriterion":
         """Replay the criterion's launch sequence as a CUDA graph (fixed shapes; see MDETR.enable_cuda_graphs)."""
@@ -505,12 +531,14 @@ class SetCriterion(nn.Module):
         if "contrastive_align" in self.losses:
             pq, ptok = st["proj_queries"], st["proj_tokens"]
             tok_pos = h2d(build_token_positive(outputs["tokenized"], targets, packed.t_max, ptok.shape[1]), dev)
-        save = torch.is_grad_enabled() and (logits.requires_grad or boxes.requires_grad)
+        save = torch.is_grad_enabled() and (logits.requires_grad or boxes.requires_grad
+                                            or (pq is not None and (pq.requires_grad or ptok.requires_grad)))
         call = Call(self._stage, {}, save, graphs=self._graphs, w_class=float(self.matcher.cost_class),
                     w_bbox=float(self.matcher.cost_bbox), w_giou=float(self.matcher.cost_giou),
                     eos_coef=float(self.eos_coef), temperature=float(self.temperature))
+        forced = self._forced_match(L, packed, dev) if self._forced is not None else None
         out, match_q, flags = run_stage(CRITERION, call, logits, boxes, pq, ptok, packed.boxes, packed.count,
-                                        packed.posmap, tok_pos, nb)
+                                        packed.posmap, tok_pos, nb, forced)
         self.last_match = (match_q, packed.counts, flags)
         terms = [("loss_ce", 0), ("loss_bbox", 1), ("loss_giou", 2), ("cardinality_error", 3)]
         if pq is not None:
@@ -530,14 +558,14 @@ class SetCriterion(nn.Module):
                 losses[prefix + "loss_mask"], losses[prefix + "loss_dice"] = mask_out[0], mask_out[1]
                 mask_out = None
             v = cells[row * L + L - 1]
-            losses[prefix + name] = v.detach() if row >= 3 else v
+            losses[prefix + name] = v.detach() if row == 3 else v  # cardinality_error: no gradient (mdetr.py:783)
         if mask_out is not None:
             losses[prefix + "loss_mask"], losses[prefix + "loss_dice"] = mask_out[0], mask_out[1]
         if use_aux:
             for i in range(L - 1):
                 for name, row in terms:
                     v = cells[row * L + i]
-                    losses[f"{prefix}{name}_{i}"] = v.detach() if row >= 3 else v
+                    losses[f"{prefix}{name}_{i}"] = v.detach() if row == 3 else v
         return losses, (st, match_q, packed, flags)
 
     def _forward_distillation(self, memory_cache, outputs, targets, positive_map):

@@ -629,9 +629,10 @@ DECODER = Spec("decoder", 4, decoder_fwd, decoder_bwd)
 
 # ------------------------------------------------------------------------------------------------ heads
 def heads_fwd(c: Call, hs: torch.Tensor, text_mem32: Optional[torch.Tensor]):
-    """hs bf16 [L, Q*B, E] -> logits [L,B,Q,C], boxes [L,B,Q,4] (sigmoid), proj_queries [L,B,Q,D], proj_tokens [B,T,D].
-    The reference evaluates the contrastive-alignment loss under torch.no_grad (models/mdetr.py:600), so the two
-    projections never receive a gradient; they are emitted as constants (non-differentiable outputs)."""
+    """hs bf16 [L, Q*B, E] -> logits [L,B,Q,C], boxes [L,B,Q,4] (sigmoid), proj_queries [L,B,Q,D], proj_tokens [B,T,D]
+    (models/mdetr.py:420-433).  All four outputs are differentiable: loss_contrastive_align (models/mdetr.py:601-666,
+    weight 1 per decoder layer at :1068-1069) back-propagates through both L2-normalised projections into the decoder
+    states and into `text_memory` (the last L rows of the encoder output)."""
     st = c.stage
     B = c.B
     w = WView(c.w, st.prefix)
@@ -643,32 +644,33 @@ def heads_fwd(c: Call, hs: torch.Tensor, text_mem32: Optional[torch.Tensor]):
     h2 = K.linear_fwd(h1, w["bbox_embed.layers.1.weight"], w["bbox_embed.layers.1.bias"], act=ACT_RELU)
     boxes = Bk.heads_linear_fwd(h2.view(L, QB, E), w["bbox_embed.layers.2.weight"], w["bbox_embed.layers.2.bias"], L, Q,
                                 B, act=ACT_SIGMOID)
-    pq = pt = None
+    pq = pt = nq = nt = tm = None
     if st.contrastive:
         raw = Bk.heads_linear_fwd(hs, w["contrastive_align_projection_image.weight"],
                                   w["contrastive_align_projection_image.bias"], L, Q, B)
         D = raw.shape[-1]
-        pq, _ = K.l2norm_fwd(raw.view(-1, D))
+        pq, nq = K.l2norm_fwd(raw.view(-1, D))  # F.normalize(p=2, dim=-1), eps 1e-12
         pq = pq.view(L, B, Q, D)
         T = text_mem32.shape[0]
         tm = K.cast_bf16(text_mem32.contiguous().view(1, T * B, E))
         rawt = Bk.heads_linear_fwd(tm, w["contrastive_align_projection_text.weight"],
                                    w["contrastive_align_projection_text.bias"], 1, T, B)
-        pt, _ = K.l2norm_fwd(rawt.view(-1, D))
+        pt, nt = K.l2norm_fwd(rawt.view(-1, D))
         pt = pt.view(B, T, D)
-    saved = (hs, h1, h2, boxes) if c.save else None
+    saved = (hs, h1, h2, boxes, pq, nq, pt, nt, tm) if c.save else None
     return (logits, boxes, pq, pt), saved
 
 
-def heads_bwd(c: Call, saved, needs, dlogits, dboxes, *unused):
+def heads_bwd(c: Call, saved, needs, dlogits, dboxes, dpq=None, dpt=None):
     st = c.stage
-    hs, h1, h2, boxes = saved
+    hs, h1, h2, boxes, pq, nq, pt, nt, tm = saved
     L, QB, E = hs.shape
     B = c.B
     Q = QB // B
     grads: Dict[str, torch.Tensor] = {}
     g, rq, w = GView(grads, st.prefix), RView(c.req, st.prefix), WView(c.w, st.prefix)
     dhs = None
+    dtext = None
     if dboxes is not None:
         dpre = K.sigmoid_bwd(dboxes.contiguous(), boxes)
         d16 = K.cast_pad_bf16(dpre, 8)
@@ -680,11 +682,28 @@ def heads_bwd(c: Call, saved, needs, dlogits, dboxes, *unused):
         Bk.lin_param_grads(g, rq, "bbox_embed.layers.0.weight", "bbox_embed.layers.0.bias", dh1, hs.view(L * QB, E),
                            (E, E))
         dhs = K.linear_dgrad(dh1, w["bbox_embed.layers.0.weight"]).view(L, QB, E)
+    if dpq is not None and pq is not None:  # F.normalize backward, then the image projection (models/mdetr.py:432)
+        D = pq.shape[-1]
+        draw = K.l2norm_bwd(dpq.contiguous().view(-1, D), pq.view(-1, D), nq)
+        d16 = K.cast_pad_bf16(draw.view(L, B, Q, D), (D + 7) // 8 * 8)
+        dhs = Bk.heads_linear_bwd(g, rq, "contrastive_align_projection_image.weight",
+                                  "contrastive_align_projection_image.bias", d16, hs,
+                                  w["contrastive_align_projection_image.weight"], L, Q, B, res=dhs)
+    if dpt is not None and pt is not None:  # text projection of memory_cache["text_memory"] (models/mdetr.py:433-435)
+        D = pt.shape[-1]
+        T = pt.shape[1]
+        draw = K.l2norm_bwd(dpt.contiguous().view(-1, D), pt.view(-1, D), nt)
+        d16 = K.cast_pad_bf16(draw.view(1, B, T, D), (D + 7) // 8 * 8)
+        dtm = Bk.heads_linear_bwd(g, rq, "contrastive_align_projection_text.weight",
+                                  "contrastive_align_projection_text.bias", d16, tm,
+                                  w["contrastive_align_projection_text.weight"], 1, T, B)
+        if needs[1]:
+            dtext = K.cast_f32(dtm.view(T * B, E)).view(T, B, E)
     if dlogits is not None:
         d16 = K.cast_bf16(dlogits.contiguous())
         dhs = Bk.heads_linear_bwd(g, rq, "class_embed.weight", "class_embed.bias", d16, hs, w["class_embed.weight"], L,
                                   Q, B, res=dhs)
-    return (dhs, None), grads
+    return (dhs, dtext), grads
 
 
-HEADS = Spec("heads", 2, heads_fwd, heads_bwd, nondiff=(2, 3))
+HEADS = Spec("heads", 2, heads_fwd, heads_bwd)

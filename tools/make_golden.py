@@ -88,28 +88,44 @@ def config1(models, tok):
     torch.manual_seed(0)
     model, criterion, _, weight_dict = models.build_model(args)
     model.eval()
+    from conftest import strided_sample
     from util.misc import NestedTensor  # reference
 
     images, mask, captions, targets, pm = make_batch(2, 480, 8, seed=1234, pad=True)
+    # one full step of engine.py:63-88 in eval mode (no dropout): forward, criterion, weighted sum, backward
+    mc = model(NestedTensor(images, mask), captions, encode_and_save=True)
+    out = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc)
+    losses = criterion(mc, out, targets, pm, None)
+    total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+    total.backward()
+    grads = {n: p.grad.detach() for n, p in model.named_parameters() if p.grad is not None}
     with torch.no_grad():
-        mc = model(NestedTensor(images, mask), captions, encode_and_save=True)
-        out = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc)
-        losses = criterion(mc, out, targets, pm, None)
         layers = list(out["aux_outputs"]) + [out]
         indices = [criterion.matcher(o, targets, pm) for o in layers]
     sd = model.state_dict()
+    small = ("contrastive_align_projection_", "class_embed.", "bbox_embed.", "query_embed.", "input_proj.bias",
+             "transformer.resizer.", "transformer.decoder.norm.")
+    det = lambda t: t.detach().clone()  # noqa: E731
     return {
         "batch": {"size": 480, "tokens": 8, "batch": 2, "seed": 1234, "pad": True},
         "state_checksum": {k: float(v.double().abs().sum()) for k, v in sd.items()},
-        "img_memory": mc["img_memory"].half(), "text_memory_resized": mc["text_memory_resized"].half(),
+        "img_memory": det(mc["img_memory"]).half(), "text_memory_resized": det(mc["text_memory_resized"]).half(),
         "mask": mc["mask"], "pos_embed_row0": mc["pos_embed"][:, 0].clone(),
-        "pred_logits": torch.stack([o["pred_logits"] for o in layers]),
-        "pred_boxes": torch.stack([o["pred_boxes"] for o in layers]),
-        "proj_queries": torch.stack([o["proj_queries"] for o in layers]),
-        "proj_tokens": out["proj_tokens"],
+        "pred_logits": torch.stack([det(o["pred_logits"]) for o in layers]),
+        "pred_boxes": torch.stack([det(o["pred_boxes"]) for o in layers]),
+        "proj_queries": torch.stack([det(o["proj_queries"]) for o in layers]),
+        "proj_tokens": det(out["proj_tokens"]),
         "losses": {k: float(v) for k, v in losses.items()},
+        "total": float(total),
         "indices": [[(i.clone(), j.clone()) for i, j in layer] for layer in indices],
         "weight_dict": dict(weight_dict),
+        # reference gradients of the weighted loss sum w.r.t. every trainable tensor (436): L2 norm + an evenly
+        # strided 2048-element sample of each, and the full tensor for the small head-side parameters
+        "grads": {
+            "norm": {k: float(g.double().norm()) for k, g in grads.items()},
+            "sample": {k: strided_sample(g) for k, g in grads.items()},
+            "full": {k: g.clone() for k, g in grads.items() if k.startswith(small)},
+        },
     }
 
 
@@ -302,16 +318,25 @@ def cluster_cases(models, tok):
 
 
 def main():
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="comma-separated subset of: matcher,config1,config3,config5,cluster")
+    only = set(filter(None, ap.parse_args().only.split(",")))
     torch.set_num_threads(8)
     OUT.mkdir(parents=True, exist_ok=True)
     tok = CharTokenizer()
     models = shims.load_reference(tok)
     v = versions()
-    torch.save({"versions": v, "cases": matcher_cases(models)}, OUT / "matcher_cases.pt")
-    torch.save({"versions": v, **config1(models, tok)}, OUT / "config1_r50.pt")
-    torch.save({"versions": v, **config3_small(models, tok)}, OUT / "config3_r50_segm_small.pt")
-    torch.save({"versions": v, **config5_softkd_small(models, tok)}, OUT / "config5_softkd_small.pt")
-    torch.save({"versions": v, **cluster_cases(models, tok)}, OUT / "cluster_cases.pt")
+    jobs = [("matcher", "matcher_cases.pt", lambda: {"cases": matcher_cases(models)}),
+            ("config1", "config1_r50.pt", lambda: config1(models, tok)),
+            ("config3", "config3_r50_segm_small.pt", lambda: config3_small(models, tok)),
+            ("config5", "config5_softkd_small.pt", lambda: config5_softkd_small(models, tok)),
+            ("cluster", "cluster_cases.pt", lambda: cluster_cases(models, tok))]
+    for tag, fname, fn in jobs:
+        if only and tag not in only:
+            continue
+        torch.save({"versions": v, **fn()}, OUT / fname)
     for f in sorted(OUT.glob("*.pt")):
         print(f.name, f.stat().st_size // 1024, "KiB")
 
