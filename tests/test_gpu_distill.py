@@ -293,3 +293,51 @@ def test_distillation_step_end_to_end():
     os_ = {"pred_logits": out_s["pred_logits"].detach().cpu(), "pred_boxes": out_s["pred_boxes"].detach().cpu()}
     want = float(O.loss_softkd(on, os_, idx_n, idx_s, 100))
     assert abs(float(losses["loss_softkd"]) - want) <= 2e-7 + 2e-3 * abs(want)
+
+
+def test_distillation_criterion_graph_replay_matches_eager(kd_gold):
+    """SetCriterion evaluates its stage twice per distillation step (noun, then sth) with identical shapes and flags:
+    each pass must own its captured graph, otherwise the second replay overwrites the first pass's losses, assignments
+    and saved gradients.  Eager vs captured vs replayed, values and gradients."""
+    from toist_b200.models import build_model
+    from toist_b200.tokenizer import CharTokenizer
+
+    g = kd_gold
+    args = make_args("resnet50", distillation=True, softkd_loss=True, softkd_coef=50.0)
+    _, criterion, _, wd = build_model(args)
+    tok = CharTokenizer()
+    batches = {"noun": make_batch(**g["batch_noun"]), "sth": make_batch(**g["batch_sth"])}
+
+    def run():
+        outs, leaves, tg, pms = [], [], [], []
+        for tag in ("noun", "sth"):
+            _, _, captions, targets, pm = batches[tag]
+            tokd = tok(captions)
+            L = g[tag]["pred_logits"].shape[0]
+            st = {k: g[tag][k].to(DEV).clone().requires_grad_(True) for k in ("pred_logits", "pred_boxes", "proj_queries")}
+            ptok = g[tag + "_proj_tokens"].to(DEV).clone().requires_grad_(True)
+            layers = [{**{k: st[k][l] for k in st}, "proj_tokens": ptok, "tokenized": tokd} for l in range(L)]
+            o = dict(layers[-1])
+            o["aux_outputs"] = layers[:-1]
+            outs.append(o)
+            leaves.append((st, ptok))
+            tg.append(targets_to(targets, DEV))
+            pms.append(pm.to(DEV))
+        losses = criterion([{}, {}], outs, tg, pms, None)
+        total = sum(losses[k] * wd[k] for k in losses if k in wd)
+        total.backward()
+        vals = {k: float(v) for k, v in losses.items()}
+        grads = [t.grad.clone() for st, ptok in leaves for t in (*st.values(), ptok)]
+        return vals, grads
+
+    v0, g0 = run()
+    for k, v in g["losses"].items():  # the eager run itself reproduces the reference's 66 terms
+        assert abs(v0[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, v0[k], v)
+    assert abs(v0["noun_loss_ce"] - v0["sth_loss_ce"]) > 1e-6  # the two halves differ: aliasing would be visible
+    criterion.enable_cuda_graphs(True)
+    for _ in range(3):  # capture, replay, replay
+        v1, g1 = run()
+        assert v1 == v0
+        for a, b in zip(g0, g1):
+            assert torch.equal(a, b)
+    criterion.enable_cuda_graphs(False)

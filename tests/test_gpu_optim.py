@@ -97,3 +97,40 @@ def test_update_ema_matches_reference_formula():
                 assert rel_err(a, b) < 1e-6, k
             else:
                 assert torch.equal(a, b), k
+
+
+def test_adamw_many_rows_and_intact_state_on_overflow():
+    """Six parameter groups (the distillation recipe, main.py:351-386) with parameters lagging behind their group fit
+    one launch; when a step would need more hyper-parameter rows than a launch carries, it raises BEFORE any step
+    counter moves."""
+    from toist_b200.util import optim as O
+
+    torch.manual_seed(0)
+    ps = [torch.randn(257, device="cuda", requires_grad=True) for _ in range(12)]
+    ref = [p.detach().clone().requires_grad_(True) for p in ps]
+    groups = lambda xs: [{"params": xs[2 * i: 2 * i + 2], "lr": 1e-3 * (i + 1)} for i in range(6)]  # noqa: E731
+    o1, o2 = O.FusedAdamW(groups(ps), lr=1e-3, weight_decay=1e-2), torch.optim.AdamW(groups(ref), lr=1e-3, weight_decay=1e-2)
+    for step in range(4):
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            if i % 2 == 1 and step % 2 == 1:  # every second parameter skips every second step: 12 distinct rows
+                p.grad = r.grad = None
+                continue
+            g = torch.randn(257, device="cuda")
+            p.grad, r.grad = g.clone(), g.clone()
+        o1.step()
+        o2.step()
+    for p, r in zip(ps, ref):
+        assert torch.allclose(p, r, rtol=2e-6, atol=1e-7)
+    # overflow: 40 parameters in one group, each with its own step count
+    qs = [torch.randn(8, device="cuda", requires_grad=True) for _ in range(O.MAX_ADAM_ROWS + 8)]
+    o3 = O.FusedAdamW(qs, lr=1e-3)
+    for i, q in enumerate(qs):  # parameter i has taken i steps
+        o3.state[q]["step"] = i
+        o3.state[q]["exp_avg"] = torch.zeros_like(q)
+        o3.state[q]["exp_avg_sq"] = torch.zeros_like(q)
+        q.grad = torch.ones_like(q)
+    before = [q.detach().clone() for q in qs]
+    with pytest.raises(RuntimeError, match="state left untouched"):
+        o3.step()
+    assert [int(o3.state[q]["step"]) for q in qs] == list(range(len(qs)))
+    assert all(torch.equal(a, q) for a, q in zip(before, qs))

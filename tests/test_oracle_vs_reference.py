@@ -191,6 +191,13 @@ def test_lr_schedule_matches_reference():
             refmod.adjust_learning_rate(o1, epoch, step, total, a)
             ours.adjust_learning_rate(o2, epoch, step, total, a)
             assert o1.param_groups == o2.param_groups, (schedule, epoch, step, total)
+            # distillation recipe: student + noun model, six groups (util/optim.py:92-152)
+            d1, d2 = Opt(), Opt()
+            d1.param_groups = [{"lr": 0.0} for _ in range(6)]
+            d2.param_groups = [{"lr": 0.0} for _ in range(6)]
+            refmod.dis_adjust_learning_rate(d1, epoch, step, total, a)
+            ours.dis_adjust_learning_rate(d2, epoch, step, total, a)
+            assert d1.param_groups == d2.param_groups, (schedule, epoch, step, total)
 
 
 def test_gradients_match_reference(ref):

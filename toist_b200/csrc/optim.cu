@@ -108,8 +108,9 @@ struct AdamHyper {
   float bc2_sqrt;     // sqrt(1 - beta2^t)
   float pad;
 };
+constexpr int kMaxAdamRows = 32;  // (parameter group, step count) rows per launch: 6 groups in the distillation recipe
 struct AdamGroups {
-  AdamHyper g[8];
+  AdamHyper g[kMaxAdamRows];
 };
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamHyper& h) {
@@ -201,7 +202,8 @@ int toist_grad_clip_scale(const void* items_dev, int32_t n_items, int32_t total_
 int toist_adamw_step(const void* items_dev, int32_t n_items, int32_t total_blocks, const float* hyper_host,
                      int32_t n_groups, void* stream) {
   TOIST_REQUIRE(items_dev && hyper_host && n_items > 0 && total_blocks > 0, "toist_adamw_step: bad arguments");
-  TOIST_REQUIRE(n_groups >= 1 && n_groups <= 8, "toist_adamw_step: 1..8 parameter groups (got %d)", n_groups);
+  TOIST_REQUIRE(n_groups >= 1 && n_groups <= kMaxAdamRows, "toist_adamw_step: 1..%d hyper-parameter rows (got %d)", kMaxAdamRows,
+                n_groups);
   AdamGroups g;
   memset(&g, 0, sizeof(g));
   memcpy(g.g, hyper_host, sizeof(AdamHyper) * n_groups);

@@ -533,9 +533,11 @@ class SetCriterion(nn.Module):
             tok_pos = h2d(build_token_positive(outputs["tokenized"], targets, packed.t_max, ptok.shape[1]), dev)
         save = torch.is_grad_enabled() and (logits.requires_grad or boxes.requires_grad
                                             or (pq is not None and (pq.requires_grad or ptok.requires_grad)))
+        # `tag`: the distillation branch evaluates this stage twice per step (noun / sth); each pass needs its own
+        # captured graph, a shared one would overwrite the first pass's outputs and saved tensors on its second replay
         call = Call(self._stage, {}, save, graphs=self._graphs, w_class=float(self.matcher.cost_class),
                     w_bbox=float(self.matcher.cost_bbox), w_giou=float(self.matcher.cost_giou),
-                    eos_coef=float(self.eos_coef), temperature=float(self.temperature))
+                    eos_coef=float(self.eos_coef), temperature=float(self.temperature), tag=prefix)
         forced = self._forced_match(L, packed, dev) if self._forced is not None else None
         out, match_q, flags = run_stage(CRITERION, call, logits, boxes, pq, ptok, packed.boxes, packed.count,
                                         packed.posmap, tok_pos, nb, forced)
@@ -549,7 +551,7 @@ class SetCriterion(nn.Module):
             pm_ = outputs["pred_masks"]
             tgt_masks = pack_target_masks(targets, packed.t_max, dev)
             msave = torch.is_grad_enabled() and pm_.requires_grad
-            mcall = Call(self._stage_mask, {}, msave, graphs=self._graphs)
+            mcall = Call(self._stage_mask, {}, msave, graphs=self._graphs, tag=prefix)
             mask_out = run_stage(MASKLOSS, mcall, pm_, tgt_masks, match_q[L - 1].contiguous(), packed.count, nb)[0]
         losses = {}
         cells = _LossTerms.apply(out) if out.requires_grad else tuple(out.reshape(-1).unbind(0))

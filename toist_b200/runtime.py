@@ -358,29 +358,44 @@ class StageFn(torch.autograd.Function):
             return gi, gr, arena.buf
 
         sync = getattr(c, "grad_sync", None)
-        fresh = all(p.grad is None for p in c.stage.params)
+        params = c.stage.params
+        fresh = all(p.grad is None for p in params)
         if c.graphs is None:
             gin, grads, abuf = body(*gouts)
             pg = _grads_for(c.stage.names, grads, c.stage.shapes)
-            if sync is not None and c.req:
-                sync.reduce(c.stage.name, abuf, pg, blocking=not fresh)
         else:
             key = ("bwd", ctx.fkey, needs, _sig(gouts))
+            if not fresh:
+                # A gradient adopted from an earlier replay of this graph IS the graph's static buffer: the replay below
+                # would overwrite what was accumulated (or zeroed in place by zero_grad(set_to_none=False)).  Detach
+                # such gradients from the static memory first.
+                e = c.graphs.entries.get(key)
+                if e is not None:
+                    static = e.outputs[1]
+                    for n, p in zip(c.stage.names, params):
+                        t = static.get(n)
+                        if t is not None and p.grad is not None and p.grad.data_ptr() == t.data_ptr():
+                            p.grad = p.grad.clone()
             gin, grads, abuf = c.graphs.run(key, body, gouts)
             pg = _grads_for(c.stage.names, grads, c.stage.shapes)
-            # data parallel: one in-place all-reduce of the stage's gradient arena on a side stream (util/dist.py);
-            # with accumulated gradients the copies below must see the reduced values, so that case waits
-            if sync is not None and c.req:
-                sync.reduce(c.stage.name, abuf, pg, blocking=not fresh)
-            # The gradient buffers are static memory of the backward graph.  When no parameter holds a gradient yet
-            # (the usual zero_grad(set_to_none=True) loop) hand autograd fresh aliases: AccumulateGrad then adopts them
-            # without a copy.  With gradients already present (accumulation over several backward passes) the next
-            # replay would overwrite what was accumulated, so copies are returned instead.
-            if fresh:
-                pg = tuple(None if t is None else t.detach() for t in pg)
-            else:
-                pg = tuple(None if t is None else t.clone() for t in pg)
             gin = tuple(None if t is None else t.detach() for t in gin)
+        if not fresh:
+            # Gradient accumulation (several backward passes per optimizer step, DistributedDataParallel.no_sync()):
+            # fold what the parameters already hold into this pass's arena and hand the sum over as the new gradient.
+            # The all-reduce below then averages the ACCUMULATED gradient, which is what torch's wrapper exchanges on
+            # the first synchronised backward after no_sync() steps.
+            idx = [i for i, p in enumerate(params) if p.grad is not None and pg[i] is not None]
+            if idx:
+                torch._foreach_add_([pg[i] for i in idx], [params[i].grad for i in idx])
+                for i in idx:
+                    params[i].grad = None
+        # data parallel: one in-place all-reduce of the stage's gradient arena on a side stream (util/dist.py)
+        if sync is not None and c.req:
+            sync.reduce(c.stage.name, abuf, pg)
+        if c.graphs is not None:
+            # The gradient buffers are static memory of the backward graph: hand autograd fresh aliases, which
+            # AccumulateGrad adopts without a copy (every parameter's .grad is None at this point).
+            pg = tuple(None if t is None else t.detach() for t in pg)
         return (None, None) + tuple(gin) + pg
 
 

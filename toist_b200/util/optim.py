@@ -22,6 +22,7 @@ from .. import _lib
 from .misc import h2d
 
 _CHUNK = 2048
+MAX_ADAM_ROWS = 32  # csrc/optim.cu kMaxAdamRows: (parameter group, step count) rows one launch can carry
 
 
 def _stream() -> int:
@@ -76,10 +77,16 @@ def clip_grad_norm_(parameters, max_norm: float, norm_type: float = 2.0) -> torc
     grads = [p.grad for p in parameters if p.grad is not None]
     if not grads:
         return torch.zeros(())
-    key = id(grads[0].device), len(grads)
-    tab = _clip_tables.setdefault(key, (_Table(), {}))
-    items, n, blocks = tab[0].get([grads])
     dev = grads[0].device
+    key = (dev.type, dev.index, len(grads))
+    tab = _clip_tables.get(key)
+    if tab is None:
+        if len(_clip_tables) >= 16:  # a handful of (device, parameter count) combinations at most: stay bounded
+            _clip_tables.clear()
+        tab = _clip_tables[key] = (_Table(), {})
+    items, n, blocks = tab[0].get([grads])
+    if len(tab[1]) > 4:
+        tab[1].clear()
     scratch = tab[1].get(blocks)
     if scratch is None:
         scratch = tab[1][blocks] = (torch.empty(blocks, dtype=torch.float32, device=dev),)
@@ -129,8 +136,8 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        if len(self.param_groups) > 8:
-            raise ValueError("FusedAdamW supports up to 8 parameter groups")
+        if len(self.param_groups) > MAX_ADAM_ROWS:
+            raise ValueError(f"FusedAdamW supports up to {MAX_ADAM_ROWS} parameter groups")
         self._table = _Table()
 
     @torch.no_grad()
@@ -142,6 +149,7 @@ class FusedAdamW(torch.optim.Optimizer):
         ps, gs, ms, vs, grp = [], [], [], [], []
         rows = {}  # (group index, step count) -> hyper-parameter row: parameters skipped in some steps lag behind
         hyper = []
+        bump = []  # step counters move only after the row count has been validated (state stays intact on error)
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -152,8 +160,8 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                t = int(st["step"])
+                t = int(st["step"]) + 1
+                bump.append(st)
                 row = rows.get((gi, t))
                 if row is None:
                     row = rows[(gi, t)] = len(hyper)
@@ -165,8 +173,11 @@ class FusedAdamW(torch.optim.Optimizer):
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
                 grp.append(row)
-        if len(hyper) > 8:
-            raise RuntimeError("FusedAdamW: more than 8 distinct (parameter group, step count) combinations in one step")
+        if len(hyper) > MAX_ADAM_ROWS:
+            raise RuntimeError(f"FusedAdamW: {len(hyper)} distinct (parameter group, step count) combinations in one "
+                               f"step (limit {MAX_ADAM_ROWS}); optimizer state left untouched")
+        for st in bump:
+            st["step"] += 1
         hyper = np.asarray(hyper, dtype=np.float32).reshape(-1, 8)
         if ps:
             items, n, blocks = self._table.get([ps, gs, ms, vs], grp)
@@ -175,8 +186,8 @@ class FusedAdamW(torch.optim.Optimizer):
         return loss
 
 
-def adjust_learning_rate(optimizer, epoch: int, curr_step: int, num_training_steps: int, args) -> None:
-    """The four schedules of util/optim.py:29-90: a decay factor for (transformer, backbone) and one for the text encoder."""
+def _schedule_gammas(epoch: int, curr_step: int, num_training_steps: int, args):
+    """(gamma of transformer / backbone, gamma of the text encoder) for the four schedules of util/optim.py:29-90."""
     warm = round(args.fraction_warmup_steps * num_training_steps)
 
     def linear():
@@ -194,7 +205,23 @@ def adjust_learning_rate(optimizer, epoch: int, curr_step: int, num_training_ste
         gamma = text_gamma = linear()
     else:
         raise NotImplementedError(args.schedule)
+    return gamma, text_gamma
+
+
+def adjust_learning_rate(optimizer, epoch: int, curr_step: int, num_training_steps: int, args) -> None:
+    """util/optim.py:29-90: three parameter groups (transformer + heads, backbone, text encoder; main.py:351-367)."""
+    gamma, text_gamma = _schedule_gammas(epoch, curr_step, num_training_steps, args)
     base = [args.lr, args.lr_backbone, args.text_encoder_lr]
     assert len(optimizer.param_groups) == len(base)
     for group, lr, g in zip(optimizer.param_groups, base, [gamma, gamma, text_gamma]):
+        group["lr"] = lr * g
+
+
+def dis_adjust_learning_rate(optimizer, epoch: int, curr_step: int, num_training_steps: int, args) -> None:
+    """util/optim.py:92-152: the distillation recipe optimises the student and the noun (teacher) model together, six
+    parameter groups = the three groups of `adjust_learning_rate` once per model (main.py:368-386)."""
+    gamma, text_gamma = _schedule_gammas(epoch, curr_step, num_training_steps, args)
+    base = [args.lr, args.lr_backbone, args.text_encoder_lr] * 2
+    assert len(optimizer.param_groups) == len(base)
+    for group, lr, g in zip(optimizer.param_groups, base, [gamma, gamma, text_gamma] * 2):
         group["lr"] = lr * g
