@@ -179,22 +179,108 @@ def cpu_training_step_rate(batch: int, steps: int, warmup: int, threads: int):
     return batch / sec, sec
 
 
+def gpu_eager_step_rate(batch: int, steps: int, warmup: int, mode: str):
+    """The practical bar: the reference ALGORITHM (oracle/model.py, the
+    restatement pinned to the unmodified reference) run by stock eager PyTorch kernels (cuDNN / cuBLAS) on the same
+    B200, same batch, forward + criterion + backward.  mode: "fp32" (TF32 off), "tf32", "bf16" (torch.autocast).
+    Returns (images/s, seconds/step) timed with CUDA events."""
+    import torch
+
+    from oracle import model as O
+    from toist_b200.models import build_model
+    from toist_b200.synth import make_args, make_batch, targets_to
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    tf32 = mode != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cudnn.benchmark = True
+    args = make_args("resnet101", device="cpu")
+    torch.manual_seed(0)
+    model, _, _, weight_dict = build_model(args)
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    sd = {k: v.detach().to(dev) for k, v in model.state_dict().items()}
+    for n in trainable:
+        sd[n].requires_grad_(True)
+    del model
+    images, mask, captions, targets, pm = make_batch(batch, SIZE, TOKENS, seed=1234)
+    from toist_b200.tokenizer import CharTokenizer
+
+    tokd = CharTokenizer()(captions).to(dev)
+    images, mask, pm = images.to(dev), mask.to(dev), pm.to(dev)
+    targets = [{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in t.items()} for t in targets]
+    cfg = O.Config(backbone="resnet101")
+    amp = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16" else contextlib.nullcontext()
+
+    def one():
+        with amp:
+            mc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+            out = O.decode(sd, cfg, mc)
+            losses, _ = O.criterion(cfg, out, tokd, targets, pm)
+            total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+        for n in trainable:
+            sd[n].grad = None
+        total.backward()
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / steps
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+    return batch / sec, sec
+
+
+def practical_bar(steps: int = 5, warmup: int = 2):
+    res = {"what": "the reference algorithm (oracle port, pinned to the unmodified reference) in stock eager PyTorch on "
+                   "the same GPU: cuDNN / cuBLAS kernels, bs=8, 640^2, 16 tokens, fwd + criterion + bwd, CUDA events",
+           "unit": UNIT, "steps": steps}
+    for mode in ("fp32", "tf32", "bf16"):
+        try:
+            rate, sec = gpu_eager_step_rate(BATCH, steps, warmup, mode)
+            res[mode] = {"value": rate, "ms_per_step": sec * 1e3}
+        except Exception as e:  # pragma: no cover
+            res[mode] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return res
+
+
 def run_reference(a):
+    """`--impl reference`: the reference algorithm on the host cores (all threads), on OUR arm's config: the full
+    8-image batch of BASELINE configs[1] per step.  The reference itself is Python under /root/reference and does not
+    exist on the GPU box; the oracle port (fp32 torch, pinned to it forward and backward) stands in: kind "port"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_batch = 2
-    rate, sec = cpu_training_step_rate(sample_batch, a.steps, a.warmup, threads)
+    rate, sec = cpu_training_step_rate(BATCH, a.steps, a.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample_batch} of the 8 images per step"},
+        "config": {"workload": WORKLOAD, "global_batch": BATCH, "sample": "the full 8-image batch per step"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{a.steps} steps of {sample_batch} images (R101, 640^2, 16 tokens), fp32 torch CPU"},
+                         "sample": f"{a.steps} steps of {BATCH} images (R101, 640^2, 16 tokens), fp32 torch CPU"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(a):
+    """`--impl reference-gpu`: the practical bar as its own JSON line (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    res = practical_bar(a.steps, a.warmup)
+    best = max((v["value"] for v in res.values() if isinstance(v, dict) and "value" in v), default=None)
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 / tf32 / bf16-autocast", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH}, "practical_bar": res}
     print(json.dumps(line), flush=True)
 
 
@@ -403,10 +489,16 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, sec = cpu_training_step_rate(2, 2, 1, threads)
+        rate, sec = cpu_training_step_rate(BATCH, 2, 1, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "2 timed steps (+1 warm-up) of 2 images (R101, 640^2, 16 tokens), fp32 torch CPU, "
-                         f"{sec:.2f} s/step"}
+               "sample": f"2 timed steps (+1 warm-up) of the full {BATCH}-image batch (R101, 640^2, 16 tokens), fp32 "
+                         f"torch CPU, {sec:.2f} s/step"}
+    bar = None
+    if rank == 0 and world == 1 and not a.no_practical_bar:
+        try:
+            bar = practical_bar()
+        except Exception as e:  # the primary measurement above must still be printed
+            bar = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         line = {
@@ -422,7 +514,7 @@ def run_ours(a):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * a.steps,
             "gpu_launches_per_step": int(launches), "roofline": roof, "attention_roofline": attn,
             "step_tensor_frac": STEP_FLOPS_PER_IMAGE * BATCH / (ms * 1e-3 / a.steps) / 1e12 / peaks["tf_sustained"],
-            "optimizer": optim, "cpu_baseline": cpu,
+            "optimizer": optim, "cpu_baseline": cpu, "practical_bar": bar,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -434,8 +526,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-practical-bar", action="store_true", help="skip the eager-PyTorch-on-the-same-GPU comparison")
     ap.add_argument("--dropout", type=float, default=0.1, help="transformer dropout (reference default 0.1, main.py:137)")
     ap.add_argument("--torch-ddp", action="store_true", help="N > 1: wrap with torch's DistributedDataParallel instead of "
                                                              "toist_b200.util.dist.DistributedDataParallel")
@@ -447,6 +540,8 @@ def main():
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-gpu":
+        run_reference_gpu(a)
     else:
         run_ours(a)
 

@@ -306,7 +306,10 @@ def test_distillation_criterion_graph_replay_matches_eager(kd_gold):
     args = make_args("resnet50", distillation=True, softkd_loss=True, softkd_coef=50.0)
     _, criterion, _, wd = build_model(args)
     tok = CharTokenizer()
-    batches = {"noun": make_batch(**g["batch_noun"]), "sth": make_batch(**g["batch_sth"])}
+    def mk(b):
+        return make_batch(b["batch"], b["size"], b["tokens"], seed=b["seed"], pad=b["pad"])
+
+    batches = {"noun": mk(g["batch_noun"]), "sth": mk(g["batch_sth"])}
 
     def run():
         outs, leaves, tg, pms = [], [], [], []

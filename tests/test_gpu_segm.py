@@ -204,6 +204,11 @@ def test_mask_branch_cuda_graph_replay_matches_eager():
                 # atomically accumulated, bf16-stored values whose result is ~1e-8 here; its run-to-run noise was
                 # measured at 3e-3 .. 7e-3 (the test passed or failed with the atomics' arrival order)
                 tol = 2e-2 if "bbox_attention." in k else 5e-3
+                if k == "bbox_attention.k_linear.bias":
+                    # exact gradient is zero (softmax shift invariance): what is left is rounding noise, ~1e-10 against
+                    # 1e-8 .. 1e-7 for q_linear.bias; only its smallness is meaningful
+                    assert float(g1[k].abs().max()) <= 5e-2 * float(g1["bbox_attention.q_linear.bias"].abs().max() + 1e-30)
+                    continue
                 assert rel_err(g1[k], g0[k]) < tol or float(g0[k].abs().max()) < 1e-10, (k, rel_err(g1[k], g0[k]))
 
 

@@ -102,6 +102,39 @@ def config1(models, tok):
     with torch.no_grad():
         layers = list(out["aux_outputs"]) + [out]
         indices = [criterion.matcher(o, targets, pm) for o in layers]
+    # The number format's own floor, measured on the REFERENCE: the same step under torch's CPU bf16 autocast with the
+    # fp32 assignments forced (the reference calls the matcher for the main output first, then aux_0..aux_4,
+    # models/mdetr.py:993,1011), per-tensor distance of its gradients from the fp32 gradients.
+    order = [indices[-1]] + indices[:-1]
+    calls = iter(order)
+    orig_forward = criterion.matcher.forward
+    criterion.matcher.forward = lambda *a, **k: next(calls)
+    model.zero_grad(set_to_none=True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):  # the model only: the reference's criterion is not autocast-clean
+        mc16 = model(NestedTensor(images, mask), captions, encode_and_save=True)
+        out16 = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc16)
+
+    def f32(d):
+        return {k: (v.float() if isinstance(v, torch.Tensor) and v.is_floating_point() else
+                    [f32(a) for a in v] if k == "aux_outputs" else v) for k, v in d.items()}
+
+    out16 = f32(out16)
+    losses16 = criterion(mc16, out16, targets, pm, None)
+    total16 = sum(losses16[k] * weight_dict[k] for k in losses16 if k in weight_dict)
+    total16.backward()
+    criterion.matcher.forward = orig_forward
+    from conftest import rel_err
+
+    floor = {n: rel_err(strided_sample(p.grad.float()), strided_sample(grads[n]))
+             for n, p in model.named_parameters() if p.grad is not None and n in grads and float(grads[n].norm()) > 0}
+    fwd_floor = {"img_memory": rel_err(mc16["img_memory"].float(), mc["img_memory"]),
+                 "pred_logits": rel_err(out16["pred_logits"].float(), out["pred_logits"]),
+                 "pred_boxes": rel_err(out16["pred_boxes"].float(), out["pred_boxes"]),
+                 "proj_queries": rel_err(out16["proj_queries"].float(), out["proj_queries"]),
+                 "proj_tokens": rel_err(out16["proj_tokens"].float(), out["proj_tokens"])}
+    print("reference under CPU bf16 autocast vs fp32, forward:", {k: f"{v:.3e}" for k, v in fwd_floor.items()})
+    fl = sorted(floor.values())
+    print(f"reference under CPU bf16 autocast vs fp32, gradients: median {fl[len(fl) // 2]:.3e}, max {fl[-1]:.3e}")
     sd = model.state_dict()
     small = ("contrastive_align_projection_", "class_embed.", "bbox_embed.", "query_embed.", "input_proj.bias",
              "transformer.resizer.", "transformer.decoder.norm.")
@@ -125,7 +158,10 @@ def config1(models, tok):
             "norm": {k: float(g.double().norm()) for k, g in grads.items()},
             "sample": {k: strided_sample(g) for k, g in grads.items()},
             "full": {k: g.clone() for k, g in grads.items() if k.startswith(small)},
+            # rel_err (same strided sample) of the reference's own gradients under torch CPU bf16 autocast
+            "bf16_floor": floor,
         },
+        "bf16_forward_floor": fwd_floor,
     }
 
 
