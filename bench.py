@@ -311,6 +311,8 @@ def run_ours(a):
     if not a.no_graphs:  # replay each stage's launch sequence as a CUDA graph (same public API, fixed shapes)
         model.enable_cuda_graphs(True)
         criterion.enable_cuda_graphs(True)
+    if not a.no_direct:  # stages assign Parameter.grad themselves (no per-parameter autograd edges), see runtime.StageFn
+        model.enable_direct_grads(True)
     ddp = None
     if world > 1:
         # main.py:336 wraps the model in DistributedDataParallel(model, device_ids=[gpu], find_unused_parameters=True).
@@ -324,6 +326,13 @@ def run_ours(a):
 
             ddp = FlatDDP(model, device_ids=[local], find_unused_parameters=True)
     net = ddp if ddp is not None else model
+    from toist_b200.util.optim import FusedAdamW
+
+    named = list(model.named_parameters())
+    optimizer = FusedAdamW(  # the three parameter groups of main.py:351-367; the step calls its zero_grad like engine.py:86
+        [{"params": [p for n, p in named if "backbone" not in n and "text_encoder" not in n and p.requires_grad]},
+         {"params": [p for n, p in named if "backbone" in n and p.requires_grad], "lr": 1e-5},
+         {"params": [p for n, p in named if "text_encoder" in n and p.requires_grad], "lr": 5e-5}], lr=1e-4, weight_decay=1e-4)
 
     images, mask, captions, targets, pm = make_batch(BATCH, SIZE, TOKENS, seed=1234 + rank)
     h_images = images.pin_memory()
@@ -339,7 +348,7 @@ def run_ours(a):
         out = net(samples, captions, encode_and_save=False, memory_cache=mc)
         losses = criterion(mc, out, tg, pmap, None)
         total = sum(losses[k] * weight_dict[k] for k in losses.keys() if k in weight_dict)
-        model.zero_grad(set_to_none=True)  # optimizer.zero_grad() sits right before backward() (engine.py:86-87)
+        optimizer.zero_grad()  # right before backward(), as in engine.py:86-87
         total.backward()
         return total
 
@@ -506,7 +515,7 @@ def run_ours(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": a.dropout,
-                       "cuda_graphs": not a.no_graphs,
+                       "cuda_graphs": not a.no_graphs, "direct_param_grads": not a.no_direct,
                        "l2": "320 MB buffer rewritten between steps (> 126 MB L2)",
                        "parallelism": f"dp{world}" + ((" (torch DDP bucketed NCCL all-reduce)" if a.torch_ddp else
                                                               " (flat NCCL all-reduce per backward stage, side stream)")
@@ -536,6 +545,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-launch roofline pass (quick A/B runs)")
     ap.add_argument("--dump-shapes", default="", help="write one JSON line per distinct tensor-core launch shape")
     ap.add_argument("--no-graphs", action="store_true", help="issue every kernel launch from Python (no CUDA graphs)")
+    ap.add_argument("--no-direct", action="store_true", help="route parameter gradients through autograd (A/B of "
+                                                             "MDETR.enable_direct_grads)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else max(a.warmup, 1)
     if a.impl == "reference":

@@ -173,3 +173,52 @@ def test_gradient_accumulation_in_graph_mode():
         assert rel_err(acc[n], g1[n] + g2[n]) < 1e-3, n            # split-K atomics: order-dependent last bits
         assert rel_err(after_inplace_zero[n], g1[n]) < 1e-3, n
     assert set(acc) == set(g1)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_direct_param_grads_match_autograd_routed(graphs):
+    """MDETR.enable_direct_grads: the stages assign Parameter.grad themselves.  Same gradients as the autograd-routed
+    default (bit for bit except split-K atomics), same accumulation semantics, frozen / unused parameters stay None."""
+    from conftest import rel_err
+    from toist_b200.models import build_model
+    from toist_b200.synth import make_args, make_batch, targets_to
+    from toist_b200.util.misc import NestedTensor
+
+    torch.manual_seed(0)
+    model, criterion, _, wd = build_model(make_args("resnet50"))
+    model.cuda().eval()
+    if graphs:
+        model.enable_cuda_graphs(True)
+        criterion.enable_cuda_graphs(True)
+    batches = [make_batch(2, 160, 8, seed=s) for s in (21, 22)]
+
+    def backward(b):
+        images, mask, captions, targets, pm = b
+        s = NestedTensor(images.cuda(), mask.cuda())
+        mc = model(s, captions, encode_and_save=True)
+        out = model(s, captions, encode_and_save=False, memory_cache=mc)
+        losses = criterion(mc, out, targets_to(targets, "cuda"), pm.cuda(), None)
+        sum(losses[k] * wd[k] for k in losses if k in wd).backward()
+        torch.cuda.synchronize()
+
+    def grads():
+        return {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    res = {}
+    for direct in (False, True):
+        model.enable_direct_grads(direct)
+        for rep in range(2):  # second round replays
+            model.zero_grad(set_to_none=True)
+            backward(batches[0])
+            g1 = grads()
+            backward(batches[1])  # accumulate on top
+            acc = grads()
+        res[direct] = (g1, acc)
+    (a1, aacc), (d1, dacc) = res[False], res[True]
+    assert set(a1) == set(d1) and len(d1) > 300
+    assert "transformer.text_encoder.pooler.dense.weight" not in d1 and "backbone.0.body.layer1.0.conv1.weight" not in d1
+    for k in a1:
+        assert rel_err(d1[k], a1[k]) < 1e-3 or float(a1[k].abs().max()) < 1e-12, k
+        assert rel_err(dacc[k], aacc[k]) < 1e-3 or float(aacc[k].abs().max()) < 1e-12, k
+    k = "transformer.decoder.layers.2.linear1.weight"
+    assert rel_err(dacc[k], d1[k]) > 1e-2  # the second pass really added something

@@ -8,7 +8,7 @@ the reference's names so state dicts are interchangeable.  Everything numerical 
 from __future__ import annotations
 
 import os
-
+from collections import OrderedDict
 from typing import Dict, List, Optional
 
 import torch
@@ -46,6 +46,9 @@ class ModelRuntime:
         self.seed: Optional[torch.Tensor] = None  # device int64 [1]: dropout seed of the current step
         self.grad_sync = None  # set by util.dist.DistributedDataParallel
         self.dirty = True  # parameters may have moved / been reloaded since the shadow bank was built
+        self.tok_cache = OrderedDict()
+        self.direct = False  # MDETR.enable_direct_grads: stages assign Parameter.grad themselves
+        self.anchor: Optional[torch.Tensor] = None
 
     def __deepcopy__(self, memo):  # the EMA copy (main.py:322) rebuilds its own
         return ModelRuntime()
@@ -84,6 +87,9 @@ class ModelRuntime:
         self.steps = getattr(self, "steps", 0) + 1
         dirty = self.dirty or self.steps % 64 == 0
         self.dirty = False
+        if dirty:
+            for st in self.stages.values():
+                st.invalidate()  # requires_grad flags may have changed
         self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body, dirty)
         if self.graphs is not None and sig is not None and sig != self.bank._sig:
             self.graphs.clear()  # shadow buffers moved: captured pointers are stale
@@ -96,7 +102,30 @@ class ModelRuntime:
         c = Call(self.stages[name], self.bank.w, save, graphs=graphs, drop_p=drop_p,
                  seed=self.seed, **kw)
         c.grad_sync = self.grad_sync  # util.dist.FlatGradSync when wrapped for data-parallel training, else None
+        if self.direct:
+            dev = next(iter(self.stages[name].params)).device if self.stages[name].params else None
+            if self.anchor is None or self.anchor.device != dev:
+                self.anchor = torch.zeros(1, device=dev, requires_grad=True)
+            c.anchor = self.anchor
         return c
+
+    def tokenize(self, tokenizer, captions, dev):
+        """models/transformer.py:129 tokenises the captions on the host every step and copies the ids to the device.
+        TOIST's pronoun captions are a small closed set (14 task verbs x 'something', datasets/tdod.py:23-38), so the
+        device-resident result is cached by caption tuple (LRU, 512 batches)."""
+        key = (tuple(captions), dev)
+        hit = self.tok_cache.get(key)
+        if hit is not None:
+            self.tok_cache.move_to_end(key)
+            return hit
+        tokenized = tokenizer.batch_encode_plus(list(captions), padding="longest", return_tensors="pt").to(dev)
+        ids = tokenized["input_ids"].contiguous()
+        attn = tokenized["attention_mask"].to(torch.int64).contiguous()
+        hit = (tokenized, ids, attn, attn.ne(1))
+        self.tok_cache[key] = hit
+        if len(self.tok_cache) > 512:
+            self.tok_cache.popitem(last=False)
+        return hit
 
     def new_step_seed(self, device) -> None:
         """Draws the dropout seed of this step from torch's CPU generator (reproducible under torch.manual_seed)."""
@@ -158,6 +187,16 @@ class MDETR(nn.Module):
         self._rt.graphs_text = GraphCache() if on else None
         return self
 
+    def enable_direct_grads(self, on: bool = True) -> "MDETR":
+        """Let every backward stage assign its parameters' `.grad` itself (views of the stage's flat gradient arena)
+        instead of returning ~1000 gradients through autograd: removes several ms of host time per step
+        (Function.apply over all parameters + one AccumulateGrad node per parameter).  Semantics kept: `.grad` is
+        None -> set; `.grad` present -> accumulated.  NOT compatible with torch.nn.parallel.DistributedDataParallel
+        (its reducer listens on AccumulateGrad) nor with per-parameter gradient hooks; toist_b200.util.dist.
+        DistributedDataParallel switches this mode on by itself."""
+        self._rt.direct = bool(on)
+        return self
+
     def _grad_wanted(self) -> bool:
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
@@ -179,11 +218,7 @@ class MDETR(nn.Module):
         E = self.transformer.d_model
         text_stream = None
         if isinstance(captions[0], str):
-            tokenized = self.transformer.tokenizer.batch_encode_plus(captions, padding="longest",
-                                                                     return_tensors="pt").to(dev)
-            ids = tokenized["input_ids"].contiguous()
-            attn = tokenized["attention_mask"].to(torch.int64).contiguous()
-            text_attention_mask = attn.ne(1)
+            tokenized, ids, attn, text_attention_mask = rt.tokenize(self.transformer.tokenizer, captions, dev)
             # The text branch (12 RoBERTa layers on B x L <= a few hundred rows: ~150 tiny, latency-bound launches) does
             # not depend on the image: it runs on its own stream next to the backbone's large kernels, forward and
             # (autograd replays a node's backward on its forward stream) backward.  TOIST_TEXT_STREAM=0 disables.

@@ -103,6 +103,10 @@ class DETRsegm(nn.Module):
         self._rt.graphs = GraphCache() if on else None
         return self
 
+    def enable_direct_grads(self, on: bool = True) -> "DETRsegm":
+        self.detr.enable_direct_grads(on)
+        return self
+
     def _refresh(self) -> None:
         rt = self._rt
         if rt.stage is None:
@@ -111,6 +115,8 @@ class DETRsegm(nn.Module):
         rt.steps += 1
         dirty = rt.dirty or rt.steps % 64 == 0
         rt.dirty = False
+        if dirty:
+            rt.stage.invalidate()
         sig = rt.bank._sig
         rt.bank.ensure(self, None, None, dirty, only=("bbox_attention.", "mask_head."))
         if rt.graphs is not None and sig is not None and sig != rt.bank._sig:
@@ -132,6 +138,10 @@ class DETRsegm(nn.Module):
         save = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         call = Call(rt.stage, rt.bank.w, save, graphs=rt.graphs, n_dec_layers=int(hs.shape[0]), seq_len=int(mem.shape[0]))
         call.grad_sync = getattr(rt, "grad_sync", None)
+        if self.detr._rt.direct and rt.stage.params:
+            if self.detr._rt.anchor is None:
+                self.detr._rt.anchor = torch.zeros(1, device=rt.stage.params[0].device, requires_grad=True)
+            call.anchor = self.detr._rt.anchor
         pred = run_stage(MASKHEAD, call, hs, mem, memory_cache["_b200_src_proj"], feats[2], feats[1], feats[0],
                          memory_cache["_b200_small_mask"])[0]
         out["pred_masks"] = pred

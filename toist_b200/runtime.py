@@ -202,6 +202,9 @@ def _grads_for(names: Sequence[str], g: Dict[str, torch.Tensor], params_shapes) 
     return tuple(out)
 
 
+_EMPTY: frozenset = frozenset()
+
+
 class Stage:
     """Static description of one autograd stage: which parameters it owns (ordered) and configuration."""
 
@@ -222,7 +225,27 @@ class Stage:
         return st
 
     def req(self) -> Set[str]:
-        return requires(self.names, self.params, torch.is_grad_enabled())
+        """Names of this stage's parameters that want a gradient (empty under no_grad).  Cached: walking ~1000
+        parameters per step costs more than several graph replays; `invalidate()` (ModelRuntime.refresh: after
+        Module._apply / load_state_dict, and every 64 steps) rescans."""
+        if not torch.is_grad_enabled():
+            return _EMPTY
+        r = self.__dict__.get("_req")
+        if r is None:
+            r = self.__dict__["_req"] = frozenset(requires(self.names, self.params, True))
+        return r
+
+    def invalidate(self) -> None:
+        self.__dict__.pop("_req", None)
+        self.__dict__.pop("_numel", None)
+
+    def arena_numel(self, req) -> int:
+        """fp32 elements of the gradient arena of one backward pass: every wanted gradient, 256-byte aligned."""
+        cache = self.__dict__.setdefault("_numel", {})
+        n = cache.get(req)
+        if n is None:
+            n = cache[req] = sum((_numel(shp) + 63) // 64 * 64 for nm, shp in zip(self.names, self.shapes) if nm in req)
+        return n
 
 
 class Call:
@@ -231,7 +254,7 @@ class Call:
     def __init__(self, stage: Stage, w: Dict[str, torch.Tensor], save: bool, graphs: "Optional[GraphCache]" = None,
                  drop_p: float = 0.0, seed: Optional[torch.Tensor] = None, **kw):
         self.stage, self.w = stage, w
-        self.req = stage.req() if save else set()
+        self.req = stage.req() if save else _EMPTY
         self.save = save  # keep activations for a backward pass (some tensor upstream or here wants a gradient)
         self.graphs = graphs
         self.drop_p = float(drop_p) if seed is not None else 0.0  # training-mode dropout probability of this stage
@@ -240,7 +263,7 @@ class Call:
         self.__dict__.update(kw)
 
     def signature(self) -> tuple:
-        return (self.stage.name, self.save, frozenset(self.req), self.extra, self.drop_p)
+        return (self.stage.name, self.save, self.req, self.extra, self.drop_p)
 
     def drop(self, base: int) -> Optional[Bk.Drop]:
         return Bk.Drop(self.drop_p, self.seed, base) if self.drop_p > 0.0 else None
@@ -248,7 +271,7 @@ class Call:
 
 # ------------------------------------------------------------------------------------------------ CUDA graphs
 class _GraphEntry:
-    __slots__ = ("graph", "static_in", "outputs", "launches")
+    __slots__ = ("graph", "static_in", "outputs", "launches", "aux")
 
 
 class GraphCache:
@@ -301,7 +324,7 @@ class GraphCache:
         if self.pool is None:
             self.pool = g.pool()
         e = _GraphEntry()
-        e.graph, e.static_in, e.outputs, e.launches = g, static_in, outputs, K.launches() - n0
+        e.graph, e.static_in, e.outputs, e.launches, e.aux = g, static_in, outputs, K.launches() - n0, None
         self.entries[key] = e
         g.replay()
         return outputs
@@ -329,6 +352,7 @@ class StageFn(torch.autograd.Function):
         inputs = [a.contiguous() if isinstance(a, torch.Tensor) and spec.contiguous_inputs else a for a in args[:n_in]]
         ctx.spec, ctx.c = spec, c
         ctx.n_in = n_in
+        ctx.n_tail = len(args) - n_in  # the stage's parameters, or ONE anchor tensor in direct-gradient mode
         if c.graphs is None:
             outs, saved = spec.fwd(c, *inputs)
             ctx.fkey = None
@@ -350,7 +374,7 @@ class StageFn(torch.autograd.Function):
         needs = tuple(ctx.needs_input_grad[2: 2 + ctx.n_in])
         gouts = [None if g is None else g.contiguous() for g in gouts]
         dev = next((g.device for g in gouts if g is not None), None)
-        numel = sum((_numel(shp) + 63) // 64 * 64 for n, shp in zip(c.stage.names, c.stage.shapes) if n in c.req)
+        numel = c.stage.arena_numel(c.req)
 
         def body(*g):
             with Bk.zero_arena(numel, dev) as arena, K.wgrad_lanes():
@@ -358,7 +382,7 @@ class StageFn(torch.autograd.Function):
             return gi, gr, arena.buf
 
         sync = getattr(c, "grad_sync", None)
-        params = c.stage.params
+        params = c.stage.params if ctx.n_tail else ()
         fresh = all(p.grad is None for p in params)
         if c.graphs is None:
             gin, grads, abuf = body(*gouts)
@@ -377,7 +401,10 @@ class StageFn(torch.autograd.Function):
                         if t is not None and p.grad is not None and p.grad.data_ptr() == t.data_ptr():
                             p.grad = p.grad.clone()
             gin, grads, abuf = c.graphs.run(key, body, gouts)
-            pg = _grads_for(c.stage.names, grads, c.stage.shapes)
+            e = c.graphs.entries[key]
+            if e.aux is None:  # the gradient buffers are static: their per-parameter views are made once per graph
+                e.aux = _grads_for(c.stage.names, grads, c.stage.shapes)
+            pg = e.aux
             gin = tuple(None if t is None else t.detach() for t in gin)
         if not fresh:
             # Gradient accumulation (several backward passes per optimizer step, DistributedDataParallel.no_sync()):
@@ -392,11 +419,51 @@ class StageFn(torch.autograd.Function):
         # data parallel: one in-place all-reduce of the stage's gradient arena on a side stream (util/dist.py)
         if sync is not None and c.req:
             sync.reduce(c.stage.name, abuf, pg)
+        if ctx.n_tail == 0:
+            return (None, None) + tuple(gin)
+        if getattr(c, "anchor", None) is not None and ctx.n_tail == 1:
+            # Direct mode: the stage owns its parameters' .grad.  Routing ~1000 parameter edges through autograd
+            # (Function.apply inputs, AccumulateGrad per parameter) costs several ms of host time per step; here the
+            # views of the arena are assigned in one loop and autograd only sees the anchor.
+            for p, t in zip(params, pg):
+                if t is not None:
+                    p.grad = t
+            _direct_join.note()
+            return (None, None) + tuple(gin) + (None,)
         if c.graphs is not None:
             # The gradient buffers are static memory of the backward graph: hand autograd fresh aliases, which
             # AccumulateGrad adopts without a copy (every parameter's .grad is None at this point).
             pg = tuple(None if t is None else t.detach() for t in pg)
         return (None, None) + tuple(gin) + pg
+
+
+class _DirectJoin:
+    """Stream hygiene of direct-gradient mode.  autograd runs a node's backward on the stream its forward ran on (the
+    text branch has its own) and, for gradients it accumulates itself, makes the caller's stream wait for those
+    streams when backward() returns.  Gradients assigned by the stages bypass that, so every stage records an event
+    on its stream and one engine callback per backward pass makes the caller's stream wait for them."""
+
+    def __init__(self):
+        self.events: List[torch.cuda.Event] = []
+        self.armed = False
+
+    def note(self) -> None:
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events.append(ev)
+        if not self.armed:
+            self.armed = True
+            torch.autograd.Variable._execution_engine.queue_callback(self.join)
+
+    def join(self) -> None:
+        cur = torch.cuda.current_stream()
+        for ev in self.events:
+            cur.wait_event(ev)
+        self.events.clear()
+        self.armed = False
+
+
+_direct_join = _DirectJoin()
 
 
 class Spec:
@@ -406,6 +473,10 @@ class Spec:
 
 
 def run_stage(spec: Spec, c: Call, *inputs):
+    if not c.req:  # no parameter of this stage wants a gradient (no_grad, eval loops, frozen detector): inputs only
+        return StageFn.apply(spec, c, *inputs)
+    if getattr(c, "anchor", None) is not None:
+        return StageFn.apply(spec, c, *inputs, c.anchor)
     return StageFn.apply(spec, c, *inputs, *c.stage.params)
 
 

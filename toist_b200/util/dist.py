@@ -94,6 +94,7 @@ class DistributedDataParallel(nn.Module):
         if rt is None or not hasattr(rt, "grad_sync"):
             raise TypeError("toist_b200.util.dist.DistributedDataParallel wraps toist_b200 models (MDETR / DETRsegm)")
         rt.grad_sync = self.grad_sync
+        rt.direct = True  # stages assign .grad themselves: nothing here listens on AccumulateGrad (runtime.StageFn)
         covered = ()
         if inner is not module:  # the mask branch is a stage of its own
             module._rt.grad_sync = self.grad_sync

@@ -140,6 +140,15 @@ class FusedAdamW(torch.optim.Optimizer):
             raise ValueError(f"FusedAdamW supports up to {MAX_ADAM_ROWS} parameter groups")
         self._table = _Table()
 
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """engine.py:86.  With `set_to_none` (torch's default) this is one attribute store per parameter; torch's own
+        loop (per-parameter hook / foreach bookkeeping) costs 1.5 ms per step for this model's ~950 tensors."""
+        if not set_to_none:
+            return super().zero_grad(set_to_none=False)
+        for group in self.param_groups:
+            for p in group["params"]:
+                p.grad = None
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None

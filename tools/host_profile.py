@@ -28,12 +28,19 @@ def main():
     model.cuda().train()
     model.enable_cuda_graphs(True)
     criterion.enable_cuda_graphs(True)
+    import os
+
+    from toist_b200.util.optim import FusedAdamW
+
+    if os.environ.get("TOIST_DIRECT", "1") != "0":
+        model.enable_direct_grads(True)
+    optimizer = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
     images, mask, captions, targets, pm = make_batch(8, 640, 16)
     s = NestedTensor(images.cuda(), mask.cuda())
     tg, pmd = targets_to(targets, "cuda"), pm.cuda()
 
     def step():
-        model.zero_grad(set_to_none=True)
+        optimizer.zero_grad()
         mc = model(s, captions, encode_and_save=True)
         out = model(s, captions, encode_and_save=False, memory_cache=mc)
         losses = criterion(mc, out, tg, pmd, None)
