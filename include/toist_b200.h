@@ -400,6 +400,32 @@ int toist_adamw_step(const void* items_dev, int32_t n_items, int32_t total_block
 int toist_ema_update(const void* items_dev, int32_t n_items, int32_t total_blocks, float decay, float one_minus_decay,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The two ends of the path (csrc/io.cu).
+ *
+ * Batch assembly -- replaces NestedTensor.from_tensor_list's per-image copy + mask fill (util/misc.py:185-209) and,
+ * for the u8 entry, ToTensor + Normalize of the CPU data workers (datasets/transforms.py:257-272):
+ *   image_ptrs [B] DEVICE array of device pointers, image_hw [B, 2] DEVICE int32 (height, width);
+ *   u8 images are HWC (3 channels), f32 images CHW; out [B, C, H, W] f32 zero padded, mask [B, H, W] u8 (1 = padding);
+ *   mean3_host / std3_host: 3 HOST floats.  Arithmetic per pixel: ((x / 255) - mean) / std, each step rounded once.
+ * PostProcess (models/postprocessors.py:15-58): scores = 1 - softmax(logits)[..., -1], labels = 1, boxes cxcywh ->
+ *   xyxy * (w, h, w, h) with sizes [B, 2] = (height, width) as f32 OR i64 (pass the other as null); optional
+ *   is_final [B, Q] -> scores_refexp = scores * sigmoid(is_final).
+ * PostProcessSegm (models/postprocessors.py:61-109), one image per call: pred_masks [Q, mask_h, mask_w] f32 ->
+ *   bilinear to (stage1_h, stage1_w) [the padded batch size], crop to (crop_h, crop_w), bilinear to (out_h, out_w),
+ *   sigmoid > threshold -> out [Q, out_h, out_w] u8.  Both interpolations align_corners = false, fused into one pass.
+ * ------------------------------------------------------------------------------------------------------------ */
+int toist_pad_normalize_u8(const uint64_t* image_ptrs, const int32_t* image_hw, float* out, uint8_t* mask, int32_t batch,
+                           int32_t height, int32_t width, const float* mean3_host, const float* std3_host, void* stream);
+int toist_pad_batch_f32(const uint64_t* image_ptrs, const int32_t* image_hw, float* out, uint8_t* mask, int32_t batch,
+                        int32_t channels, int32_t height, int32_t width, void* stream);
+int toist_postprocess_boxes(const float* logits, const float* boxes, const float* sizes_f32, const int64_t* sizes_i64,
+                            const float* is_final, float* scores, int64_t* labels, float* out_boxes, float* scores_refexp,
+                            int32_t batch, int32_t n_queries, int32_t n_classes, void* stream);
+int toist_postprocess_masks(const float* pred_masks, uint8_t* out, int32_t n_queries, int32_t mask_h, int32_t mask_w,
+                            int32_t stage1_h, int32_t stage1_w, int32_t crop_h, int32_t crop_w, int32_t out_h,
+                            int32_t out_w, float threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

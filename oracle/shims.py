@@ -42,6 +42,7 @@ def _install_import_shims() -> None:
             orig = getattr(torchvision.models, name)
 
             def wrapped(*a, pretrained=False, _orig=orig, **k):
+                k.pop("weights", None)  # toist_b200's own builder passes weights=None itself
                 return _orig(*a, weights=None, **k)
 
             setattr(torchvision.models, name, wrapped)

@@ -1187,3 +1187,81 @@ def cdist_l1(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
     _ck(_L().toist_cdist_l1(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], b.shape[0], a.shape[1], _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ path ends (csrc/io.cu)
+def _image_table(images: Sequence[torch.Tensor], hw: Sequence[Tuple[int, int]], dev):
+    """Device arrays (pointers [B] uint64, sizes [B, 2] int32) describing a list of per-image device tensors."""
+    import numpy as np
+
+    from .util.misc import h2d
+
+    ptrs = torch.from_numpy(np.asarray([t.data_ptr() for t in images], dtype=np.int64))
+    sizes = torch.tensor([[int(h), int(w)] for h, w in hw], dtype=torch.int32)
+    return h2d(ptrs, dev), h2d(sizes, dev)
+
+
+def pad_normalize_u8(images: Sequence[torch.Tensor], mean, std, height: int, width: int):
+    """uint8 HWC images (CUDA, contiguous, 3 channels) -> (fp32 [B, 3, H, W] normalised + zero padded, uint8 mask
+    [B, H, W] with 1 = padding): ToTensor + Normalize + NestedTensor padding in one launch."""
+    dev = images[0].device
+    for t in images:
+        assert t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and t.dim() == 3 and t.shape[2] == 3
+    B = len(images)
+    ptrs, sizes = _image_table(images, [(t.shape[0], t.shape[1]) for t in images], dev)
+    out = torch.empty((B, 3, height, width), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, height, width), dtype=torch.uint8, device=dev)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    _ck(_L().toist_pad_normalize_u8(ptrs.data_ptr(), sizes.data_ptr(), out.data_ptr(), mask.data_ptr(), B, height, width,
+                                    C.cast(m, C.c_void_p), C.cast(s, C.c_void_p), _stream()))
+    return out, mask
+
+
+def pad_batch_f32(images: Sequence[torch.Tensor], height: int, width: int):
+    """fp32 CHW images (CUDA, contiguous) -> (zero padded [B, C, H, W], uint8 mask [B, H, W]) in one launch."""
+    dev = images[0].device
+    c = images[0].shape[0]
+    for t in images:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 3 and t.shape[0] == c
+    B = len(images)
+    ptrs, sizes = _image_table(images, [(t.shape[1], t.shape[2]) for t in images], dev)
+    out = torch.empty((B, c, height, width), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, height, width), dtype=torch.uint8, device=dev)
+    _ck(_L().toist_pad_batch_f32(ptrs.data_ptr(), sizes.data_ptr(), out.data_ptr(), mask.data_ptr(), B, c, height, width,
+                                 _stream()))
+    return out, mask
+
+
+def postprocess_boxes(logits: torch.Tensor, boxes: torch.Tensor, target_sizes: torch.Tensor,
+                      is_final: Optional[torch.Tensor] = None):
+    """models/postprocessors.py:15-58 -> (scores [B, Q], labels [B, Q] int64, boxes xyxy absolute [B, Q, 4], scores_refexp)."""
+    B, Q, Cc = logits.shape
+    logits, boxes = logits.float().contiguous(), boxes.float().contiguous()
+    ts = target_sizes.contiguous()
+    assert ts.shape == (B, 2) and ts.is_cuda
+    if ts.dtype not in (torch.int64, torch.float32):
+        ts = ts.to(torch.float32)
+    dev = logits.device
+    scores = torch.empty((B, Q), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, Q), dtype=torch.int64, device=dev)
+    out = torch.empty((B, Q, 4), dtype=torch.float32, device=dev)
+    fin = ref = None
+    if is_final is not None:
+        fin = is_final.float().contiguous().view(B, Q)
+        ref = torch.empty((B, Q), dtype=torch.float32, device=dev)
+    _ck(_L().toist_postprocess_boxes(logits.data_ptr(), boxes.data_ptr(), ts.data_ptr() if ts.dtype == torch.float32 else None,
+                                     ts.data_ptr() if ts.dtype == torch.int64 else None, _ptr(fin), scores.data_ptr(),
+                                     labels.data_ptr(), out.data_ptr(), _ptr(ref), B, Q, Cc, _stream()))
+    return scores, labels, out, ref
+
+
+def postprocess_masks(pred: torch.Tensor, stage1_hw, crop_hw, out_hw, threshold: float) -> torch.Tensor:
+    """pred [Q, h, w] fp32 of one image -> bool [Q, out_h, out_w] (models/postprocessors.py:79-107, fused)."""
+    assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    Q, hm, wm = pred.shape
+    out = torch.empty((Q, int(out_hw[0]), int(out_hw[1])), dtype=torch.uint8, device=pred.device)
+    _ck(_L().toist_postprocess_masks(pred.data_ptr(), out.data_ptr(), Q, hm, wm, int(stage1_hw[0]), int(stage1_hw[1]),
+                                     int(crop_hw[0]), int(crop_hw[1]), int(out_hw[0]), int(out_hw[1]), float(threshold),
+                                     _stream()))
+    return out.view(torch.bool)

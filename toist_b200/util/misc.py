@@ -35,12 +35,37 @@ class NestedTensor(object):
             w = (w + 127) // 128 * 128
         b = len(tensor_list)
         dtype, device = tensor_list[0].dtype, tensor_list[0].device
+        if device.type == "cuda" and dtype == torch.float32:
+            # one launch for the whole batch (the reference issues one copy and one mask fill per image)
+            from .. import kernels as K
+
+            tensor, mask_u8 = K.pad_batch_f32([t.contiguous() for t in tensor_list], h, w)
+            return cls(tensor, mask_u8.view(torch.bool))
         tensor = torch.zeros((b, c, h, w), dtype=dtype, device=device)
         mask = torch.ones((b, h, w), dtype=torch.bool, device=device)
         for i, img in enumerate(tensor_list):
             tensor[i, :, : img.shape[1], : img.shape[2]].copy_(img)
             mask[i, : img.shape[1], : img.shape[2]] = False
         return cls(tensor, mask)
+
+    @classmethod
+    def from_uint8_list(cls, images: List[Tensor], mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225),
+                        do_round: bool = False) -> "NestedTensor":
+        """Decoded images as uint8 [h, w, 3] tensors (on the GPU, or on the host: copied through pinned staging) ->
+        the normalised, padded fp32 batch + mask in ONE launch: ToTensor + Normalize (datasets/transforms.py:257-272,
+        ImageNet statistics as in datasets/tdod.py:303) + from_tensor_list (util/misc.py:185-209).  Moves 1 byte per
+        pixel and channel over PCIe instead of 4 and takes the per-image float work off the data-loader workers."""
+        from .. import kernels as K
+
+        dev = next((t.device for t in images if t.is_cuda), torch.device("cuda"))
+        imgs = [h2d(t, dev).contiguous() for t in images]
+        h = max(int(t.shape[0]) for t in imgs)
+        w = max(int(t.shape[1]) for t in imgs)
+        if do_round:
+            h = (h + 127) // 128 * 128
+            w = (w + 127) // 128 * 128
+        tensor, mask_u8 = K.pad_normalize_u8(imgs, mean, std, h, w)
+        return cls(tensor, mask_u8.view(torch.bool))
 
     def __repr__(self) -> str:
         return repr(self.tensors)
