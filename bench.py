@@ -382,11 +382,21 @@ def run_ours(a):
     clocks = sampler.stop()
     value = world * BATCH * a.steps / (ms * 1e-3)
 
-    # ---- end to end: host buffers in, loss scalar out, every step
+    # ---- end to end: host buffers in, loss scalar out, every step.  Every step's images / mask / positive map are
+    # copied from pinned host memory inside the timed region; the copy of step i+1 runs on a copy stream under step i
+    # (toist_b200.util.misc.Prefetcher, what a prefetching data loader does), the loss is read back every step.
+    from toist_b200.util.misc import Prefetcher
+
+    def host_batches():
+        while True:
+            yield (NestedTensor(h_images, h_mask), h_pm)
+
+    feed = Prefetcher(host_batches(), dev)
+
     def e2e_step():
-        s = NestedTensor(h_images.to(dev, non_blocking=True), h_mask.to(dev, non_blocking=True))
+        s, pmap = next(feed)
         tg = targets_to(targets, dev)
-        total = step(s, tg, h_pm.to(dev, non_blocking=True))
+        total = step(s, tg, pmap)
         return float(total.item())
 
     e2e_step()

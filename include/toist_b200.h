@@ -286,9 +286,17 @@ int toist_pos_sine(const uint8_t* mask, float* pos_f32, void* pos_bf16, int32_t 
 int toist_embed_gather(const int64_t* ids, const float* word, const float* pos, const float* type0, float* out,
                        int32_t* pos_ids, int32_t batch, int32_t len, int32_t dim, int32_t pad_id, int32_t seq_first,
                        void* stream);
+/* backward of the three embedding lookups (atomic adds into zeroed tables).  pad_id: nn.Embedding(padding_idx) of
+ * transformers' RobertaEmbeddings -- rows `pad_id` of the word and position tables receive no gradient (-1: none). */
 int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, const int32_t* pos_ids, float* dword,
                         float* dpos, float* dtype0, int32_t batch, int32_t len, int32_t dim, int32_t seq_first,
-                        void* stream);
+                        int32_t pad_id, void* stream);
+/* Sparse data-parallel exchange of the word-embedding gradient (reference main.py:336 all-reduces the dense table):
+ * ids [n_rows] / rows [n_rows, dim] = the (token id, gradient row) pairs of ALL ranks in rank order (all-gathered by the
+ * caller); table[id, :] = scale * sum of the rows carrying that id, summed in list order and written (deterministic:
+ * bit-identical on every rank); `pad_id` rows are skipped. */
+int toist_embed_rows_merge(float* table, const int64_t* ids, const float* rows, int32_t n_rows, int32_t dim,
+                           int64_t pad_id, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Mask branch of DETRsegm (reference models/segmentation.py:157-241, 244-273; models/mdetr.py:827-853).

@@ -229,7 +229,10 @@ def roberta_encode(input_ids: Tensor, attention_mask: Tensor, sd: SD, prefix: st
     e = prefix + "embeddings."
     nonpad = input_ids.ne(pad_id).int()
     pos_ids = (torch.cumsum(nonpad, dim=1) * nonpad).long() + pad_id
-    x = sd[e + "word_embeddings.weight"][input_ids] + sd[e + "position_embeddings.weight"][pos_ids]
+    # both tables are nn.Embedding(..., padding_idx=pad_token_id) in transformers' RobertaEmbeddings: the rows of
+    # padded positions receive no gradient
+    x = F.embedding(input_ids, sd[e + "word_embeddings.weight"], padding_idx=pad_id) + \
+        F.embedding(pos_ids, sd[e + "position_embeddings.weight"], padding_idx=pad_id)
     x = x + sd[e + "token_type_embeddings.weight"][0]
     x = F.layer_norm(x, x.shape[-1:], sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], eps)
     B, L, E = x.shape

@@ -222,3 +222,44 @@ def test_direct_param_grads_match_autograd_routed(graphs):
         assert rel_err(dacc[k], aacc[k]) < 1e-3 or float(aacc[k].abs().max()) < 1e-12, k
     k = "transformer.decoder.layers.2.linear1.weight"
     assert rel_err(dacc[k], d1[k]) > 1e-2  # the second pass really added something
+
+
+def test_ragged_captions_match_oracle_and_pad_rows_get_no_gradient():
+    """Captions of different lengths (the shorter one padded with <pad> = 1): RoBERTa's word / position tables are
+    nn.Embedding(padding_idx=1), so their <pad> rows receive no gradient; padded text keys are masked.  Against the
+    oracle (pinned to the reference on exactly this case by tests/test_oracle_vs_reference.py::
+    test_ragged_captions_gradients_match_reference) with our assignments forced."""
+    from conftest import rel_err
+    from e2e_report import run_oracle
+    from toist_b200.models import build_model
+    from toist_b200.synth import make_args, make_batch, targets_to
+    from toist_b200.util.misc import NestedTensor
+
+    torch.manual_seed(0)
+    model, criterion, _, wd = build_model(make_args("resnet50"))
+    sd_cpu = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    model.cuda().eval()
+    images, mask, captions, targets, pm = make_batch(2, 128, 12, seed=9, pad=True)
+    captions = [captions[0], captions[1][4:]]
+    targets[1]["tokens_positive"] = [[[0, len(captions[1])]] for _ in targets[1]["tokens_positive"]]
+    s = NestedTensor(images.cuda(), mask.cuda())
+    mc = model(s, captions, encode_and_save=True)
+    assert int(mc["text_attention_mask"].sum()) == 4
+    out = model(s, captions, encode_and_save=False, memory_cache=mc)
+    losses = criterion(mc, out, targets_to(targets, "cuda"), pm.cuda(), None)
+    sum(losses[k] * wd[k] for k in losses if k in wd).backward()
+    idx = criterion.last_indices()
+    emb = model.transformer.text_encoder.embeddings
+    assert float(emb.word_embeddings.weight.grad[1].abs().max()) == 0.0
+    assert float(emb.position_embeddings.weight.grad[1].abs().max()) == 0.0
+    assert float(emb.word_embeddings.weight.grad[0].abs().max()) > 0.0  # <s> is a real token
+    forced = idx[-1:] + idx[:-1]
+    omc, oout, olosses, _, ograds = run_oracle(sd_cpu, "resnet50", (images, mask, captions, targets, pm),
+                                               model.transformer.tokenizer, wd, True, trainable, forced)
+    assert rel_err(mc["img_memory"], omc["img_memory"]) < 4e-2
+    for n in ("transformer.text_encoder.embeddings.word_embeddings.weight",
+              "transformer.text_encoder.embeddings.position_embeddings.weight"):
+        g = dict(model.named_parameters())[n].grad
+        assert float(ograds[n][1].abs().max()) == 0.0
+        assert rel_err(g, ograds[n]) < 0.35, (n, rel_err(g, ograds[n]))  # bf16 budget of a first-layer gradient

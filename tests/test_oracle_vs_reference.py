@@ -241,3 +241,44 @@ def test_gradients_match_reference(ref):
     errs = sorted(((rel_err(sd[k].grad, rgrads[k]), k) for k in rgrads
                    if float(rgrads[k].norm()) > 0 and "key.bias" not in k), reverse=True)
     assert errs[0][0] < 2e-3, errs[:5]
+
+
+def test_ragged_captions_gradients_match_reference(ref):
+    """Captions of different lengths: the shorter one is padded with <pad> (id 1).  RoBERTa's word and position tables
+    are nn.Embedding(padding_idx=1): their <pad> rows receive NO gradient, and padded keys are masked in the text
+    encoder and in the cross-modal encoder.  Reference vs oracle, embedding gradients and a few others."""
+    from synth import make_batch as mk
+    from util.misc import NestedTensor  # reference
+
+    model, criterion = ref["model"], ref["criterion"]
+    weight_dict = shims.load_reference(ref["tok"]).build_model(ref["args"])[3]
+    images, mask, captions, targets, pm = mk(2, 128, 12, seed=9, pad=True)
+    captions = [captions[0], captions[1][4:]]  # 10 and 6 characters -> 12 and 8 tokens
+    targets[1]["tokens_positive"] = [[[0, len(captions[1])]] for _ in targets[1]["tokens_positive"]]
+    tokd = ref["tok"](captions)
+    assert int((tokd["input_ids"] == 1).sum()) == 4
+    model.zero_grad(set_to_none=True)
+    mc = model(NestedTensor(images, mask), captions, encode_and_save=True)
+    out = model(NestedTensor(images, mask), captions, encode_and_save=False, memory_cache=mc)
+    losses = criterion(mc, out, targets, pm, None)
+    sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict).backward()
+    names = ["transformer.text_encoder.embeddings.word_embeddings.weight",
+             "transformer.text_encoder.embeddings.position_embeddings.weight",
+             "transformer.text_encoder.encoder.layer.0.attention.self.value.weight",
+             "transformer.encoder.layers.0.linear1.weight", "contrastive_align_projection_text.weight", "input_proj.weight"]
+    lookup = dict(model.named_parameters())
+    rg = {n: lookup[n].grad.clone() for n in names}
+    model.zero_grad(set_to_none=True)
+    assert float(rg[names[0]][1].abs().max()) == 0.0 and float(rg[names[1]][1].abs().max()) == 0.0  # <pad> rows
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k in names:
+        sd[k].requires_grad_(True)
+    cfg = O.Config(backbone="resnet50")
+    omc = O.encode(sd, cfg, images, mask, tokd["input_ids"], tokd["attention_mask"])
+    oout = O.decode(sd, cfg, omc)
+    olosses, _ = O.criterion(cfg, oout, tokd, targets, pm)
+    sum(olosses[k] * weight_dict[k] for k in olosses if k in weight_dict).backward()
+    for k, v in losses.items():
+        assert abs(float(olosses[k].detach()) - float(v.detach())) <= 2e-4 * max(1.0, abs(float(v.detach()))), k
+    for n in names:
+        assert rel_err(sd[n].grad, rg[n]) < 2e-3, (n, rel_err(sd[n].grad, rg[n]))

@@ -14,6 +14,7 @@ torchvision Bottleneck + models/backbone.py:21-58, models/mdetr.py:420-433 (head
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Set, Tuple
 
 import torch
@@ -31,10 +32,14 @@ class zero_arena:
     fp32 allocation (one memset instead of several hundred); falls back to torch.zeros when exhausted."""
 
     current = None
+    mark_bytes = int(os.environ.get("TOIST_GRAD_MARK_MB", "64")) << 20
 
-    def __init__(self, numel: int, dev):
+    def __init__(self, numel: int, dev, marks: bool = False):
         self.buf = torch.zeros(max(int(numel), 1), dtype=torch.float32, device=dev)
         self.off = 0
+        self.want_marks = marks
+        self.marks = []   # (offset in elements, event): everything below the offset is final once the event has fired
+        self.last = 0
 
     def __enter__(self):
         self.prev, zero_arena.current = zero_arena.current, self
@@ -54,6 +59,28 @@ class zero_arena:
         v = self.buf[self.off:end].view(shape)
         self.off = (end + 63) // 64 * 64  # keep every buffer 256-byte aligned (vector epilogues, TMA)
         return v
+
+
+def mark_grads() -> None:
+    """Called by the backward loops between layers / blocks.  When the data-parallel exchange asked for it, records an
+    event once another `mark_bytes` of parameter gradients are complete: gradients are served from the arena in the
+    order the backward produces them, so "complete" is a prefix of the arena and util/dist.FlatGradSync can all-reduce
+    that prefix while the rest of the stage is still running.  Weight-gradient kernels run on the side lane
+    (kernels.wgrad_lane); the event is recorded there, after the lane has been made to wait for the main stream, so it
+    covers both.  Inside a CUDA-graph capture the event is an external event-record node."""
+    a = zero_arena.current
+    if a is None or not a.want_marks or (a.off - a.last) * 4 < zero_arena.mark_bytes:
+        return
+    main = torch.cuda.current_stream()
+    lane = K._WgradLane
+    stream = main
+    if lane.active and lane.dirty and lane.stream is not None:
+        lane.stream.wait_stream(main)
+        stream = lane.stream
+    ev = torch.cuda.Event(external=torch.cuda.is_current_stream_capturing())
+    ev.record(stream)
+    a.marks.append((a.off, ev))
+    a.last = a.off
 
 
 def _zeros(shape, dev):

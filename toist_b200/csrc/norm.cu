@@ -431,17 +431,57 @@ template <typename T>
 __global__ void embed_scatter_kernel(const T* __restrict__ dx, const long long* __restrict__ ids,
                                      const int* __restrict__ pos_ids, float* __restrict__ dword,
                                      float* __restrict__ dpos, float* __restrict__ dtype0, int B, int L, int E,
-                                     int seq_first) {
+                                     int seq_first, int pad_id) {
   pdl_prologue();
   const int b = blockIdx.x / L, l = blockIdx.x % L;
   const int row = seq_first ? l * B + b : blockIdx.x;
   const long long id = ids[blockIdx.x];
   const int pid = pos_ids[row];
+  // nn.Embedding(padding_idx = pad_id): the <pad> rows of the word and position tables receive no gradient
+  const bool w_ok = dword != nullptr && id != (long long)pad_id;
+  const bool p_ok = dpos != nullptr && pid != pad_id;
   for (int c = threadIdx.x; c < E; c += blockDim.x) {
     const float g = ld_as_float(dx, (long long)row * E + c);
-    if (dword) atomicAdd(dword + id * E + c, g);
-    if (dpos) atomicAdd(dpos + (long long)pid * E + c, g);
+    if (w_ok) atomicAdd(dword + id * E + c, g);
+    if (p_ok) atomicAdd(dpos + (long long)pid * E + c, g);
     if (dtype0) atomicAdd(dtype0 + c, g);
+  }
+}
+
+// Data-parallel exchange of the word-embedding gradient as (id, row) pairs instead of the dense [vocab, E] table
+// (154 MB of which at most B * L rows are non-zero): `ids` / `rows` hold the pairs of ALL ranks, gathered in rank
+// order.  table[id] = scale * sum of the rows with that id, summed in list order by the block of the id's FIRST
+// occurrence and WRITTEN (not added): deterministic, so every rank ends up with bit-identical gradients, as after an
+// all-reduce.  Rows of ids nobody holds stay as they are (zero).  grid = n_rows, block = 256.
+__global__ void embed_rows_merge_kernel(float* __restrict__ table, const long long* __restrict__ ids,
+                                        const float* __restrict__ rows, int n_rows, int E, long long pad_id,
+                                        float scale) {
+  pdl_prologue();
+  __shared__ int s_list[1024];
+  __shared__ int s_n;
+  const int j = blockIdx.x;
+  const long long id = ids[j];
+  if (id == pad_id) return;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    bool first = true;
+    for (int i = 0; i < j; ++i)
+      if (ids[i] == id) {
+        first = false;
+        break;
+      }
+    if (first)
+      for (int i = j; i < n_rows && n < 1024; ++i)
+        if (ids[i] == id) s_list[n++] = i;
+    s_n = first ? n : 0;
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n == 0) return;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k) acc += rows[(long long)s_list[k] * E + c];
+    table[id * E + c] = acc * scale;
   }
 }
 
@@ -606,14 +646,25 @@ int toist_embed_gather(const int64_t* ids, const float* word, const float* pos, 
 
 int toist_embed_scatter(const void* dx, int32_t dx_dtype, const int64_t* ids, const int32_t* pos_ids, float* dword,
                         float* dpos, float* dtype0, int32_t batch, int32_t len, int32_t dim, int32_t seq_first,
-                        void* stream) {
+                        int32_t pad_id, void* stream) {
   TOIST_REQUIRE(dx && ids && pos_ids, "toist_embed_scatter: null pointer");
   const int rows = batch * len;
   if (rows == 0) return TOIST_OK;
   if (dx_dtype == TOIST_BF16)
-    launch_pdl((embed_scatter_kernel<__nv_bfloat16>), dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
+    launch_pdl((embed_scatter_kernel<__nv_bfloat16>), dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first, pad_id);
   else
-    launch_pdl((embed_scatter_kernel<float>), dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const float*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first);
+    launch_pdl((embed_scatter_kernel<float>), dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const float*)dx, (const long long*)ids, pos_ids, dword, dpos, dtype0, batch, len, dim, seq_first, pad_id);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_embed_rows_merge(float* table, const int64_t* ids, const float* rows, int32_t n_rows, int32_t dim,
+                           int64_t pad_id, float scale, void* stream) {
+  TOIST_REQUIRE(table && ids && rows, "toist_embed_rows_merge: null pointer");
+  TOIST_REQUIRE(n_rows >= 0 && n_rows <= 65535 && dim >= 1, "toist_embed_rows_merge: bad sizes");
+  if (n_rows == 0) return TOIST_OK;
+  launch_pdl(embed_rows_merge_kernel, dim3((unsigned)n_rows), dim3(256), 0, (cudaStream_t)stream, table,
+             (const long long*)ids, rows, (int)n_rows, (int)dim, (long long)pad_id, scale);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

@@ -618,12 +618,22 @@ def embed_gather(ids: torch.Tensor, word: torch.Tensor, pos: torch.Tensor, type_
 
 
 def embed_scatter(dx: torch.Tensor, ids: torch.Tensor, pos_ids: torch.Tensor, dword: Optional[torch.Tensor],
-                  dpos: Optional[torch.Tensor], dtype0: Optional[torch.Tensor], seq_first: bool = False) -> None:
+                  dpos: Optional[torch.Tensor], dtype0: Optional[torch.Tensor], seq_first: bool = False,
+                  pad_id: int = -1) -> None:
     b, l = ids.shape
     rows, e = dx.shape
     assert rows == b * l and dx.is_contiguous()
     _ck(_L().toist_embed_scatter(dx.data_ptr(), _dt(dx), ids.data_ptr(), pos_ids.data_ptr(), _ptr(dword), _ptr(dpos),
-                                 _ptr(dtype0), b, l, e, 1 if seq_first else 0, _stream()))
+                                 _ptr(dtype0), b, l, e, 1 if seq_first else 0, int(pad_id), _stream()))
+
+
+def embed_rows_merge(table: torch.Tensor, ids: torch.Tensor, rows: torch.Tensor, pad_id: int, scale: float) -> None:
+    """table[id] = scale * (sum of the rows with that id, in list order), written in place; deterministic."""
+    n, e = rows.shape
+    assert table.dtype == torch.float32 and table.is_contiguous() and table.shape[1] == e
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.numel() == n and rows.is_contiguous()
+    _ck(_L().toist_embed_rows_merge(table.data_ptr(), ids.data_ptr(), rows.data_ptr(), n, e, int(pad_id), float(scale),
+                                    _stream()))
 
 
 def permute_021(src: torch.Tensor) -> torch.Tensor:

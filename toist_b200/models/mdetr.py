@@ -79,7 +79,7 @@ class ModelRuntime:
             "heads": Stage(m, "heads", pick(*heads), prefix="", contrastive=m.contrastive_align_loss),
         }
 
-    def refresh(self, m: "MDETR") -> None:
+    def refresh(self, m: "MDETR", defer_rest: bool = False) -> None:
         if self.stages is None:
             self.build(m)
         sig = self.bank._sig
@@ -90,7 +90,7 @@ class ModelRuntime:
         if dirty:
             for st in self.stages.values():
                 st.invalidate()  # requires_grad flags may have changed
-        self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body, dirty)
+        self.bank.ensure(m, "backbone.0.body.", m.backbone[0].body, dirty, defer_rest=defer_rest)
         if self.graphs is not None and sig is not None and sig != self.bank._sig:
             self.graphs.clear()  # shadow buffers moved: captured pointers are stale
             self.graphs_text.clear()
@@ -203,7 +203,10 @@ class MDETR(nn.Module):
     # ------------------------------------------------------------------ phase A (engine.py:63)
     def encode(self, samples: NestedTensor, captions, want_features: bool = False) -> dict:
         rt = self._rt
-        rt.refresh(self)
+        # the trunk's shadow weights are refreshed here, in front of the backbone; the rest (RoBERTa, transformer, heads)
+        # on the text branch's stream below, next to the backbone, when that stream is in use
+        on_text_stream = rt.text_stream_enabled and isinstance(captions[0], str)
+        rt.refresh(self, defer_rest=on_text_stream)
         save = self._grad_wanted()
         dp = self._drop_probs()
         images = samples.tensors
@@ -229,6 +232,7 @@ class MDETR(nn.Module):
                 text_stream = rt.text_stream
                 text_stream.wait_stream(main)
                 with torch.cuda.stream(text_stream):
+                    rt.bank.run_rest()
                     text_resized = run_stage(TEXT, rt.call("text", save, dp["text"] if dp else 0.0), ids,
                                              text_attention_mask.view(torch.uint8))[0]
             else:

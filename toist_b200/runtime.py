@@ -112,7 +112,8 @@ class ShadowBank:
 
     def __init__(self):
         self.w: Dict[str, torch.Tensor] = {}
-        self.prep: Optional[K.WeightPrep] = None
+        self.prep: Optional[K.WeightPrep] = None       # trunk convolutions
+        self.prep_rest: Optional[K.WeightPrep] = None  # every other shadow
         self._sig = None
 
     def __deepcopy__(self, memo):  # EMA deep-copies the model (util/optim.py, main.py:322); rebuild lazily there
@@ -124,10 +125,14 @@ class ShadowBank:
         bs = tuple((b.data_ptr(), b._version) for b in buffers)
         return ps + bs
 
-    def ensure(self, model, backbone_prefix: Optional[str], body, dirty: bool = True, only=None) -> None:
+    def ensure(self, model, backbone_prefix: Optional[str], body, dirty: bool = True, only=None,
+               defer_rest: bool = False) -> None:
         """(Re)builds the bank when parameters moved (device change, load of a new module) or BN buffers changed,
         then refreshes every shadow from its fp32 master.  `dirty=False` (nothing called Module._apply or
-        load_state_dict since the last check) skips the pointer / version scan of ~1000 tensors."""
+        load_state_dict since the last check) skips the pointer / version scan of ~1000 tensors.
+        The refresh is two launches: the trunk's convolution weights (needed first, 0.26 GB of traffic) and everything
+        else (RoBERTa, transformer, heads: 0.85 GB).  With `defer_rest` the caller issues the second one itself
+        (`run_rest()`, on the text branch's stream, next to the trunk) instead of in front of it."""
         if dirty or self._sig is None:
             params = {n: p for n, p in model.named_parameters() if only is None or n.startswith(only)}
             sig = self._signature(params, list(model.buffers()) if body is not None else [])
@@ -135,12 +140,18 @@ class ShadowBank:
                 self._build(params, backbone_prefix, body)
                 self._sig = sig
         self.prep.run()
+        if not defer_rest:
+            self.prep_rest.run()
+
+    def run_rest(self) -> None:
+        self.prep_rest.run()
 
     def _build(self, params, backbone_prefix: Optional[str], body) -> None:
         dev = next(iter(params.values())).device
         if dev.type != "cuda":
             raise RuntimeError("toist_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
-        prep = K.WeightPrep(dev)
+        trunk = K.WeightPrep(dev)   # conv + FrozenBatchNorm pairs of the backbone
+        prep = K.WeightPrep(dev)    # everything else
         w: Dict[str, torch.Tensor] = {}
         conv_names = set()
         # ---- backbone: conv + FrozenBatchNorm pairs
@@ -152,10 +163,10 @@ class ShadowBank:
             cout, cin, kh, kw = conv_w.shape
             if conv_name == "conv1":  # 7x7 stem, consumed as an im2col GEMM
                 sh = torch.zeros((cout, STEM_LDK), dtype=BF, device=dev)
-                prep.add(conv_w.detach(), sh, cout, cin * kh * kw, STEM_LDK, scale, taps=kh * kw)
+                trunk.add(conv_w.detach(), sh, cout, cin * kh * kw, STEM_LDK, scale, taps=kh * kw)
             else:
                 sh = torch.empty((cout, kh, kw, cin), dtype=BF, device=dev)
-                prep.add(conv_w.detach(), sh, cout, cin * kh * kw, None, scale, taps=kh * kw)
+                trunk.add(conv_w.detach(), sh, cout, cin * kh * kw, None, scale, taps=kh * kw)
             w[backbone_prefix + conv_name + ".weight"] = sh
             w[backbone_prefix + bn_name + ".scale"] = scale
             w[backbone_prefix + bn_name + ".shift"] = shift
@@ -187,7 +198,7 @@ class ShadowBank:
                 for i, nm in enumerate(("query", "key", "value")):
                     prep.add(params[base + nm + ".weight"].detach(), qkv[i * E:(i + 1) * E], E, E)
                 w[base + "qkv"] = qkv
-        self.w, self.prep = w, prep
+        self.w, self.prep, self.prep_rest = w, trunk, prep
 
 
 def requires(names: Iterable[str], params: Sequence[torch.Tensor], enabled: bool) -> Set[str]:
@@ -361,7 +372,12 @@ class StageFn(torch.autograd.Function):
             outs, saved = c.graphs.run(ctx.fkey, lambda *t: spec.fwd(c, *t), inputs)
             outs = tuple(None if o is None else o.detach() for o in outs)  # fresh aliases of the static buffers
         if c.save:
-            _save(ctx, saved)
+            if c.graphs is None:
+                _save(ctx, saved)
+            else:
+                # everything the backward needs is static memory of the forward graph: keep the Python structure
+                # itself instead of packing ~750 tensors through save_for_backward every step
+                ctx.static_saved = saved
         nd = [outs[i] for i in spec.nondiff if i < len(outs) and outs[i] is not None]
         if nd:
             ctx.mark_non_differentiable(*nd)
@@ -370,25 +386,27 @@ class StageFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         spec, c = ctx.spec, ctx.c
-        saved = _load(ctx)
+        saved = _load(ctx) if c.graphs is None else ctx.static_saved
         needs = tuple(ctx.needs_input_grad[2: 2 + ctx.n_in])
         gouts = [None if g is None else g.contiguous() for g in gouts]
         dev = next((g.device for g in gouts if g is not None), None)
         numel = c.stage.arena_numel(c.req)
 
-        def body(*g):
-            with Bk.zero_arena(numel, dev) as arena, K.wgrad_lanes():
-                gi, gr = spec.bwd(c, saved, needs, *g)
-            return gi, gr, arena.buf
-
         sync = getattr(c, "grad_sync", None)
+        marks_on = bool(sync is not None and c.req and sync.wants_marks())
+
+        def body(*g):
+            with Bk.zero_arena(numel, dev, marks=marks_on) as arena, K.wgrad_lanes():
+                gi, gr = spec.bwd(c, saved, needs, *g)
+            return gi, gr, arena.buf, tuple(arena.marks)
+
         params = c.stage.params if ctx.n_tail else ()
         fresh = all(p.grad is None for p in params)
         if c.graphs is None:
-            gin, grads, abuf = body(*gouts)
+            gin, grads, abuf, marks = body(*gouts)
             pg = _grads_for(c.stage.names, grads, c.stage.shapes)
         else:
-            key = ("bwd", ctx.fkey, needs, _sig(gouts))
+            key = ("bwd", ctx.fkey, needs, _sig(gouts), marks_on)
             if not fresh:
                 # A gradient adopted from an earlier replay of this graph IS the graph's static buffer: the replay below
                 # would overwrite what was accumulated (or zeroed in place by zero_grad(set_to_none=False)).  Detach
@@ -400,7 +418,7 @@ class StageFn(torch.autograd.Function):
                         t = static.get(n)
                         if t is not None and p.grad is not None and p.grad.data_ptr() == t.data_ptr():
                             p.grad = p.grad.clone()
-            gin, grads, abuf = c.graphs.run(key, body, gouts)
+            gin, grads, abuf, marks = c.graphs.run(key, body, gouts)
             e = c.graphs.entries[key]
             if e.aux is None:  # the gradient buffers are static: their per-parameter views are made once per graph
                 e.aux = _grads_for(c.stage.names, grads, c.stage.shapes)
@@ -418,7 +436,10 @@ class StageFn(torch.autograd.Function):
                     params[i].grad = None
         # data parallel: one in-place all-reduce of the stage's gradient arena on a side stream (util/dist.py)
         if sync is not None and c.req:
-            sync.reduce(c.stage.name, abuf, pg)
+            sparse = grads.get("@sparse") if fresh else None  # accumulated gradients are dense: exchange them densely
+            if sparse is not None:
+                sparse = sparse + (pg[c.stage.names.index(sparse[0])],)
+            sync.reduce(c.stage.name, abuf, pg, marks=marks, sparse=sparse)
         if ctx.n_tail == 0:
             return (None, None) + tuple(gin)
         if getattr(c, "anchor", None) is not None and ctx.n_tail == 1:
@@ -524,6 +545,7 @@ def backbone_bwd(c: Call, gfeats: Dict[int, torch.Tensor], feats: Sequence[torch
             need_dx = not (li == st.first_trainable and bi == 0)
             gz = Bk.bottleneck_bwd(w.sub(pre), GView(grads, st.prefix + pre), RView(c.req, st.prefix + pre), gz,
                                    saved[(li, bi)], stride, bi == 0, need_dx)
+            Bk.mark_grads()
     return grads
 
 
@@ -596,23 +618,28 @@ def text_bwd(c: Call, saved, needs, dout: torch.Tensor):
         pre = st.prefix + f"encoder.layer.{i}."
         dx = Bk.roberta_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dx, saved_layers[i],
                                   st.num_heads, B, drop=c.drop(100 + 8 * i))
+        Bk.mark_grads()
     d_emb = c.drop(10)
     if d_emb is not None:
         dx = K.dropout(dx, d_emb.site(0))
     pre = st.prefix + "embeddings."
     e = WView(c.w, pre)
     dx32 = Bk.ln_bwd(e, GView(grads, pre), RView(c.req, pre), "LayerNorm.", dx, x32, m0, r0, dx_dtype=torch.float32)
-    names = ("word_embeddings.weight", "position_embeddings.weight", "token_type_embeddings.weight")
-    bufs = []
+    # the word table is taken LAST: it is the tail of the stage's gradient arena, which lets the data-parallel exchange
+    # leave it out of the dense all-reduce and ship it as (id, row) pairs instead (util/dist.py)
+    names = ("position_embeddings.weight", "token_type_embeddings.weight", "word_embeddings.weight")
+    bufs = {}
     for nm in names:
         if (pre + nm) in c.req:
             t = Bk._zeros(tuple(e[nm].shape), e[nm].device)
             grads[pre + nm] = t
-            bufs.append(t)
-        else:
-            bufs.append(None)
-    if any(b is not None for b in bufs):
-        K.embed_scatter(dx32, input_ids, pos_ids, bufs[0], bufs[1], bufs[2], seq_first=True)
+            bufs[nm] = t
+    if bufs:
+        K.embed_scatter(dx32, input_ids, pos_ids, bufs.get(names[2]), bufs.get(names[0]), bufs.get(names[1]),
+                        seq_first=True, pad_id=st.pad_id)
+    if names[2] in bufs:
+        # rows of dx32 are l * B + b: the matching ids in the same order
+        grads["@sparse"] = (pre + names[2], input_ids.t().contiguous().view(-1), dx32, st.pad_id)
     return (None, None), grads
 
 

@@ -85,3 +85,71 @@ def h2d(t: torch.Tensor, device, dtype: Optional[torch.dtype] = None) -> torch.T
         t = t.contiguous().pin_memory()
     return t.to(device, non_blocking=True)
 
+
+
+class Prefetcher:
+    """Overlaps the host -> device copy of the NEXT batch with the current step (the reference copies
+    synchronously at the top of every step, engine.py:51-58).  `batches` yields tuples / lists / dicts whose tensors
+    live in pinned host memory; every batch is copied on a dedicated stream while the previous one is being consumed,
+    and the consumer's stream is made to wait for exactly that copy.
+
+        for samples, pmap in Prefetcher(loader, device):
+            ...step...
+    """
+
+    def __init__(self, batches, device):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.next = None
+        self._fill()
+
+    def _to(self, obj):
+        if isinstance(obj, torch.Tensor):
+            return obj.to(self.device, non_blocking=True) if obj.device.type == "cpu" else obj
+        if isinstance(obj, NestedTensor):
+            return NestedTensor(self._to(obj.tensors), self._to(obj.mask))
+        if isinstance(obj, dict):
+            return {k: self._to(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._to(v) for v in obj)
+        return obj
+
+    def _fill(self) -> None:
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        with torch.cuda.stream(self.stream):
+            dev = self._to(host)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.next = (dev, ev, host)
+
+    def _record(self, obj, stream) -> None:
+        if isinstance(obj, torch.Tensor):
+            if obj.is_cuda:
+                obj.record_stream(stream)
+        elif isinstance(obj, NestedTensor):
+            self._record(obj.tensors, stream)
+            self._record(obj.mask, stream)
+        elif isinstance(obj, dict):
+            for v in obj.values():
+                self._record(v, stream)
+        elif isinstance(obj, (list, tuple)):
+            for v in obj:
+                self._record(v, stream)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        dev, ev, _host = self.next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        self._record(dev, cur)  # allocated on the copy stream, used on the consumer's
+        self._fill()            # the next batch's copy starts now and runs under this step
+        return dev

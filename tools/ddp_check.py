@@ -39,7 +39,9 @@ def main():
     ws = [torch.empty_like(w0) for _ in range(world)]
     dist.all_gather(ws, w0)
     assert all(torch.equal(ws[0], w) for w in ws), "parameters were not broadcast from rank 0"
-    images, mask, captions, targets, pm = make_batch(2, 224, 8, seed=100 + rank)
+    images, mask, captions, targets, pm = make_batch(2, 224, 12, seed=100 + rank)
+    if rank % 2:  # different token ids on different ranks: the sparse word-embedding exchange has something to merge
+        captions = [c.replace("sit", "dig").replace("open", "lift") for c in captions[::-1]]
     s = NestedTensor(images.to(dev), mask.to(dev))
     tg, pmd = targets_to(targets, dev), pm.to(dev)
 
@@ -81,6 +83,47 @@ def main():
         if rank == 0:
             print(f"[ddp_check] pass {it} graphs={graphs}: {len(synced)} gradients identical across ranks, "
                   f"max deviation from the mean of local gradients {worst:.2e}", flush=True)
+    # gradient accumulation: a no_sync() backward followed by a synchronised one WITHOUT zero_grad in between must leave
+    # the mean over ranks of (g_a + g_b) on every rank (what torch's wrapper exchanges after no_sync steps)
+    images2, mask2, _, targets2, pm2 = make_batch(2, 224, 12, seed=300 + rank)
+    s2, tg2, pmd2 = NestedTensor(images2.to(dev), mask2.to(dev)), targets_to(targets2, dev), pm2.to(dev)
+
+    def backward(samples, tgs, pmap):
+        mc = net(samples, captions, encode_and_save=True)
+        out = net(samples, captions, encode_and_save=False, memory_cache=mc)
+        losses = criterion(mc, out, tgs, pmap, None)
+        sum(losses[k] * wd[k] for k in losses if k in wd).backward()
+        torch.cuda.synchronize()
+
+    def grads():
+        return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    with net.no_sync():
+        model.zero_grad(set_to_none=True)
+        backward(s, tg, pmd)
+        ga = grads()
+        model.zero_grad(set_to_none=True)
+        backward(s2, tg2, pmd2)
+        gb = grads()
+        model.zero_grad(set_to_none=True)
+        backward(s, tg, pmd)  # accumulated locally ...
+    backward(s2, tg2, pmd2)  # ... and exchanged together with this pass
+    acc = grads()
+    worst = 0.0
+    for n in sorted(acc):
+        want = ga[n] + gb[n]
+        dist.all_reduce(want)
+        want /= world
+        other = [torch.empty_like(acc[n]) for _ in range(world)]
+        dist.all_gather(other, acc[n])
+        assert all(torch.equal(other[0], o) for o in other), f"{n}: ranks disagree after the accumulated exchange"
+        den = float(want.abs().max())
+        if den > 0:
+            worst = max(worst, float((acc[n] - want).abs().max()) / den)
+    assert worst < 2e-2, worst
+    if rank == 0:
+        print(f"[ddp_check] no_sync + sync accumulation: {len(acc)} gradients identical across ranks, max deviation from "
+              f"the mean of the summed local gradients {worst:.2e}", flush=True)
     dist.destroy_process_group()
 
 
