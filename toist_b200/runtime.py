@@ -439,7 +439,8 @@ class StageFn(torch.autograd.Function):
             sparse = grads.get("@sparse") if fresh else None  # accumulated gradients are dense: exchange them densely
             if sparse is not None:
                 sparse = sparse + (pg[c.stage.names.index(sparse[0])],)
-            sync.reduce(c.stage.name, abuf, pg, marks=marks, sparse=sparse)
+            # (the marks were recorded inside the stage's backward: after a fold they no longer say "final")
+            sync.reduce(c.stage.name, abuf, pg, marks=marks if fresh else (), sparse=sparse)
         if ctx.n_tail == 0:
             return (None, None) + tuple(gin)
         if getattr(c, "anchor", None) is not None and ctx.n_tail == 1:
