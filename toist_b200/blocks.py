@@ -380,10 +380,18 @@ def bottleneck_fwd(w: W, x, stride: int, has_ds: bool):
 def _conv_wgrad_param(g: G, name: str, dy, x, w_shadow, scale, stride: int, pad: int) -> None:
     cout, kh, kw, cin = w_shadow.shape
     with K.wgrad_lane(dy, x):
-        dw = _zeros((cout, kh, kw, cin), dy.device)
-        K.conv_wgrad(dy, x, dw, stride=stride, pad=pad, row_scale=scale)
         if kh * kw > 1:
-            dw = K.permute_021(dw.view(cout, kh * kw, cin))
+            # the GEMM produces [Cout, taps, Cin]; the parameter's layout is [Cout, Cin, taps].  The GEMM accumulates
+            # (split-K) into a zeroed scratch OUTSIDE the gradient arena and the permute writes the final layout INTO
+            # the arena: every gradient of the stage then travels in the stage's one flat all-reduce (a gradient
+            # outside the arena costs a collective of its own: ~30 trailing all-reduces per step before this)
+            tmp = torch.zeros((cout, kh, kw, cin), dtype=torch.float32, device=dy.device)
+            K.conv_wgrad(dy, x, tmp, stride=stride, pad=pad, row_scale=scale)
+            dw = _zeros((cout, cin, kh, kw), dy.device)
+            K.permute_021(tmp.view(cout, kh * kw, cin), out=dw.view(cout, cin, kh * kw))
+        else:
+            dw = _zeros((cout, kh, kw, cin), dy.device)
+            K.conv_wgrad(dy, x, dw, stride=stride, pad=pad, row_scale=scale)
     g[name] = dw.view(cout, cin, kh, kw)
 
 

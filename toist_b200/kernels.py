@@ -636,11 +636,12 @@ def embed_rows_merge(table: torch.Tensor, ids: torch.Tensor, rows: torch.Tensor,
                                     _stream()))
 
 
-def permute_021(src: torch.Tensor) -> torch.Tensor:
+def permute_021(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [A, B, C] -> [A, C, B] (conv weight gradient OHWI -> OIHW)."""
     a, b, c = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
-    dst = torch.empty((a, c, b), dtype=torch.float32, device=src.device)
+    dst = out if out is not None else torch.empty((a, c, b), dtype=torch.float32, device=src.device)
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.numel() == src.numel()
     _ck(_L().toist_permute_021(src.data_ptr(), dst.data_ptr(), a, b, c, _stream()))
     return dst
 

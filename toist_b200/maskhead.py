@@ -38,10 +38,14 @@ def _conv_param_grads(g, rq, name: str, dz, x, w_shadow, pad: int) -> None:
     """Weight (OIHW, fp32) and bias gradients of a biased convolution; dz may have zero-padded channels."""
     cout, kh, kw, cin = w_shadow.shape
     if (name + ".weight") in rq:
-        dw = Bk._zeros((cout, kh, kw, cin), dz.device)
-        K.conv_wgrad(dz, x, dw, pad=pad)
-        if kh * kw > 1:
-            dw = K.permute_021(dw.view(cout, kh * kw, cin))
+        if kh * kw > 1:  # scratch outside the arena, final layout inside it (see blocks._conv_wgrad_param)
+            tmp = torch.zeros((cout, kh, kw, cin), dtype=torch.float32, device=dz.device)
+            K.conv_wgrad(dz, x, tmp, pad=pad)
+            dw = Bk._zeros((cout, cin, kh, kw), dz.device)
+            K.permute_021(tmp.view(cout, kh * kw, cin), out=dw.view(cout, cin, kh * kw))
+        else:
+            dw = Bk._zeros((cout, kh, kw, cin), dz.device)
+            K.conv_wgrad(dz, x, dw, pad=pad)
         g[name + ".weight"] = dw.view(cout, cin, kh, kw)
     if (name + ".bias") in rq:
         c = dz.shape[-1]

@@ -47,6 +47,7 @@ class FlatGradSync:
         # One communicator executes its collectives in issue order, so the text stage gets a communicator and a stream
         # of its own (set by DistributedDataParallel, created collectively); everything else shares the default one.
         self.lanes = {}  # stage name -> (process group, stream)
+        self.n_extra = 0  # gradients exchanged one by one because they were not served from a stage arena (should stay 0)
         self._used = set()
 
     def _lane(self, stage_name: str, device):
@@ -86,6 +87,7 @@ class FlatGradSync:
                 lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
                 self._outside[key] = [i for i, t in enumerate(grads) if t is not None and not (lo <= t.data_ptr() < hi)]
             extra = [grads[i] for i in self._outside[key]]
+            self.n_extra += len(extra)
         # the word-embedding table is the tail of the text stage's arena (runtime.text_bwd): left out of the dense
         # exchange when it can travel as (id, row) pairs
         dense_end = flat.numel()

@@ -59,6 +59,7 @@ def main():
         torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
+        print(f"[ddp_timeline] gradients exchanged outside the stage arenas so far: {net.grad_sync.n_extra}")
         evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
         evs.sort(key=lambda e: e.time_range.start)
         t0 = evs[0].time_range.start
