@@ -1,0 +1,171 @@
+"""The drop-in claim, exercised: the body of the reference's training loop (engine.py:50-101) and of its evaluation
+loop (engine.py:275-309) driven through toist_b200.models / toist_b200.util with the reference's own call sequence:
+targets_to, two-phase forward, criterion, weighted sum, reduce_dict, finite check, optimizer.zero_grad, backward,
+clip_grad_norm_, optimizer.step, adjust_learning_rate, update_ema on a deepcopy, then PostProcess on eval outputs.
+The same steps run a second time with torch's own optimizer / clip / EMA formula on a copy of the model: parameters
+after three steps must agree (the model's backward is deterministic up to split-K atomics, so 1e-4 relative)."""
+from __future__ import annotations
+
+import argparse
+import math
+from copy import deepcopy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+
+
+def _param_groups(model, args):  # main.py:351-367
+    return [
+        {"params": [p for n, p in model.named_parameters()
+                    if "backbone" not in n and "text_encoder" not in n and p.requires_grad]},
+        {"params": [p for n, p in model.named_parameters() if "backbone" in n and p.requires_grad], "lr": args.lr_backbone},
+        {"params": [p for n, p in model.named_parameters() if "text_encoder" in n and p.requires_grad],
+         "lr": args.text_encoder_lr},
+    ]
+
+
+def _train_steps(fused: bool, graphs: bool):
+    from toist_b200.models import build_model
+    from toist_b200.synth import make_args, make_batch, targets_to
+    from toist_b200.util import dist
+    from toist_b200.util import optim as O
+    from toist_b200.util.misc import NestedTensor
+
+    args = make_args("resnet50", lr=1e-4, text_encoder_lr=5e-5, weight_decay=1e-4, clip_max_norm=0.1, ema_decay=0.9998,
+                     schedule="linear_with_warmup", fraction_warmup_steps=0.01, lr_drop=35, epochs=40)
+    torch.manual_seed(0)
+    model, criterion, cluster_criterion, weight_dict = build_model(args)
+    model.to(DEV)
+    model_ema = deepcopy(model)  # main.py:333: the EMA copy must be deep-copyable and independent
+    if graphs:
+        model.enable_cuda_graphs(True)
+        criterion.enable_cuda_graphs(True)
+        model.enable_direct_grads(True)
+    if fused:
+        optimizer = O.FusedAdamW(_param_groups(model, args), lr=args.lr, weight_decay=args.weight_decay)
+        clip, ema_update, adjust = O.clip_grad_norm_, O.update_ema, O.adjust_learning_rate
+    else:
+        optimizer = torch.optim.AdamW(_param_groups(model, args), lr=args.lr, weight_decay=args.weight_decay)
+        clip = torch.nn.utils.clip_grad_norm_
+
+        def ema_update(m, e, decay):  # util/optim.py:9-26
+            with torch.no_grad():
+                msd = m.state_dict()
+                for k, ema_v in e.state_dict().items():
+                    ema_v.copy_(ema_v * decay + (1.0 - decay) * msd[k].detach())
+        adjust = O.adjust_learning_rate
+    model.eval()  # dropout off: the two runs must see the same arithmetic (train() differs only by the dropout masks)
+    criterion.train()
+    loader = [make_batch(2, 160, 8, seed=40 + i, pad=(i % 2 == 0)) for i in range(3)]
+    num_training_steps = len(loader) * args.epochs
+    epoch, max_norm = 0, args.clip_max_norm
+    logged = []
+    for i, (images, mask, captions, targets, pm) in enumerate(loader):
+        curr_step = epoch * len(loader) + i
+        batch_dict = {"samples": NestedTensor(images, mask), "positive_map": pm,
+                      "targets": [dict(t, caption=c, dataset_name="tdod_1") for t, c in zip(targets, captions)]}
+        # ---- engine.py:53-101
+        example_rel = 0
+        samples = batch_dict["samples"].to(DEV)
+        positive_map = batch_dict["positive_map"].to(DEV) if "positive_map" in batch_dict else None
+        targets = batch_dict["targets"]
+        captions = [t["caption"] for t in targets]
+        targets = targets_to(targets, DEV)
+        memory_cache = model(samples, captions, encode_and_save=True)
+        outputs = model(samples, captions, encode_and_save=False, memory_cache=memory_cache)
+        loss_dict = {}
+        loss_dict.update(criterion(memory_cache, outputs, targets, positive_map, example_rel))
+        losses = sum(loss_dict[k] * weight_dict[k] for k in loss_dict.keys() if k in weight_dict)
+        loss_dict_reduced = dist.reduce_dict(loss_dict)
+        loss_dict_reduced_unscaled = {f"{k}_unscaled": v for k, v in loss_dict_reduced.items()}
+        loss_dict_reduced_scaled = {k: v * weight_dict[k] for k, v in loss_dict_reduced.items() if k in weight_dict}
+        losses_reduced_scaled = sum(loss_dict_reduced_scaled.values())
+        loss_value = losses_reduced_scaled.item()
+        assert math.isfinite(loss_value)
+        optimizer.zero_grad()
+        losses.backward()
+        if max_norm > 0:
+            clip(model.parameters(), max_norm)
+        optimizer.step()
+        adjust(optimizer, epoch, curr_step, num_training_steps=num_training_steps, args=args)
+        if model_ema is not None:
+            ema_update(model, model_ema, args.ema_decay)
+        logged.append((loss_value, {k: float(v) for k, v in loss_dict_reduced_unscaled.items()},
+                       [g["lr"] for g in optimizer.param_groups]))
+    return model, model_ema, logged, args
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_training_loop_body_matches_torch_optimizer_side(graphs):
+    from conftest import rel_err
+
+    m1, e1, log1, args = _train_steps(fused=True, graphs=graphs)
+    m2, e2, log2, _ = _train_steps(fused=False, graphs=False)
+    assert len(log1) == 3 and len(log1[0][1]) == 30  # 5 terms x 6 decoder layers, "_unscaled" suffix
+    for (l1, d1, lr1), (l2, d2, lr2) in zip(log1, log2):
+        assert abs(l1 - l2) <= 2e-3 * abs(l2), (l1, l2)
+        assert lr1 == lr2 and len(lr1) == 3
+    assert log1[-1][2][2] != args.text_encoder_lr  # the warm-up schedule moved the text encoder's learning rate
+    p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    def same(a, b, what):
+        # AdamW's update is lr * g / (|g| + eps): an element whose gradient is at the rounding-noise level (split-K
+        # atomics order differs run to run) may move by +lr in one run and -lr in the other.  Everything else agrees
+        # to 1e-4 relative; allow a handful of such elements per tensor.
+        bad = int(((a - b).abs() > 2e-6 + 1e-4 * b.abs()).sum())
+        assert bad <= max(2, int(0.002 * a.numel())), (what, bad, a.numel())
+
+    moved = 0
+    for n in p1:
+        if not p1[n].requires_grad:
+            assert torch.equal(p1[n], p2[n]), n  # frozen stem / layer1
+            continue
+        same(p1[n], p2[n], n)
+        moved += int(not torch.equal(p1[n], e1.state_dict()[n]))
+    assert moved > 300  # the EMA copy lags behind the model: it is an independent deep copy that was updated
+    s1, s2 = e1.state_dict(), e2.state_dict()
+    for k in s1:
+        if s1[k].is_floating_point():
+            same(s1[k].float(), s2[k].float(), "ema:" + k)
+    assert rel_err(s1["class_embed.weight"], s2["class_embed.weight"]) < 1e-5
+
+
+def test_evaluation_loop_body():
+    """engine.py:275-309: eval-mode forward under no_grad, criterion for logging, PostProcess to the COCO format."""
+    from toist_b200.models import build_model
+    from toist_b200.models.postprocessors import build_postprocessors
+    from toist_b200.synth import make_args, make_batch, targets_to
+    from toist_b200.util import dist
+    from toist_b200.util.misc import NestedTensor
+
+    args = make_args("resnet50")
+    torch.manual_seed(0)
+    model, criterion, _, weight_dict = build_model(args)
+    model.to(DEV).eval()
+    criterion.eval()
+    postprocessors = build_postprocessors(args, "tdod")
+    images, mask, captions, targets, pm = make_batch(2, 160, 8, seed=77, pad=True)
+    for i, t in enumerate(targets):
+        t["orig_size"] = torch.tensor([480, 640 - 40 * i])
+        t["size"] = torch.tensor([160, 160 - 20 * i])
+        t["image_id"] = torch.tensor([1000 + i])
+    with torch.no_grad():
+        samples = NestedTensor(images, mask).to(DEV)
+        positive_map = pm.to(DEV)
+        targets = targets_to(targets, DEV)
+        memory_cache = model(samples, captions, encode_and_save=True)
+        outputs = model(samples, captions, encode_and_save=False, memory_cache=memory_cache)
+        loss_dict = criterion(memory_cache, outputs, targets, positive_map, 0)
+        loss_dict_reduced = dist.reduce_dict(loss_dict)
+        loss_dict_reduced_scaled = {k: v * weight_dict[k] for k, v in loss_dict_reduced.items() if k in weight_dict}
+        assert math.isfinite(float(sum(loss_dict_reduced_scaled.values())))
+        orig_target_sizes = torch.stack([t["orig_size"] for t in targets], dim=0)
+        results = postprocessors["bbox"](outputs, orig_target_sizes)
+        res = {target["image_id"].item(): output for target, output in zip(targets, results)}
+    assert sorted(res) == [1000, 1001]
+    for r in res.values():
+        assert r["boxes"].shape == (100, 4) and r["scores"].shape == (100,) and r["labels"].dtype == torch.int64
+        assert float(r["scores"].min()) >= 0 and float(r["scores"].max()) <= 1
+    assert float(res[1001]["boxes"][:, 2].max()) <= 600 * 1.5  # scaled by the original width of THAT image

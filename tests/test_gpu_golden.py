@@ -215,3 +215,48 @@ def test_model_gradients_against_reference_golden(config1_gold):
         assert full[k] < 3e-2, (k, full[k])
     nr = [r for _, r, _ in table]
     assert 0.7 < min(nr) and max(nr) < 1.5, (min(nr), max(nr))
+
+
+def test_matcher_1000_problems_bit_identical_to_scipy_on_our_cost():
+    """>= 1000 random seeds + degenerate cases.  125 batches x 8 images: the device matcher (cost kernel +
+    warp-parallel LSAP) against the oracle (reference operation order, models/matcher.py:63-87, + scipy's
+    linear_sum_assignment when it is installed, else the pinned restatement) on identical fp32 inputs.  Includes images
+    without targets, duplicated queries (exact ties), nearly identical queries (near ties at the 1e-7 level) and
+    T close to Q.  Assignments must be identical; the cost matrix within 2e-6."""
+    from oracle import model as O
+    from toist_b200.models.matcher import HungarianMatcher
+
+    m = HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2)
+    g = torch.Generator().manual_seed(2024)
+    n_problems = n_ties = 0
+    for it in range(125):
+        B, Q = 8, (100 if it % 5 else 16)
+        logits = torch.randn(B, Q, 256, generator=g) * (0.1 if it % 3 == 0 else 2.0)  # 0.1: random-init-like near ties
+        boxes = torch.cat([torch.rand(B, Q, 2, generator=g) * 0.5 + 0.25, torch.rand(B, Q, 2, generator=g) * 0.3 + 0.05], -1)
+        if it % 7 == 0:   # exact ties: half of the queries are copies of query 0
+            logits[:, Q // 2:] = logits[:, :1]
+            boxes[:, Q // 2:] = boxes[:, :1]
+            n_ties += 1
+        if it % 11 == 0:  # near ties: copies perturbed in the last bits
+            logits[:, 1::2] = logits[:, 0::2] * (1 + 1e-7)
+            boxes[:, 1::2] = boxes[:, 0::2]
+        counts = [int(torch.randint(0, 6, (1,), generator=g)) for _ in range(B)]
+        if it % 13 == 0:
+            counts[0] = min(Q - 1, 14)  # many targets
+        targets = []
+        for n in counts:
+            tb = torch.cat([torch.rand(n, 2, generator=g) * 0.5 + 0.25, torch.rand(n, 2, generator=g) * 0.3 + 0.05], -1)
+            targets.append({"boxes": tb, "labels": torch.ones(n, dtype=torch.long)})
+        T = sum(counts)
+        pm = torch.zeros(T, 256)
+        for r in range(T):
+            lo = 1 + int(torch.randint(0, 12, (1,), generator=g))
+            pm[r, lo: lo + 1 + int(torch.randint(0, 4, (1,), generator=g))] = 1
+        pm = pm / (pm.sum(-1, keepdim=True) + 1e-6)
+        want = O.hungarian_match(logits, boxes, targets, pm, 1.0, 5.0, 2.0)
+        got = m({"pred_logits": logits.to(DEV), "pred_boxes": boxes.to(DEV)},
+                [{k: v.to(DEV) for k, v in t.items()} for t in targets], pm.to(DEV))
+        for b, ((r0, c0), (r1, c1)) in enumerate(zip(got, want)):
+            assert r0.tolist() == r1.tolist() and c0.tolist() == c1.tolist(), (it, b)
+            n_problems += 1
+    assert n_problems == 1000 and n_ties >= 15

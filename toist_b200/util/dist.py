@@ -22,6 +22,25 @@ def get_rank() -> int:
     return dist.get_rank() if is_dist_avail_and_initialized() else 0
 
 
+def is_main_process() -> bool:
+    return get_rank() == 0
+
+
+def reduce_dict(input_dict, average: bool = True):
+    """util/dist.py:93-117: the loss dictionary averaged over ranks for logging (engine.py:75); keys sorted so that every
+    rank stacks them in the same order; the dictionary itself when there is a single rank."""
+    world = get_world_size()
+    if world < 2:
+        return input_dict
+    with torch.no_grad():
+        names = sorted(input_dict.keys())
+        values = torch.stack([input_dict[k] for k in names], dim=0)
+        dist.all_reduce(values)
+        if average:
+            values /= world
+        return {k: v for k, v in zip(names, values)}
+
+
 # ------------------------------------------------------------------------------------------------ gradient all-reduce
 class FlatGradSync:
     """Gradient exchange of data-parallel training (reference main.py:336: DistributedDataParallel's bucketed

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
     torch.manual_seed(0)
-    model, criterion, _, wd = build_model(make_args(a.backbone))
+    model, criterion, _, wd = build_model(make_args(a.backbone, dropout=0.1))  # the bench configuration
     model.cuda().train()
     images, mask, captions, targets, pm = make_batch(a.batch, a.size, a.tokens)
     s = NestedTensor(images.cuda(), mask.cuda())
