@@ -95,6 +95,7 @@ class GemmProfiler:
 
     def __init__(self):
         self.rec = []
+        self.bytes = {}  # launch signature -> algorithmic bytes (operands once + output once), filled by kernels.gemm
 
     @contextlib.contextmanager
     def record(self, tag, flops, sig=None, relaunch=None):
@@ -311,6 +312,8 @@ def run_ours(a):
     if not a.no_graphs:  # replay each stage's launch sequence as a CUDA graph (same public API, fixed shapes)
         model.enable_cuda_graphs(True)
         criterion.enable_cuda_graphs(True)
+    if not a.no_fused_loss_sum:
+        criterion.enable_fused_loss_sum(True)
     if not a.no_direct:  # stages assign Parameter.grad themselves (no per-parameter autograd edges), see runtime.StageFn
         model.enable_direct_grads(True)
     ddp = None
@@ -439,9 +442,22 @@ def run_ours(a):
             nl = sum(v[2] for v in agg.values())
             gem = [(f, iso[sg]) for tag, f, sg, _ in prof.rec if sg is not None and sg[0] == "gemm"]
             fl_g, tm_g = sum(f for f, _ in gem), sum(t for _, t in gem)
+            # DRAM traffic of the same kernel family from the committed ncu launch list of one eager step
+            # (profiles/r02_dram_traffic.json <- tools/launch_summary.py), per launch like `achieved`, next to the
+            # algorithmic bytes per launch (operands read once + output written once, summed over the step's launches)
+            traffic = traffic_src = None
+            tj = ROOT / "profiles" / "r02_dram_traffic.json"
+            if tj.exists():
+                t = json.loads(tj.read_text())["gemm_family"]
+                traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) / max(t["launches"], 1)
+                traffic_src = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the {t['launches']} gemm_kernel launches of "
+                               "one eager step (cold L2 per launch), profiles/r02_ncu_launch_summary_eager_step.txt")
+            alg_bytes = sum(prof.bytes.get(sg, 0.0) for tag, f, sg, _ in prof.rec if sg is not None and sg[0] == "gemm")
             roof = {"bound": "tensor", "kernel": "toist::gemm_kernel (all modes, all layers)", "achieved": fl_g / tm_g / 1e12,
                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": fl_g / tm_g / 1e12 / peaks["tf_sustained"],
-                    "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)", "launches_per_step": len(gem),
+                    "traffic": traffic, "traffic_unit": "bytes per launch (DRAM)", "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": alg_bytes / max(len(gem), 1),
+                    "peak_source": peaks["source"] + " (sustained bf16)", "launches_per_step": len(gem),
                     "distinct_launch_shapes": len({sg for _, _, sg, _ in prof.rec if sg is not None and sg[0] == "gemm"}),
                     "flops_per_step": fl_g, "kernel_seconds_per_step": tm_g,
                     "serial_share_of_step": tm_g / (ms * 1e-3 / a.steps),
@@ -525,7 +541,7 @@ def run_ours(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": a.dropout,
-                       "cuda_graphs": not a.no_graphs, "direct_param_grads": not a.no_direct,
+                       "cuda_graphs": not a.no_graphs, "direct_param_grads": not a.no_direct, "fused_loss_sum": not a.no_fused_loss_sum,
                        "l2": "320 MB buffer rewritten between steps (> 126 MB L2)",
                        "parallelism": f"dp{world}" + ((" (torch DDP bucketed NCCL all-reduce)" if a.torch_ddp else
                                                               " (flat NCCL all-reduce per backward stage, side stream)")
@@ -599,6 +615,8 @@ def run_other(a):
             m.enable_direct_grads(True)
     if not a.no_graphs:
         criterion.enable_cuda_graphs(True)
+    if not a.no_fused_loss_sum:
+        criterion.enable_fused_loss_sum(True)
     nets = list(models)
     if world > 1:
         from toist_b200.util.dist import DistributedDataParallel as FlatDDP
@@ -731,7 +749,7 @@ def run_other(a):
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload, "baseline_config": a.config, "global_batch": world * batch,
-                           "dropout": a.dropout, "cuda_graphs": not a.no_graphs, "direct_param_grads": not a.no_direct,
+                           "dropout": a.dropout, "cuda_graphs": not a.no_graphs, "direct_param_grads": not a.no_direct, "fused_loss_sum": not a.no_fused_loss_sum,
                            "l2": "320 MB buffer rewritten between steps (> 126 MB L2)", "parallelism": f"dp{world}"},
                 "clocks": clocks,
                 "e2e": {"value": world * batch * a.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -757,6 +775,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-launch roofline pass (quick A/B runs)")
     ap.add_argument("--dump-shapes", default="", help="write one JSON line per distinct tensor-core launch shape")
     ap.add_argument("--no-graphs", action="store_true", help="issue every kernel launch from Python (no CUDA graphs)")
+    ap.add_argument("--no-fused-loss-sum", action="store_true", help="plain-tensor loss terms (A/B of "
+                                                                     "SetCriterion.enable_fused_loss_sum)")
     ap.add_argument("--no-direct", action="store_true", help="route parameter gradients through autograd (A/B of "
                                                              "MDETR.enable_direct_grads)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],

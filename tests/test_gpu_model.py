@@ -263,3 +263,48 @@ def test_ragged_captions_match_oracle_and_pad_rows_get_no_gradient():
         g = dict(model.named_parameters())[n].grad
         assert float(ograds[n][1].abs().max()) == 0.0
         assert rel_err(g, ograds[n]) < 0.35, (n, rel_err(g, ograds[n]))  # bf16 budget of a first-layer gradient
+
+
+def test_fused_loss_sum_equals_plain_tensors():
+    """SetCriterion.enable_fused_loss_sum: LossValue terms through the reference's weighted sum + backward give the same
+    total and the same gradients as plain tensors; every other use of a term (item, stack, float, detach, comparison)
+    behaves like the tensor it stands for."""
+    import math
+
+    from conftest import rel_err
+    from toist_b200.models import build_model
+    from toist_b200.models.lossvalue import LossValue
+    from toist_b200.synth import make_args, make_batch, targets_to
+    from toist_b200.util.misc import NestedTensor
+
+    torch.manual_seed(0)
+    model, criterion, _, wd = build_model(make_args("resnet50"))
+    model.cuda().eval()
+    images, mask, captions, targets, pm = make_batch(2, 160, 8, seed=5, pad=True)
+    s = NestedTensor(images.cuda(), mask.cuda())
+    tg, pmd = targets_to(targets, "cuda"), pm.cuda()
+    res = {}
+    for fused in (False, True):
+        criterion.enable_fused_loss_sum(fused)
+        model.zero_grad(set_to_none=True)
+        mc = model(s, captions, encode_and_save=True)
+        out = model(s, captions, encode_and_save=False, memory_cache=mc)
+        losses = criterion(mc, out, tg, pmd, None)
+        total = sum(losses[k] * wd[k] for k in losses.keys() if k in wd)
+        assert isinstance(total, LossValue) == fused and isinstance(total, torch.Tensor)
+        assert losses["loss_ce"].requires_grad and not losses["cardinality_error"].requires_grad
+        vals = {k: v.item() for k, v in losses.items()}
+        stacked = torch.stack([losses[k] for k in sorted(losses)])  # util/dist.py:reduce_dict
+        assert stacked.shape == (30,) and not isinstance(stacked, LossValue)
+        scaled = {k: v * wd[k] for k, v in losses.items() if k in wd}
+        logged = sum(scaled.values()).item()
+        assert math.isfinite(logged) and bool(torch.isfinite(total)) and float(losses["loss_bbox"].detach()) > 0
+        total.backward()
+        res[fused] = (float(total.detach()), logged, vals, {n: p.grad.clone() for n, p in model.named_parameters()
+                                                             if p.grad is not None})
+    criterion.enable_fused_loss_sum(False)
+    (t0, l0, v0, g0), (t1, l1, v1, g1) = res[False], res[True]
+    assert abs(t0 - t1) <= 1e-5 * abs(t0) and abs(l0 - l1) <= 1e-5 * abs(l0) and abs(t1 - l1) <= 1e-5 * abs(t1)
+    assert v0 == v1 and set(g0) == set(g1)
+    for n in g0:
+        assert rel_err(g1[n], g0[n]) < 1e-3 or float(g0[n].abs().max()) < 1e-12, n

@@ -238,6 +238,16 @@ def gemm(mode: int, a: Tensor4, b: Tensor4, out: torch.Tensor, *, ext: Tuple[int
         sig = ("gemm", mode, tuple(ext), tuple(tile), n_cols, m_rows, k_per_tap, len(taps), tuple(stride), splits,
                tuple(batch), act, d.out_dtype, res is not None, mask is not None, aux is not None, bool(accumulate),
                bool(b_batched), tuple(out_strides))
+        # algorithmic bytes of the launch: every operand read once, the output written once (DESIGN.md "Measurement")
+        sxy = stride[0] * stride[1] if len(taps) > 1 else 1
+        if mode == GEMM_WGRAD:
+            abytes = (pix * m_rows * 2 + pix * sxy * n_cols * 2) * batch[0] * batch[1] + m_rows * n_cols * len(taps) * 4
+        else:
+            abytes = pix * sxy * k_per_tap * 2 + n_cols * k_per_tap * len(taps) * 2 * (pix // 128 if b_batched else 1) \
+                + pix * n_cols * (out.element_size() + (res.element_size() if res is not None else 0)
+                                  + (2 if mask is not None else 0) + (2 if aux is not None else 0))
+        if hasattr(_gemm_profiler, "bytes"):
+            _gemm_profiler.bytes[sig] = float(abytes)
         dcopy = GemmDesc.from_buffer_copy(d)
         keep = (out, res, mask, aux, col_scale, col_shift, row_scale, getattr(a, "_keep", None), getattr(b, "_keep", None))
 

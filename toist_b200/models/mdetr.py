@@ -498,6 +498,7 @@ class SetCriterion(nn.Module):
         self._stage_kd = Stage.empty("softkd")
         self._graphs: Optional[GraphCache] = None
         self._forced = None
+        self._fused_sum = False
 
     def force_match(self, indices) -> None:
         """Testing hook: `indices[l][b] = (query_idx, target_idx)` (the matcher's output format, one list per decoder
@@ -512,6 +513,13 @@ class SetCriterion(nn.Module):
             for b, (qi, ti) in enumerate(self._forced[l]):
                 mq[l, b, ti.to(torch.int64)] = qi.to(torch.int32)
         return h2d(mq, dev)
+
+    def enable_fused_loss_sum(self, on: bool = True) -> "SetCriterion":
+        """Hand out the loss terms as `LossValue`s (models/lossvalue.py): the caller's `sum(loss_dict[k] * weight_dict[k]
+        ...)` and `.backward()` (engine.py:72,88) then cost one small upload instead of ~75 tiny launches; any other use
+        of a term behaves like the plain tensor it stands for."""
+        self._fused_sum = bool(on)
+        return self
 
     def enable_cuda_graphs(self, on: bool = True) -> "SetCriterion":
         """Replay the criterion's launch sequence as a CUDA graph (fixed shapes; see MDETR.enable_cuda_graphs)."""
@@ -593,7 +601,13 @@ class SetCriterion(nn.Module):
             mcall = Call(self._stage_mask, {}, msave, graphs=self._graphs, tag=prefix)
             mask_out = run_stage(MASKLOSS, mcall, pm_, tgt_masks, match_q[L - 1].contiguous(), packed.count, nb)[0]
         losses = {}
-        cells = _LossTerms.apply(out) if out.requires_grad else tuple(out.reshape(-1).unbind(0))
+        if self._fused_sum and out.requires_grad:
+            from .lossvalue import loss_cells
+
+            # rows: ce, bbox, giou, cardinality (no gradient, mdetr.py:783), contrastive align
+            cells = loss_cells(out, (True, True, True, False, True))[1]
+        else:
+            cells = _LossTerms.apply(out) if out.requires_grad else tuple(out.reshape(-1).unbind(0))
         for name, row in terms:
             if name == "loss_contrastive_align" and mask_out is not None:
                 losses[prefix + "loss_mask"], losses[prefix + "loss_dice"] = mask_out[0], mask_out[1]

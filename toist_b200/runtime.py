@@ -17,6 +17,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable, List, Optional, Sequence, Set, Tuple
 
 import torch
@@ -102,6 +103,7 @@ def _load(ctx):
 
 
 # ------------------------------------------------------------------------------------------------ shadow weights
+_SHADOW_ALWAYS = os.environ.get("TOIST_SHADOW_ALWAYS", "0") != "0"
 _EMBEDDING_KEYS = ("word_embeddings", "position_embeddings", "token_type_embeddings", "query_embed")
 RESNET_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
 STEM_LDK = 192  # 7*7*3 = 147 patch columns padded to a multiple of 64
@@ -114,6 +116,9 @@ class ShadowBank:
         self.w: Dict[str, torch.Tensor] = {}
         self.prep: Optional[K.WeightPrep] = None       # trunk convolutions
         self.prep_rest: Optional[K.WeightPrep] = None  # every other shadow
+        self._tracked: List[torch.Tensor] = []
+        self._ver = -1
+        self._stale_rest = True
         self._sig = None
 
     def __deepcopy__(self, memo):  # EMA deep-copies the model (util/optim.py, main.py:322); rebuild lazily there
@@ -133,18 +138,31 @@ class ShadowBank:
         The refresh is two launches: the trunk's convolution weights (needed first, 0.26 GB of traffic) and everything
         else (RoBERTa, transformer, heads: 0.85 GB).  With `defer_rest` the caller issues the second one itself
         (`run_rest()`, on the text branch's stream, next to the trunk) instead of in front of it."""
+        rebuilt = False
         if dirty or self._sig is None:
             params = {n: p for n, p in model.named_parameters() if only is None or n.startswith(only)}
             sig = self._signature(params, list(model.buffers()) if body is not None else [])
             if sig != self._sig:
                 self._build(params, backbone_prefix, body)
                 self._sig = sig
-        self.prep.run()
-        if not defer_rest:
-            self.prep_rest.run()
+                self._tracked = list(params.values()) + (list(model.buffers()) if body is not None else [])
+                rebuilt = True
+        # The shadows are a cache of the fp32 masters: refresh them only when a master changed.  Every in-place update
+        # that goes through torch (torch.optim.*, load_state_dict, copy_ on state_dict() entries) bumps the tensor's
+        # version counter; toist_b200.util.optim.FusedAdamW bumps it explicitly.  (Writes through `.data` do not:
+        # TOIST_SHADOW_ALWAYS=1 restores the unconditional refresh.)  Cost: one pass over ~500 counters, ~40 us.
+        ver = sum(t._version for t in self._tracked)
+        self._stale_rest = rebuilt or _SHADOW_ALWAYS or ver != self._ver
+        self._ver = ver
+        if self._stale_rest:
+            self.prep.run()
+            if not defer_rest:
+                self.run_rest()
 
     def run_rest(self) -> None:
-        self.prep_rest.run()
+        if self._stale_rest:
+            self.prep_rest.run()
+            self._stale_rest = False
 
     def _build(self, params, backbone_prefix: Optional[str], body) -> None:
         dev = next(iter(params.values())).device

@@ -192,6 +192,9 @@ class FusedAdamW(torch.optim.Optimizer):
             items, n, blocks = self._table.get([ps, gs, ms, vs], grp)
             _lib.check(_lib.load().toist_adamw_step(items.data_ptr(), n, blocks, hyper.ctypes.data_as(C.c_void_p),
                                                     int(hyper.shape[0]), _stream()))
+            # the kernel writes through raw pointers: tell autograd (and the models' bf16 shadow-weight cache, which
+            # refreshes when a master's version moved: runtime.ShadowBank.ensure) that the parameters changed
+            torch.autograd.graph.increment_version(ps)
         return loss
 
 

@@ -34,6 +34,7 @@ def main():
     model.to(dev).train()
     model.enable_cuda_graphs(True)
     criterion.enable_cuda_graphs(True)
+    criterion.enable_fused_loss_sum(True)
     net = DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
     opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4)
     images, mask, captions, targets, pm = make_batch(8, 640, 16, seed=1234 + rank)

@@ -28,6 +28,7 @@ def main():
     model.cuda().train()
     model.enable_cuda_graphs(True)
     criterion.enable_cuda_graphs(True)
+    criterion.enable_fused_loss_sum(True)
     import os
 
     from toist_b200.util.optim import FusedAdamW
