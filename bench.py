@@ -734,6 +734,29 @@ def run_other(a):
             d[2] += 1
         R.GraphCache.timing = None
         stages = {k: {"ms": round(v[0], 4), "launches": v[1], "replays": v[2]} for k, v in agg.items()}
+    if a.kernel_table and rank == 0:  # one step under torch.profiler: GPU time by kernel name + host wall time
+        import collections
+
+        from torch.profiler import ProfilerActivity, profile
+
+        torch.cuda.synchronize()
+        t_host = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(db)
+            t_issue = time.perf_counter() - t_host
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for e in evs:
+            k = e.name.split("(")[0][:100]
+            agg[k][0] += 1
+            agg[k][1] += e.time_range.end - e.time_range.start
+        span = max(e.time_range.end for e in evs) - min(e.time_range.start for e in evs)
+        with open(a.kernel_table, "w") as fh:
+            fh.write(f"config {a.config}: one step, host issue {t_issue * 1e3:.2f} ms, device span {span / 1e3:.2f} ms, "
+                     f"sum of kernel time {sum(v[1] for v in agg.values()) / 1e3:.2f} ms, {len(evs)} GPU activities\n")
+            for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+                fh.write(f"{t / 1e3:9.3f} ms {n:5d}x  {k}\n")
     extra = {}
     if seg and stages:
         # minimal HBM traffic of the mask head forward at B=8 (every intermediate written once and read
@@ -779,6 +802,7 @@ def main():
                                                                      "SetCriterion.enable_fused_loss_sum)")
     ap.add_argument("--no-direct", action="store_true", help="route parameter gradients through autograd (A/B of "
                                                              "MDETR.enable_direct_grads)")
+    ap.add_argument("--kernel-table", default="", help="configs 3 / 5: write GPU time by kernel name of one profiled step")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
                     help="BASELINE.json config (1-based): 2 = detection (headline, default), 3 = + mask head, 5 = distillation")
     a = ap.parse_args()

@@ -365,9 +365,10 @@ int toist_lsap_batched(const float* cost, const int32_t* n_rows, const int32_t* 
                        int32_t* flags, int32_t n_problems, int32_t ld_rows, int32_t ld_cols, void* stream);
 /* ClusterCriterion arithmetic (models/mdetr.py:29-312, models/kmeans.py:21-133).
  * toist_kmeans: Lloyd iterations on x [n, dim] from `centers` [k, dim] (updated in place) until
- * (sum_k ||shift_k||)^2 < tol, without host round trips; choice [n]; iters (may be null) = iterations run. */
-int toist_kmeans(const float* x, float* centers, int32_t* choice, int32_t* iters, int32_t n, int32_t dim, int32_t k,
-                 float tol, int32_t max_iter, void* stream);
+ * (sum_k ||shift_k||)^2 < tol, without host round trips; choice [n]; iters (may be null) = iterations run;
+ * xt_workspace: f32 [dim, n] scratch for the transposed bank (may be null: slower row-strided access, same results). */
+int toist_kmeans(const float* x, float* centers, int32_t* choice, int32_t* iters, float* xt_workspace, int32_t n,
+                 int32_t dim, int32_t k, float tol, int32_t max_iter, void* stream);
 int toist_kmeans_predict(const float* x, const float* centers, int32_t* choice, int32_t m, int32_t dim, int32_t k,
                          void* stream);
 /* out[b, :] = sum_t w[b, t] * x[t, b, :]   (x f32 [n_tokens, batch, dim]; w = selection / count gives the token means of

@@ -1159,8 +1159,9 @@ def kmeans(x: torch.Tensor, centers: torch.Tensor, tol: float = 1e-4, max_iter: 
     assert x.is_contiguous() and centers.is_contiguous() and x.dtype == centers.dtype == torch.float32
     choice = torch.empty((n,), dtype=torch.int32, device=x.device)
     iters = torch.empty((1,), dtype=torch.int32, device=x.device)
-    _ck(_L().toist_kmeans(x.data_ptr(), centers.data_ptr(), choice.data_ptr(), iters.data_ptr(), n, d, k, float(tol),
-                          int(max_iter), _stream()))
+    xt = torch.empty((d, n), dtype=torch.float32, device=x.device)  # transposed bank (coalesced assignment step)
+    _ck(_L().toist_kmeans(x.data_ptr(), centers.data_ptr(), choice.data_ptr(), iters.data_ptr(), xt.data_ptr(), n, d, k,
+                          float(tol), int(max_iter), _stream()))
     return choice, iters
 
 

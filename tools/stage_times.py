@@ -48,6 +48,28 @@ def main():
         total = sum(losses[k] * wd[k] for k in losses if k in wd)
         total.backward()
 
+    def traced_step(log):
+        """The same step with (label, host clock, CUDA event) probes between the calls: shows whether a gap on the
+        device is the host being late or device-side work / dependencies."""
+        def probe(label):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            log.append((label, time.perf_counter(), ev))
+
+        probe("step start")
+        optimizer.zero_grad()
+        probe("zero_grad done")
+        mc = model(s, captions, encode_and_save=True)
+        probe("phase A issued")
+        out = model(s, captions, encode_and_save=False, memory_cache=mc)
+        probe("phase B issued")
+        losses = criterion(mc, out, tg, pmd, None)
+        probe("criterion issued")
+        total = sum(losses[k] * wd[k] for k in losses if k in wd)
+        probe("weighted sum issued")
+        total.backward()
+        probe("backward issued")
+
     for _ in range(4):
         step()
     torch.cuda.synchronize()
@@ -72,6 +94,17 @@ def main():
     base = marks[-2]
     for ph, sig, n, e0, e1 in last:
         print(f"  start {base.elapsed_time(e0):7.3f} ms  dur {e0.elapsed_time(e1):7.3f} ms  {n:4d} launches  {ph} {sig}")
+    # host clock vs device clock at the call boundaries of a step, once with the host running ahead (back-to-back steps)
+    R.GraphCache.timing = None
+    for _ in range(3):
+        step()
+    log = []
+    traced_step(log)
+    torch.cuda.synchronize()
+    h0, e0 = log[0][1], log[0][2]
+    print("probe                      host ms   device ms   (device time = when the GPU reached the probe)")
+    for label, h, ev in log:
+        print(f"  {label:24s} {(h - h0) * 1e3:7.3f}   {e0.elapsed_time(ev):8.3f}")
 
 
 if __name__ == "__main__":
