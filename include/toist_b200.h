@@ -369,6 +369,12 @@ int toist_lsap_batched(const float* cost, const int32_t* n_rows, const int32_t* 
  * xt_workspace: f32 [dim, n] scratch for the transposed bank (may be null: slower row-strided access, same results). */
 int toist_kmeans(const float* x, float* centers, int32_t* choice, int32_t* iters, float* xt_workspace, int32_t n,
                  int32_t dim, int32_t k, float tol, int32_t max_iter, void* stream);
+/* One launch for several INDEPENDENT problems (one CTA each): problem p clusters bank task_of[p] of banks [n_tasks, n, dim]
+ * from centers [p, k, dim] (in place); choice [p, n]; iters [p] (may be null); xt_workspace [p, dim, n] (may be null);
+ * query [p, dim] -> query_choice[p] = nearest final centre (toist_kmeans_predict arithmetic), both may be null. */
+int toist_kmeans_batched(const float* banks, const int32_t* task_of, float* centers, int32_t* choice, int32_t* iters,
+                         float* xt_workspace, const float* query, int32_t* query_choice, int32_t n_problems, int32_t n,
+                         int32_t dim, int32_t k, float tol, int32_t max_iter, void* stream);
 int toist_kmeans_predict(const float* x, const float* centers, int32_t* choice, int32_t m, int32_t dim, int32_t k,
                          void* stream);
 /* out[b, :] = sum_t w[b, t] * x[t, b, :]   (x f32 [n_tokens, batch, dim]; w = selection / count gives the token means of

@@ -118,9 +118,12 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMa
         "r"(c2), "r"(c3)
       : "memory");
 }
-// arrive (count 1, no transaction bytes) on the leader CTA's copy of `bar`
+// arrive (count 1, no transaction bytes) on the leader CTA's copy of `bar`.  Relaxed: the arrival only says "this
+// CTA's loads of the stage have been issued"; the data itself is published by the loads' complete_tx on the same
+// barrier.  (A release at cluster scope here stalled the peer's producer thread for ~2000 clocks per stage: the
+// cta_group::2 kernel ran at a QUARTER of the tensor rate, profiles/r02_ncu_2sm_notes.md.)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
                : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -264,9 +264,41 @@ __device__ __forceinline__ void kmeans_assign(const float* __restrict__ XT, cons
   }
 }
 
-__global__ void kmeans_kernel(const float* __restrict__ X, float* __restrict__ centers, int* __restrict__ choice,
-                              int* __restrict__ iters, float* __restrict__ xt, int N, int D, int K, float tol,
-                              int max_iter) {
+template <int KK>
+__device__ __forceinline__ void kmeans_update(const float* __restrict__ X, const int* __restrict__ choice,
+                                              const int* __restrict__ cnt, float* __restrict__ cen,
+                                              float* __restrict__ shift2, int N, int D) {
+  // thread d owns column d of every centre: ONE pass over X, `member ? x : 0` added to each cluster's running sum in
+  // point order (bit-identical to summing the members only)
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc[KK];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) acc[k] = 0.f;
+#pragma unroll 8
+    for (int n = 0; n < N; ++n) {
+      const float x = X[(size_t)n * D + d];
+      const int c = choice[n];
+#pragma unroll
+      for (int k = 0; k < KK; ++k) acc[k] += (c == k) ? x : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      if (cnt[k] == 0) continue;  // an empty cluster keeps its centre (kmeans.py:70-72)
+      const float nc = acc[k] / (float)cnt[k];
+      const float df = nc - cen[k * D + d];
+      atomicAdd(&shift2[k], df * df);
+      cen[k * D + d] = nc;
+    }
+  }
+}
+
+// grid = number of problems.  Problem p clusters bank `task_of[p]` of X_base [n_tasks, N, D] (task_of null: X_base is
+// the single bank) from centers [p, K, D] (in place); choice [p, N]; iters [p]; xt [p, D, N] workspace (may be null);
+// query [p, D] (may be null) -> qchoice[p] = nearest final centre of the query (kmeans_predict arithmetic).
+__global__ void kmeans_kernel(const float* __restrict__ X_base, const int* __restrict__ task_of,
+                              float* __restrict__ centers_all, int* __restrict__ choice_all, int* __restrict__ iters,
+                              float* __restrict__ xt_all, const float* __restrict__ query, int* __restrict__ qchoice,
+                              int N, int D, int K, float tol, int max_iter) {
   pdl_prologue();
   extern __shared__ float km_smem[];
   float* cen = km_smem;                 // [K, D]
@@ -274,6 +306,11 @@ __global__ void kmeans_kernel(const float* __restrict__ X, float* __restrict__ c
   int* cnt = reinterpret_cast<int*>(shift2 + K);  // [K]
   __shared__ int done;
   __shared__ float tile[32][33];
+  const int prob = blockIdx.x;
+  const float* X = X_base + (task_of != nullptr ? (size_t)task_of[prob] * N * D : 0);
+  float* centers = centers_all + (size_t)prob * K * D;
+  int* choice = choice_all + (size_t)prob * N;
+  float* xt = xt_all != nullptr ? xt_all + (size_t)prob * D * N : nullptr;
   for (int i = threadIdx.x; i < K * D; i += blockDim.x) cen[i] = centers[i];
   if (threadIdx.x == 0) done = 0;
   const bool fast = xt != nullptr && K <= kKmMaxK && blockDim.x == 1024;
@@ -330,20 +367,30 @@ __global__ void kmeans_kernel(const float* __restrict__ X, float* __restrict__ c
     __syncthreads();
     for (int n = threadIdx.x; n < N; n += blockDim.x) atomicAdd(&cnt[choice[n]], 1);
     __syncthreads();
-    // update: mean of the members; an empty cluster keeps its centre (kmeans.py:70-72)
-    for (int e = threadIdx.x; e < K * D; e += blockDim.x) {
-      const int k = e / D, d = e % D;
-      if (cnt[k] == 0) continue;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int n = 0; n < N; ++n) {
-        const float x = X[(size_t)n * D + d];
-        acc += (choice[n] == k) ? x : 0.f;  // + 0 leaves the running sum unchanged bit for bit
+    // update: mean of the members
+    if (K <= kKmMaxK) {
+      switch (K) {
+        case 1: kmeans_update<1>(X, choice, cnt, cen, shift2, N, D); break;
+        case 2: kmeans_update<2>(X, choice, cnt, cen, shift2, N, D); break;
+        case 3: kmeans_update<3>(X, choice, cnt, cen, shift2, N, D); break;
+        case 4: kmeans_update<4>(X, choice, cnt, cen, shift2, N, D); break;
+        case 5: kmeans_update<5>(X, choice, cnt, cen, shift2, N, D); break;
+        case 6: kmeans_update<6>(X, choice, cnt, cen, shift2, N, D); break;
+        case 7: kmeans_update<7>(X, choice, cnt, cen, shift2, N, D); break;
+        default: kmeans_update<8>(X, choice, cnt, cen, shift2, N, D); break;
       }
-      const float nc = acc / (float)cnt[k];
-      const float df = nc - cen[e];
-      atomicAdd(&shift2[k], df * df);
-      cen[e] = nc;
+    } else {
+      for (int e = threadIdx.x; e < K * D; e += blockDim.x) {
+        const int k = e / D, d = e % D;
+        if (cnt[k] == 0) continue;
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n)
+          if (choice[n] == k) acc += X[(size_t)n * D + d];
+        const float nc = acc / (float)cnt[k];
+        const float df = nc - cen[e];
+        atomicAdd(&shift2[k], df * df);
+        cen[e] = nc;
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -358,7 +405,26 @@ __global__ void kmeans_kernel(const float* __restrict__ X, float* __restrict__ c
     }
   }
   for (int i = threadIdx.x; i < K * D; i += blockDim.x) centers[i] = cen[i];
-  if (threadIdx.x == 0 && iters != nullptr) iters[0] = it;
+  if (threadIdx.x == 0 && iters != nullptr) iters[prob] = it;
+  if (query != nullptr && threadIdx.x < 32) {  // nearest final centre of the query: kmeans_predict_kernel's arithmetic
+    const int lane = threadIdx.x;
+    const float* q = query + (size_t)prob * D;
+    float best = INFINITY;
+    int bk = 0;
+    for (int k = 0; k < K; ++k) {
+      float acc = 0.f;
+      for (int d = lane; d < D; d += 32) {
+        const float df = q[d] - cen[(size_t)k * D + d];
+        acc += df * df;
+      }
+      acc = warp_sum(acc);
+      if (acc < best) {
+        best = acc;
+        bk = k;
+      }
+    }
+    if (lane == 0) qchoice[prob] = bk;
+  }
 }
 
 // choice[m] = argmin_k ||x_m - c_k||^2 (kmeans_predict, kmeans.py:99-133); one warp per row
@@ -533,8 +599,24 @@ int toist_kmeans(const float* x, float* centers, int32_t* choice, int32_t* iters
   TOIST_REQUIRE(n >= 1 && dim >= 1 && k >= 1 && max_iter >= 1, "toist_kmeans: bad sizes");
   const size_t smem = ((size_t)k * dim + 2 * k) * sizeof(float);
   TOIST_REQUIRE(smem <= 48 * 1024, "toist_kmeans: %d x %d centres do not fit shared memory", k, dim);
-  launch_pdl(kmeans_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream, x, centers, choice, iters, xt_workspace, n, dim, k,
-             tol, max_iter);
+  launch_pdl(kmeans_kernel, dim3(1), dim3(1024), smem, (cudaStream_t)stream, x, (const int*)nullptr, centers, (int*)choice,
+             (int*)iters, xt_workspace, (const float*)nullptr, (int*)nullptr, (int)n, (int)dim, (int)k, tol, (int)max_iter);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_kmeans_batched(const float* banks, const int32_t* task_of, float* centers, int32_t* choice, int32_t* iters,
+                         float* xt_workspace, const float* query, int32_t* query_choice, int32_t n_problems, int32_t n,
+                         int32_t dim, int32_t k, float tol, int32_t max_iter, void* stream) {
+  TOIST_REQUIRE(banks && task_of && centers && choice, "toist_kmeans_batched: null pointer");
+  TOIST_REQUIRE((query == nullptr) == (query_choice == nullptr), "toist_kmeans_batched: query needs query_choice");
+  TOIST_REQUIRE(n >= 1 && dim >= 1 && k >= 1 && max_iter >= 1 && n_problems >= 0, "toist_kmeans_batched: bad sizes");
+  if (n_problems == 0) return TOIST_OK;
+  const size_t smem = ((size_t)k * dim + 2 * k) * sizeof(float);
+  TOIST_REQUIRE(smem <= 48 * 1024, "toist_kmeans_batched: %d x %d centres do not fit shared memory", k, dim);
+  launch_pdl(kmeans_kernel, dim3((unsigned)n_problems), dim3(1024), smem, (cudaStream_t)stream, banks, (const int*)task_of,
+             centers, (int*)choice, (int*)iters, xt_workspace, query, (int*)query_choice, (int)n, (int)dim, (int)k, tol,
+             (int)max_iter);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

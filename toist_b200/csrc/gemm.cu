@@ -754,7 +754,11 @@ static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 gr
     sk = std::max(sk, (staging + stage_bytes - 1) / stage_bytes);
   }
   if (kp.cluster == 3 && bn == 256) {  // 32 KB stages: six of them, the epilogue needs at most four (res + mask tiles)
-    kp.stages = 6;
+    static const int st2 = []() {  // TOIST_GEMM_2SM_STAGES: ring depth of the cta_group::2 variant (experiments)
+      const char* e = getenv("TOIST_GEMM_2SM_STAGES");
+      return e ? std::max(4, std::min(6, atoi(e))) : 6;
+    }();
+    kp.stages = st2;
     return dispatch_epi<256, MODE>(maps, kp, grid, stream);
   }
   switch (bn) {

@@ -1165,6 +1165,24 @@ def kmeans(x: torch.Tensor, centers: torch.Tensor, tol: float = 1e-4, max_iter: 
     return choice, iters
 
 
+def kmeans_batched(banks: torch.Tensor, task_of: torch.Tensor, centers: torch.Tensor, query: torch.Tensor,
+                   tol: float = 1e-4, max_iter: int = 10000) -> torch.Tensor:
+    """Independent k-means problems in one launch: problem p clusters banks[task_of[p]] ([N, D]) from centers[p] [K, D]
+    (updated in place).  Returns the index [P] of the final centre nearest to query[p] [D]."""
+    t, n, d = banks.shape
+    p, k, _ = centers.shape
+    assert banks.is_contiguous() and centers.is_contiguous() and query.is_contiguous() and query.shape == (p, d)
+    assert task_of.dtype == torch.int32 and task_of.numel() == p
+    dev = banks.device
+    choice = torch.empty((p, n), dtype=torch.int32, device=dev)
+    xt = torch.empty((p, d, n), dtype=torch.float32, device=dev)
+    qc = torch.empty((p,), dtype=torch.int32, device=dev)
+    _ck(_L().toist_kmeans_batched(banks.data_ptr(), task_of.data_ptr(), centers.data_ptr(), choice.data_ptr(), None,
+                                  xt.data_ptr(), query.data_ptr(), qc.data_ptr(), p, n, d, k, float(tol), int(max_iter),
+                                  _stream()))
+    return qc
+
+
 def kmeans_predict(x: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
     m, d = x.shape
     choice = torch.empty((m,), dtype=torch.int32, device=x.device)

@@ -189,6 +189,53 @@ class ClusterCriterion(nn.Module):
         feature = centers.index_select(0, choice.long())[0]
         return choice, feature
 
+    def memory_cluster_many(self, feats: torch.Tensor, tasks: List[int], active: List[bool]) -> torch.Tensor:
+        """`memory_cluster` for every active sample of a batch, in the reference's order (models/mdetr.py:196-209,
+        260-270 loop over the samples), with the samples whose tasks are pairwise distinct clustered by ONE launch:
+        k-means runs on different banks are independent; a sample whose task already occurred in the current group
+        starts a new group, so that it sees the centres its predecessor left (the sequential dependency of the loop).
+        numpy's generator is drawn from in sample order, as the loop does.  Returns [bs, D]: the centre chosen for each
+        sample, read AFTER its group's update of `cluster_centers` (zeros for inactive samples)."""
+        bs, D = feats.shape
+        dev = feats.device
+        full, _ = self._host_state()
+        chosen = torch.zeros((bs, D), dtype=torch.float32, device=dev)
+        group: List[int] = []
+        inits: List[torch.Tensor] = []
+
+        def flush():
+            if not group:
+                return
+            tk = torch.as_tensor([tasks[i] for i in group], dtype=torch.int64)
+            task_dev = h2d(tk.to(torch.int32), dev)
+            centers = torch.stack(inits).contiguous()
+            rows = h2d(torch.as_tensor(group, dtype=torch.int64), dev)
+            q = feats.index_select(0, rows).contiguous()
+            qc = K.kmeans_batched(self.feature_bank, task_dev, centers, q)
+            task_long = h2d(tk, dev)
+            self.cluster_centers.index_copy_(0, task_long, centers)
+            pick = torch.arange(len(group), device=dev) * self.cluster_num + qc.long()
+            chosen.index_copy_(0, rows, centers.view(-1, D).index_select(0, pick))
+            group.clear()
+            inits.clear()
+
+        for i in range(bs):
+            if not active[i]:
+                continue
+            t = tasks[i]
+            if any(tasks[j] == t for j in group):
+                flush()
+            bank = self.feature_bank[t]
+            if full[t] == 0:
+                pick = np.random.choice(bank.shape[0], self.cluster_num, replace=False)
+                inits.append(bank[h2d(torch.as_tensor(pick, dtype=torch.int64), dev)])
+            else:
+                # (a task repeated inside the batch was flushed above: the stored centres are up to date)
+                inits.append(self.cluster_centers[t].clone())
+            group.append(i)
+        flush()
+        return chosen
+
     # ---- teacher side
     def update_memory(self, memory_cache_noun, targets_noun, captions_noun):
         """models/mdetr.py:105-211."""
@@ -214,13 +261,10 @@ class ClusterCriterion(nn.Module):
         task_col = torch.as_tensor(tasks, dtype=torch.float32, device=dev).view(-1, 1)
         with torch.no_grad():
             self.update_memory_queue(torch.cat([feature_list, task_col], dim=-1), tasks)
-            chosen = torch.zeros((bs, D), dtype=torch.float32, device=dev)
             for i in range(bs):
                 if skip[i]:
                     sel[i] = 0
-                    continue
-                choice, _ = self.memory_cluster(feats[i], tasks[i])
-                chosen[i] = self.cluster_centers[tasks[i]].index_select(0, choice.long())[0]
+            chosen = self.memory_cluster_many(feats, tasks, [not s_ for s_ in skip])
         sel_dev = torch.from_numpy(sel).to(dev)
         memory_cache_noun["img_memory_mod"] = _TokenReplace.apply(memory_cache_noun["img_memory"], sel_dev, chosen, T)
         memory_cache_noun["full_label"] = self.full_label
@@ -249,14 +293,11 @@ class ClusterCriterion(nn.Module):
         w_dev, sel_dev = torch.from_numpy(w).to(dev), torch.from_numpy(sel).to(dev)
         feats = _TokenWeightedSum.apply(text, w_dev)  # temp_token_feature of every sample, differentiable
         tasks = [int(t["dataset_name"].split("_")[1]) - 1 for t in targets_sth]
-        chosen = torch.zeros((bs, D), dtype=torch.float32, device=dev)     # cluster_centers[task, choice] at fill time
-        centre = torch.zeros((bs, D), dtype=torch.float32, device=dev)     # the centre the loss compares against
         with torch.no_grad():
-            fd = feats.detach()
-            for i in range(bs):
-                choice, centre_i = self.memory_cluster(fd[i], tasks[i])
-                centre[i] = centre_i
-                chosen[i] = self.cluster_centers[tasks[i]].index_select(0, choice.long())[0]
+            # cluster_centers[task, choice] right after the sample's own k-means: both the replacement feature and the
+            # centre the loss compares against (models/mdetr.py:262-270 read the same tensor)
+            chosen = self.memory_cluster_many(feats.detach().contiguous(), tasks, [True] * bs)
+            centre = chosen
         memory_cache_sth["img_memory_mod"] = _TokenReplace.apply(memory_cache_sth["img_memory"], sel_dev, chosen, T)
         use = torch.ones(bs, dtype=torch.uint8, device=dev)
         loss_feature = _MseRows.apply(feats, centre, use) if bs else torch.zeros((), device=dev)
@@ -271,11 +312,8 @@ class ClusterCriterion(nn.Module):
         w, sel = self._something(memory_cache_sth["tokenized"], captions, T)
         with torch.no_grad():
             feats = K.token_wsum(text.detach().contiguous(), torch.from_numpy(w).to(dev))
-            chosen = torch.zeros((bs, D), dtype=torch.float32, device=dev)
-            for i in range(bs):
-                task = int(dataset_name_list[i].split("_")[1]) - 1
-                choice, _ = self.memory_cluster(feats[i], task)
-                chosen[i] = self.cluster_centers[task].index_select(0, choice.long())[0]
+            tasks = [int(name.split("_")[1]) - 1 for name in dataset_name_list]
+            chosen = self.memory_cluster_many(feats, tasks, [True] * bs)
         memory_cache_sth["img_memory_mod"] = _TokenReplace.apply(memory_cache_sth["img_memory"],
                                                                  torch.from_numpy(sel).to(dev), chosen, T)
         return memory_cache_sth

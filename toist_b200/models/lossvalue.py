@@ -22,87 +22,92 @@ from ..util.misc import h2d
 
 class _Bundle:
     """One criterion output tensor [rows, L] (fp32, with grad_fn when anything upstream trains)."""
-    __slots__ = ("out", "flat")
+    __slots__ = ("out", "flat", "plain")
 
     def __init__(self, out: torch.Tensor):
         self.out = out
         self.flat = out.reshape(-1)
+        self.plain = self.flat.detach()  # values without autograd history: storage behind the LossValue objects
 
 
 _NUM = (int, float)
+_make = torch.Tensor._make_subclass
 
 
 class LossValue(torch.Tensor):
-    @staticmethod
-    def cell(bundle: _Bundle, index: int, requires_grad: bool) -> "LossValue":
-        v = torch.Tensor._make_subclass(LossValue, bundle.flat.detach()[index])
-        v._lv = ({id(bundle): (bundle, {index: 1.0})}, [], requires_grad)
-        return v
+    """_lv = (terms {(id(bundle), cell index): coefficient}, bundles {id: bundle}, extras [(tensor, coef)], requires_grad).
+    The tensor storage behind the object is a placeholder (the first cell it refers to): every read goes through
+    __torch_function__, which materialises the real value."""
 
     @staticmethod
-    def _new(terms, extras, requires_grad, like: torch.Tensor) -> "LossValue":
-        v = torch.Tensor._make_subclass(LossValue, like.detach().as_subclass(torch.Tensor).reshape(()))
-        v._lv = (terms, extras, requires_grad)
+    def cell(bundle: _Bundle, index: int, requires_grad: bool) -> "LossValue":
+        plain = bundle.plain[index]
+        v = _make(LossValue, plain)
+        v._lv = ({(id(bundle), index): 1.0}, {id(bundle): bundle}, (), requires_grad)
+        v._plain = plain
+        return v
+
+    def _derive(self, terms, bundles, extras, rg) -> "LossValue":
+        v = _make(LossValue, self._plain)  # shares the placeholder storage: no kernel, no copy
+        v._lv = (terms, bundles, extras, rg)
+        v._plain = self._plain
         return v
 
     # ------------------------------------------------------------------ symbolic algebra
     def _scaled(self, a: float) -> "LossValue":
-        terms, extras, rg = self._lv
-        t2 = {k: (b, {i: c * a for i, c in d.items()}) for k, (b, d) in terms.items()}
-        return LossValue._new(t2, [(t, c * a) for t, c in extras], rg, self)
+        terms, bundles, extras, rg = self._lv
+        return self._derive({k: c * a for k, c in terms.items()}, bundles, tuple((t, c * a) for t, c in extras), rg)
 
     def _plus(self, other) -> "LossValue":
-        terms, extras, rg = self._lv
-        t2 = {k: (b, dict(d)) for k, (b, d) in terms.items()}
-        e2 = list(extras)
+        terms, bundles, extras, rg = self._lv
         if isinstance(other, LossValue):
-            ot, oe, org = other._lv
-            for k, (b, d) in ot.items():
-                if k in t2:
-                    dst = t2[k][1]
-                    for i, c in d.items():
-                        dst[i] = dst.get(i, 0.0) + c
-                else:
-                    t2[k] = (b, dict(d))
-            e2 += oe
-            rg = rg or org
-        else:  # an ordinary tensor (e.g. loss_cluster_feature): carried along, added when materialised / differentiated
-            e2.append((other, 1.0))
-            rg = rg or bool(other.requires_grad)
-        return LossValue._new(t2, e2, rg, self)
+            ot, ob, oe, org = other._lv
+            t2 = dict(terms)
+            for k, c in ot.items():
+                t2[k] = t2.get(k, 0.0) + c
+            b2 = bundles if ob.keys() <= bundles.keys() else {**bundles, **ob}
+            return self._derive(t2, b2, extras + oe, rg or org)
+        # an ordinary tensor (e.g. loss_cluster_feature): carried along, added when materialised / differentiated
+        return self._derive(terms, bundles, extras + ((other, 1.0),), rg or bool(other.requires_grad))
+
+    def _coef_vectors(self):
+        """[(bundle, host fp32 coefficient vector over its cells)]"""
+        terms, bundles, _, _ = self._lv
+        vecs = {}
+        for (bid, i), c in terms.items():
+            w = vecs.get(bid)
+            if w is None:
+                w = vecs[bid] = torch.zeros(bundles[bid].flat.numel(), dtype=torch.float32)
+            w[i] = c
+        return [(bundles[bid], w) for bid, w in vecs.items()]
 
     def materialize(self) -> torch.Tensor:
         """The ordinary (differentiable) tensor this value stands for."""
-        terms, extras, rg = self._lv
+        terms, bundles, extras, rg = self._lv
         total = None
-        for b, d in terms.values():
-            idx = sorted(d)
-            if len(idx) == 1 and d[idx[0]] == 1.0:
-                part = b.flat[idx[0]]
-            else:
-                w = torch.zeros(b.flat.numel(), dtype=torch.float32)
-                for i in idx:
-                    w[i] = d[i]
+        if len(terms) == 1 and not extras:
+            ((bid, i), c), = terms.items()
+            total = bundles[bid].flat[i]
+            if c != 1.0:
+                total = total * c
+        else:
+            for b, w in self._coef_vectors():
                 part = (b.flat * h2d(w, b.flat.device)).sum()
-            total = part if total is None else total + part
-        for t, c in extras:
-            part = t if c == 1.0 else t * c
-            total = part if total is None else total + part
+                total = part if total is None else total + part
+            for t, c in extras:
+                part = t if c == 1.0 else t * c
+                total = part if total is None else total + part
         return total if rg else total.detach()
 
     def _backward(self, gradient=None, retain_graph=None, create_graph=False, inputs=None):
-        terms, extras, rg = self._lv
+        _, _, extras, _ = self._lv
         if gradient is not None or create_graph or inputs is not None:
             return self.materialize().backward(gradient, retain_graph, create_graph, inputs=inputs)
         roots, grads = [], []
-        for b, d in terms.values():
-            if not b.out.requires_grad:
-                continue
-            w = torch.zeros(b.flat.numel(), dtype=torch.float32)
-            for i, c in d.items():
-                w[i] = c
-            roots.append(b.out)
-            grads.append(h2d(w, b.out.device).view(b.out.shape))
+        for b, w in self._coef_vectors():
+            if b.out.requires_grad:
+                roots.append(b.out)
+                grads.append(h2d(w, b.out.device).view(b.out.shape))
         for t, c in extras:
             if t.requires_grad:
                 roots.append(t)
@@ -114,29 +119,29 @@ class LossValue(torch.Tensor):
     # ------------------------------------------------------------------ dispatch
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
-        kwargs = kwargs or {}
         name = getattr(func, "__name__", "")
-        if name in ("mul", "__mul__", "__rmul__") and len(args) == 2 and not kwargs:
+        if not kwargs and len(args) == 2:
             a, b = args
-            if isinstance(a, LossValue) and isinstance(b, _NUM):
-                return a._scaled(float(b))
-            if isinstance(b, LossValue) and isinstance(a, _NUM):
-                return b._scaled(float(a))
-        elif name in ("add", "__add__", "__radd__") and len(args) == 2 and not kwargs:
-            a, b = args
-            if isinstance(b, LossValue) and not isinstance(a, LossValue):
-                a, b = b, a
-            if isinstance(a, LossValue):
-                if isinstance(b, _NUM) and b == 0:
-                    return a  # sum() starts from 0
-                if isinstance(b, torch.Tensor) and b.dim() == 0:
-                    return a._plus(b)
-        elif name == "backward" and isinstance(args[0], LossValue):
-            return args[0]._backward(*args[1:], **kwargs)
-        elif name == "__get__" and len(args) == 1 and isinstance(args[0], LossValue):
-            prop = getattr(func, "__self__", None)
-            if prop is torch.Tensor.requires_grad:
-                return args[0]._lv[2]
+            if name in ("mul", "__mul__", "__rmul__"):
+                if type(a) is LossValue and isinstance(b, _NUM):
+                    return a._scaled(float(b))
+                if type(b) is LossValue and isinstance(a, _NUM):
+                    return b._scaled(float(a))
+            elif name in ("add", "__add__", "__radd__"):
+                if type(b) is LossValue and type(a) is not LossValue:
+                    a, b = b, a
+                if type(a) is LossValue:
+                    if isinstance(b, _NUM):
+                        if b == 0:
+                            return a  # sum() starts from 0
+                    elif isinstance(b, torch.Tensor) and b.dim() == 0:
+                        return a._plus(b)
+        if name == "backward" and type(args[0]) is LossValue:
+            return args[0]._backward(*args[1:], **(kwargs or {}))
+        if name == "__get__" and len(args) == 1 and type(args[0]) is LossValue \
+                and getattr(func, "__self__", None) is torch.Tensor.requires_grad:
+            return args[0]._lv[3]
+        kwargs = kwargs or {}
         with torch._C.DisableTorchFunctionSubclass():
             real = [a.materialize() if isinstance(a, LossValue) else
                     type(a)(x.materialize() if isinstance(x, LossValue) else x for x in a) if isinstance(a, (list, tuple)) else a
