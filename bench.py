@@ -332,6 +332,7 @@ def run_ours(a):
     from toist_b200.util.optim import FusedAdamW
 
     named = list(model.named_parameters())
+    touched = next(p for _, p in named if p.requires_grad)
     optimizer = FusedAdamW(  # the three parameter groups of main.py:351-367; the step calls its zero_grad like engine.py:86
         [{"params": [p for n, p in named if "backbone" not in n and "text_encoder" not in n and p.requires_grad]},
          {"params": [p for n, p in named if "backbone" in n and p.requires_grad], "lr": 1e-5},
@@ -353,6 +354,10 @@ def run_ours(a):
         total = sum(losses[k] * weight_dict[k] for k in losses.keys() if k in weight_dict)
         optimizer.zero_grad()  # right before backward(), as in engine.py:86-87
         total.backward()
+        # The optimizer step is not part of this metric, but its effect on the NEXT forward is: in training the masters
+        # change every step, so the bf16 shadow weights are refreshed every step (toist_weight_prep, ~0.3 ms).  The
+        # refresh is skipped when no master changed (runtime.ShadowBank.ensure): tell it they did.
+        torch.autograd.graph.increment_version(touched)
         return total
 
     def barrier():
@@ -543,6 +548,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "dropout": a.dropout,
                        "cuda_graphs": not a.no_graphs, "direct_param_grads": not a.no_direct, "fused_loss_sum": not a.no_fused_loss_sum,
                        "l2": "320 MB buffer rewritten between steps (> 126 MB L2)",
+                       "weights": "marked as changed after every backward (the bf16 shadow refresh runs every step, as in training)",
                        "parallelism": f"dp{world}" + ((" (torch DDP bucketed NCCL all-reduce)" if a.torch_ddp else
                                                               " (flat NCCL all-reduce per backward stage, side stream)")
                                                              if world > 1 else "")},
@@ -629,6 +635,7 @@ def run_other(a):
                    {"params": [p for n, p in named if "backbone" in n and p.requires_grad], "lr": 1e-5},
                    {"params": [p for n, p in named if "text_encoder" in n and p.requires_grad], "lr": 5e-5}]
     optimizer = FusedAdamW([g for g in groups if g["params"]], lr=1e-4, weight_decay=1e-4)
+    touched = [next(p for p in m.parameters() if p.requires_grad) for m in models]
 
     def host_batch(seed, noun):
         images, mask, captions, targets, pm = make_batch(batch, SIZE, TOKENS, seed=seed, masks=seg)
@@ -664,6 +671,8 @@ def run_other(a):
         total = sum(losses[k] * weight_dict[k] for k in losses.keys() if k in weight_dict)
         optimizer.zero_grad()
         total.backward()
+        for t in touched:  # as in run_ours: the masters changed, every model refreshes its bf16 shadows next step
+            torch.autograd.graph.increment_version(t)
         return total
 
     flush = torch.empty(80 * 1024 * 1024, dtype=torch.float32, device=dev)

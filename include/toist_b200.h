@@ -219,6 +219,18 @@ int toist_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, cons
 int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const void* x, int32_t x_dtype,
                         const float* mean, const float* rstd, const float* gamma, void* dx, int32_t dx_dtype,
                         float* dgamma, float* dbeta, int64_t rows, int32_t n, void* stream);
+/* Fused residual branch of a transformer layer (transformer.py:298-303,378-407: dropoutN + residual + normN, and the
+ * `+ pos` / `+ query_pos` in front of the next attention), bf16 rows of 256 / 512 / 768 elements:
+ *   s = res + dropout(x)  (res nullable; p_drop = 0: no dropout), sum_out (nullable) = s, y = LayerNorm(s),
+ *   y_add = y + add (both nullable).  Every value is rounded to bf16 where the separate kernels round it.
+ * toist_layernorm_bwd_drop additionally writes dx_drop = dropout-backward(dx) with the decisions of `site`.
+ * Return TOIST_ERR_UNSUPPORTED for other widths / alignments (the caller falls back to the separate kernels). */
+int toist_layernorm_fused_fwd(const void* x, const void* res, const void* add, const float* gamma, const float* beta,
+                              void* sum_out, void* y, void* y_add, float* mean, float* rstd, int64_t rows, int32_t n,
+                              float eps, float p_drop, const uint64_t* seed, uint32_t site, void* stream);
+int toist_layernorm_bwd_drop(const void* dy, const void* dy2, const void* x, const float* mean, const float* rstd,
+                             const float* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta, int64_t rows,
+                             int32_t n, float p_drop, const uint64_t* seed, uint32_t site, void* stream);
 int toist_l2norm_fwd(const float* x, float* y, float* nrm, int64_t rows, int32_t n, float eps, void* stream);
 int toist_l2norm_bwd(const float* dy, const float* y, const float* nrm, float* dx, int64_t rows, int32_t n,
                      void* stream);

@@ -114,8 +114,8 @@ def main():
             x = src
             outs = [src.clone()]
             for i in range(model.transformer.encoder.num_layers):
-                x, _ = Bk.encoder_layer_fwd(R.WView(w, f"transformer.encoder.layers.{i}."), x, pos16, key,
-                                            model.transformer.nhead, B, None)
+                x = Bk.encoder_layer_fwd(R.WView(w, f"transformer.encoder.layers.{i}."), x, pos16, key,
+                                         model.transformer.nhead, B, None)[0]
                 outs.append(x)
             return outs
 

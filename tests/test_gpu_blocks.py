@@ -76,6 +76,7 @@ def ffn_sd(E, F):
 def test_encoder_layer():
     from oracle import model as O
     from toist_b200 import blocks as Bk
+    from toist_b200 import kernels as K
 
     torch.manual_seed(0)
     E, S, B, H = 256, 61, 2, 8
@@ -84,9 +85,9 @@ def test_encoder_layer():
     km = torch.zeros(B, S, dtype=torch.uint8, device=DEV)
     km[1, S - 5:] = 1
     g = {}
-    y, saved = Bk.encoder_layer_fwd(split_w(sd), x.to(BF), pos.to(BF), km, H, B)
+    y, saved, _ = Bk.encoder_layer_fwd(split_w(sd), x.to(BF), pos.to(BF), km, H, B)
     dy = rnd(S * B, E)
-    dx = Bk.encoder_layer_bwd(split_w(sd), g, set(sd), dy.to(BF), saved, H, B)
+    dx = K.add_bf16(*Bk.encoder_layer_bwd(split_w(sd), g, set(sd), dy.to(BF), saved, H, B))
     ref = leaf({"layers.0." + k: v for k, v in sd.items()})
     xr = x.view(S, B, E).clone().requires_grad_(True)
     yr = O.encoder(xr, km.bool(), pos.view(S, B, E), ref, "", 1, H)
@@ -111,7 +112,7 @@ def test_decoder_layer():
     w = split_w(sd)
     g = {}
     mem_pos = K.add_bf16(mem.to(BF), pos.to(BF))
-    y, saved = Bk.decoder_layer_fwd(w, tgt.to(BF), qpos.to(BF), mem.to(BF), mem_pos, km, H, B)
+    y, saved, _ = Bk.decoder_layer_fwd(w, tgt.to(BF), qpos.to(BF), mem.to(BF), mem_pos, km, H, B)
     dy = rnd(Q * B, E)
     d_tgt, d_qpos, d_mp, d_mem = Bk.decoder_layer_bwd(w, g, set(sd), dy.to(BF), None, saved, H, B)
     ref = leaf({"layers.0." + k: v for k, v in sd.items()})

@@ -98,6 +98,7 @@ def test_encoder_layer_with_dropout_matches_masked_reference():
 
     from test_gpu_blocks import ffn_sd, leaf, ln_sd, mha_sd, split_w
     from toist_b200 import blocks as Bk
+    from toist_b200 import kernels as K
 
     torch.manual_seed(1)
     E, S, B, H, p = 256, 61, 2, 8, 0.1
@@ -109,12 +110,10 @@ def test_encoder_layer_with_dropout_matches_masked_reference():
     seed = torch.tensor([2024], dtype=torch.int64, device=DEV)
     drop = Bk.Drop(p, seed, 1000)
     g = {}
-    y, saved = Bk.encoder_layer_fwd(split_w(sd), x.to(BF), pos.to(BF), km, H, B, drop)
+    y, saved, _ = Bk.encoder_layer_fwd(split_w(sd), x.to(BF), pos.to(BF), km, H, B, drop)
     dy = rnd(S * B, E)
-    dx = Bk.encoder_layer_bwd(split_w(sd), g, set(sd), dy.to(BF), saved, H, B, drop)
+    dx = K.add_bf16(*Bk.encoder_layer_bwd(split_w(sd), g, set(sd), dy.to(BF), saved, H, B, drop))
     # reference with the recovered masks
-    from toist_b200 import kernels as K
-
     if K.fused_attention_ok(S, S, dh):  # the fused kernel draws its own (paired 16-bit) decisions
         p_att, seed_att, site_att = drop.site(0)
         m_att = K.attention_dropout_mask(B, H, S, S, drop.site(0)).float() / (1.0 - round(p_att * 65536) / 65536.0)

@@ -155,6 +155,45 @@ def ln_bwd(w: W, g: G, req: Set[str], pre: str, dy, x, mean, rstd, dy2=None, dx_
     return K.layernorm_bwd(dy, x, mean, rstd, w[pre + "weight"], dy2=dy2, dgamma=dg, dbeta=db, dx_dtype=dx_dtype)
 
 
+def branch_ln_fwd(w: W, x_in, wname: str, bname: str, res, drop_site, ln_pre: str, eps: float, add=None):
+    """One residual branch: LayerNorm(res + dropout(linear(x_in))) and, with `add`, the same plus `add` (the positional
+    / query embedding the next attention adds to its input).  Returns (out, out_add | None, s, mean, rstd) where s is
+    the LayerNorm input the backward needs.  Training mode (dropout) and / or `add` go through the fused kernel
+    (csrc/norm.cu: one launch instead of dropout + LayerNorm + add); results are bit-identical to the separate kernels."""
+    gamma, beta = w[ln_pre + "weight"], w[ln_pre + "bias"]
+    if drop_site is None:
+        s = K.linear_fwd(x_in, w[wname], w[bname], res=res)  # the residual add is the GEMM's epilogue
+        if add is not None and K.fused_ln_ok(s, add):
+            out, out_add, _, m, r = K.layernorm_fused_fwd(s, None, add, gamma, beta, eps, None, want_sum=False)
+            return out, out_add, s, m, r
+        out, _, m, r = K.layernorm_fwd(s, gamma, beta, eps)
+        return out, (K.add_bf16(out, add) if add is not None else None), s, m, r
+    y = K.linear_fwd(x_in, w[wname], w[bname])
+    if K.fused_ln_ok(y, res, add):
+        return K.layernorm_fused_fwd(y, res, add, gamma, beta, eps, drop_site)
+    s = K.dropout(y, drop_site, res=res, out=y)
+    out, _, m, r = K.layernorm_fwd(s, gamma, beta, eps)
+    return out, (K.add_bf16(out, add) if add is not None else None), s, m, r
+
+
+def branch_ln_bwd(w: W, g: G, req: Set[str], ln_pre: str, dy, s, mean, rstd, drop_site, dy2=None):
+    """Backward of `branch_ln_fwd` up to the linear layer's output: returns (ds, d_linear_out) with ds the gradient of
+    the residual sum (it also flows into the residual input) and d_linear_out = dropout-backward(ds)."""
+    if drop_site is None:
+        ds = ln_bwd(w, g, req, ln_pre, dy, s, mean, rstd, dy2=dy2)
+        return ds, ds
+    if K.fused_ln_ok(dy, dy2, s):
+        dg = db = None
+        if (ln_pre + "weight") in req:
+            if (ln_pre + "weight") not in g:
+                g[ln_pre + "weight"] = _zeros((s.shape[1],), s.device)
+                g[ln_pre + "bias"] = _zeros((s.shape[1],), s.device)
+            dg, db = g[ln_pre + "weight"], g[ln_pre + "bias"]
+        return K.layernorm_bwd_drop(dy, s, mean, rstd, w[ln_pre + "weight"], drop_site, dy2=dy2, dgamma=dg, dbeta=db)
+    ds = ln_bwd(w, g, req, ln_pre, dy, s, mean, rstd, dy2=dy2)
+    return ds, K.dropout(ds, drop_site)
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int, drop_site=None):
     """nn.MultiheadAttention up to (excluding) out_proj.  xq/xk/xv: [rows, E] bf16; xq is xk -> fused q|k GEMM."""
@@ -225,19 +264,18 @@ def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int
     return dxq, dxk, dxv
 
 
-def _ffn_fwd(w: W, x, drop: Optional[Drop] = None, k_hidden: int = 0, k_out: int = 1):
-    """x + dropout(linear2(dropout(relu(linear1(x))))).  The hidden dropout is applied in place, so the saved `h` is
-    zero exactly where either the ReLU or the dropout mask is zero."""
+def _ffn_hidden(w: W, x, drop: Optional[Drop], k_hidden: int):
+    """dropout(relu(linear1(x))).  The hidden dropout is applied in place, so the saved `h` is zero exactly where
+    either the ReLU or the dropout mask is zero."""
     h = K.linear_fwd(x, w["linear1.weight"], w["linear1.bias"], act=ACT_RELU)
     if drop is not None:
         K.dropout(h, drop.site(k_hidden), out=h)
-    s = lin_drop_res(h, w["linear2.weight"], w["linear2.bias"], x, _site(drop, k_out))
-    return s, h
+    return h
 
 
-def _ffn_bwd(w: W, g: G, req: Set[str], ds, x, h, drop: Optional[Drop] = None, k_out: int = 1):
-    """ds: gradient of the FFN sum; returns dx including the residual path."""
-    dy = drop_grad(ds, _site(drop, k_out))
+def _ffn_bwd(w: W, g: G, req: Set[str], ds, dy, x, h, drop: Optional[Drop] = None):
+    """ds: gradient of the FFN sum (residual path), dy: gradient of linear2's output (= dropout-backward of ds);
+    returns dx including the residual path."""
     lin_param_grads(g, req, "linear2.weight", "linear2.bias", dy, h, w["linear2.weight"].shape)
     # (h > 0) is the product of the ReLU and hidden-dropout masks; the surviving elements carry the 1/(1-p) factor
     dh = K.linear_dgrad(dy, w["linear2.weight"], mask=h, alpha=1.0 if drop is None else drop.keep_scale)
@@ -246,64 +284,69 @@ def _ffn_bwd(w: W, g: G, req: Set[str], ds, x, h, drop: Optional[Drop] = None, k
 
 
 # ------------------------------------------------------------------------------------------------ encoder layer
-def encoder_layer_fwd(w: W, x, pos, key_mask, nhead: int, B: int, drop: Optional[Drop] = None):
+def encoder_layer_fwd(w: W, x, pos, key_mask, nhead: int, B: int, drop: Optional[Drop] = None, xp=None,
+                      want_next_xp: bool = False):
     """models/transformer.py:290-304 (post-norm).  x, pos [S*B, E] bf16.  Dropout sites (training): 0 attention
-    weights, 1 dropout1, 2 FFN hidden, 3 dropout2."""
-    xp = K.add_bf16(x, pos)
+    weights, 1 dropout1, 2 FFN hidden, 3 dropout2.  `xp` = x + pos when the previous layer already produced it;
+    with `want_next_xp` the output + pos for the next layer comes out of the last LayerNorm launch."""
+    if xp is None:
+        xp = K.add_bf16(x, pos)
     ctx, sv = mha_fwd(w, "self_attn.", xp, xp, x, key_mask, nhead, B, _site(drop, 0))
-    s1 = lin_drop_res(ctx, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], x, _site(drop, 1))
-    x1, _, m1, r1 = ln_fwd(w, "norm1.", s1, 1e-5)
-    s2, h = _ffn_fwd(w, x1, drop, 2, 3)
-    x2, _, m2, r2 = ln_fwd(w, "norm2.", s2, 1e-5)
-    return x2, (sv, ctx, s1, m1, r1, x1, h, s2, m2, r2)
+    x1, _, s1, m1, r1 = branch_ln_fwd(w, ctx, "self_attn.out_proj.weight", "self_attn.out_proj.bias", x, _site(drop, 1),
+                                      "norm1.", 1e-5)
+    h = _ffn_hidden(w, x1, drop, 2)
+    x2, xp_next, s2, m2, r2 = branch_ln_fwd(w, h, "linear2.weight", "linear2.bias", x1, _site(drop, 3), "norm2.", 1e-5,
+                                            add=pos if want_next_xp else None)
+    return x2, (sv, ctx, s1, m1, r1, x1, h, s2, m2, r2), xp_next
 
 
-def encoder_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, drop: Optional[Drop] = None):
+def encoder_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, drop: Optional[Drop] = None, dy2=None):
+    """dy (+ dy2): gradient of the layer output (dy2: the part that arrived through the next layer's x + pos input)."""
     sv, ctx, s1, m1, r1, x1, h, s2, m2, r2 = saved
-    ds2 = ln_bwd(w, g, req, "norm2.", dy, s2, m2, r2)
-    dx1 = _ffn_bwd(w, g, req, ds2, x1, h, drop, 3)
-    ds1 = ln_bwd(w, g, req, "norm1.", dx1, s1, m1, r1)
-    dy1 = drop_grad(ds1, _site(drop, 1))
+    ds2, dlin2 = branch_ln_bwd(w, g, req, "norm2.", dy, s2, m2, r2, _site(drop, 3), dy2=dy2)
+    dx1 = _ffn_bwd(w, g, req, ds2, dlin2, x1, h, drop)
+    ds1, dy1 = branch_ln_bwd(w, g, req, "norm1.", dx1, s1, m1, r1, _site(drop, 1))
     lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", dy1, ctx,
                     w["self_attn.out_proj.weight"].shape)
     dctx = K.linear_dgrad(dy1, w["self_attn.out_proj.weight"])
     dxp, _, dxv = mha_bwd(w, g, req, "self_attn.", dctx, sv, nhead, B, drop_site=_site(drop, 0))
-    return K.add_bf16(ds1, dxp, dxv)  # residual + (q,k) path + v path; pos carries no gradient (sine embedding)
+    # residual + v path = gradient of x itself; dxp = gradient of (x + pos), handed over separately so that the caller
+    # can feed it to the previous layer's LayerNorm backward as its second gradient (pos carries none: sine embedding)
+    return K.add_bf16(ds1, dxv), dxp
 
 
 # ------------------------------------------------------------------------------------------------ decoder layer
-def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: int, drop: Optional[Drop] = None):
+def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: int, drop: Optional[Drop] = None,
+                      tq=None, want_next_tq: bool = False):
     """models/transformer.py:362-408 (post-norm; the text cross-attention is disabled in the reference).  Dropout
-    sites: 0 self-attention weights, 1 dropout1, 2 cross-attention weights, 3 dropout3, 4 FFN hidden, 5 dropout4."""
-    tq = K.add_bf16(tgt, qpos)
+    sites: 0 self-attention weights, 1 dropout1, 2 cross-attention weights, 3 dropout3, 4 FFN hidden, 5 dropout4.
+    `tq` = tgt + qpos when the previous layer already produced it (want_next_tq)."""
+    if tq is None:
+        tq = K.add_bf16(tgt, qpos)
     ctx1, sv1 = mha_fwd(w, "self_attn.", tq, tq, tgt, None, nhead, B, _site(drop, 0))
-    s1 = lin_drop_res(ctx1, w["self_attn.out_proj.weight"], w["self_attn.out_proj.bias"], tgt, _site(drop, 1))
-    t1, _, m1, r1 = ln_fwd(w, "norm1.", s1, 1e-5)
-    cq = K.add_bf16(t1, qpos)
+    t1, cq, s1, m1, r1 = branch_ln_fwd(w, ctx1, "self_attn.out_proj.weight", "self_attn.out_proj.bias", tgt,
+                                       _site(drop, 1), "norm1.", 1e-5, add=qpos)
     ctx2, sv2 = mha_fwd(w, "cross_attn_image.", cq, mem_pos, mem, key_mask, nhead, B, _site(drop, 2))
-    s2 = lin_drop_res(ctx2, w["cross_attn_image.out_proj.weight"], w["cross_attn_image.out_proj.bias"], t1,
-                      _site(drop, 3))
-    t2, _, m2, r2 = ln_fwd(w, "norm3.", s2, 1e-5)
-    s3, h = _ffn_fwd(w, t2, drop, 4, 5)
-    t3, _, m3, r3 = ln_fwd(w, "norm4.", s3, 1e-5)
-    return t3, (sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3)
+    t2, _, s2, m2, r2 = branch_ln_fwd(w, ctx2, "cross_attn_image.out_proj.weight", "cross_attn_image.out_proj.bias", t1,
+                                      _site(drop, 3), "norm3.", 1e-5)
+    h = _ffn_hidden(w, t2, drop, 4)
+    t3, tq_next, s3, m3, r3 = branch_ln_fwd(w, h, "linear2.weight", "linear2.bias", t2, _site(drop, 5), "norm4.", 1e-5,
+                                            add=qpos if want_next_tq else None)
+    return t3, (sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3), tq_next
 
 
 def decoder_layer_bwd(w: W, g: G, req: Set[str], dy, dy2, saved, nhead: int, B: int, need_tgt: bool = True,
                       drop: Optional[Drop] = None):
     """dy (+ dy2): gradient of the layer output.  Returns (d_tgt, d_qpos, d_mem_pos, d_mem)."""
     sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3 = saved
-    ds3 = ln_bwd(w, g, req, "norm4.", dy, s3, m3, r3, dy2=dy2)
-    dt2 = _ffn_bwd(w, g, req, ds3, t2, h, drop, 5)
-    ds2 = ln_bwd(w, g, req, "norm3.", dt2, s2, m2, r2)
-    dy2_ = drop_grad(ds2, _site(drop, 3))
+    ds3, dlin3 = branch_ln_bwd(w, g, req, "norm4.", dy, s3, m3, r3, _site(drop, 5), dy2=dy2)
+    dt2 = _ffn_bwd(w, g, req, ds3, dlin3, t2, h, drop)
+    ds2, dy2_ = branch_ln_bwd(w, g, req, "norm3.", dt2, s2, m2, r2, _site(drop, 3))
     lin_param_grads(g, req, "cross_attn_image.out_proj.weight", "cross_attn_image.out_proj.bias", dy2_, ctx2,
                     w["cross_attn_image.out_proj.weight"].shape)
     dctx2 = K.linear_dgrad(dy2_, w["cross_attn_image.out_proj.weight"])
     dcq, dmem_pos, dmem = mha_bwd(w, g, req, "cross_attn_image.", dctx2, sv2, nhead, B, drop_site=_site(drop, 2))
-    dt1 = K.add_bf16(ds2, dcq)
-    ds1 = ln_bwd(w, g, req, "norm1.", dt1, s1, m1, r1)
-    dy1 = drop_grad(ds1, _site(drop, 1))
+    ds1, dy1 = branch_ln_bwd(w, g, req, "norm1.", ds2, s1, m1, r1, _site(drop, 1), dy2=dcq)
     lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", dy1, ctx1,
                     w["self_attn.out_proj.weight"].shape)
     dctx1 = K.linear_dgrad(dy1, w["self_attn.out_proj.weight"])
@@ -327,12 +370,12 @@ def roberta_layer_fwd(w: W, x, key_mask, nhead: int, B: int, eps: float, drop: O
     q3, k3, v3 = (qkv[:, i * E:(i + 1) * E].view(L, B, E) for i in range(3))
     ctx, probs = K.attention_fwd(q3, k3, v3, key_mask, nhead, drop=_site(drop, 0))
     ctx = ctx.view(M, E)
-    s1 = lin_drop_res(ctx, w["attention.output.dense.weight"], w["attention.output.dense.bias"], x, _site(drop, 1))
-    x1, _, m1, r1 = ln_fwd(w, "attention.output.LayerNorm.", s1, eps)
+    x1, _, s1, m1, r1 = branch_ln_fwd(w, ctx, "attention.output.dense.weight", "attention.output.dense.bias", x,
+                                      _site(drop, 1), "attention.output.LayerNorm.", eps)
     pre = torch.empty((M, w["intermediate.dense.weight"].shape[0]), dtype=BF, device=x.device)
     h = K.linear_fwd(x1, w["intermediate.dense.weight"], w["intermediate.dense.bias"], act=ACT_GELU, aux=pre)
-    s2 = lin_drop_res(h, w["output.dense.weight"], w["output.dense.bias"], x1, _site(drop, 2))
-    x2, _, m2, r2 = ln_fwd(w, "output.LayerNorm.", s2, eps)
+    x2, _, s2, m2, r2 = branch_ln_fwd(w, h, "output.dense.weight", "output.dense.bias", x1, _site(drop, 2),
+                                      "output.LayerNorm.", eps)
     return x2, (x, qkv, probs, ctx, s1, m1, r1, x1, pre, h, s2, m2, r2)
 
 
@@ -341,16 +384,14 @@ def roberta_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, 
     x, qkv, probs, ctx, s1, m1, r1, x1, pre, h, s2, m2, r2 = saved
     M, E = x.shape
     L = M // B
-    ds2 = ln_bwd(w, g, req, "output.LayerNorm.", dy, s2, m2, r2)
-    dy2 = drop_grad(ds2, _site(drop, 2))
+    ds2, dy2 = branch_ln_bwd(w, g, req, "output.LayerNorm.", dy, s2, m2, r2, _site(drop, 2))
     lin_param_grads(g, req, "output.dense.weight", "output.dense.bias", dy2, h, w["output.dense.weight"].shape)
     dh = K.linear_dgrad(dy2, w["output.dense.weight"])
     dpre = K.gelu_bwd(dh, pre)
     lin_param_grads(g, req, "intermediate.dense.weight", "intermediate.dense.bias", dpre, x1,
                     w["intermediate.dense.weight"].shape)
     dx1 = K.linear_dgrad(dpre, w["intermediate.dense.weight"], res=ds2)
-    ds1 = ln_bwd(w, g, req, "attention.output.LayerNorm.", dx1, s1, m1, r1)
-    dy1 = drop_grad(ds1, _site(drop, 1))
+    ds1, dy1 = branch_ln_bwd(w, g, req, "attention.output.LayerNorm.", dx1, s1, m1, r1, _site(drop, 1))
     lin_param_grads(g, req, "attention.output.dense.weight", "attention.output.dense.bias", dy1, ctx,
                     w["attention.output.dense.weight"].shape)
     dctx = K.linear_dgrad(dy1, w["attention.output.dense.weight"])

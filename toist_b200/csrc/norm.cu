@@ -5,6 +5,8 @@
 // RoBERTa embedding gather / scatter.
 #include <math.h>
 
+#include <initializer_list>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -191,7 +193,10 @@ layernorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
                          const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                          const float* __restrict__ rstd, const float* __restrict__ gamma,
                          __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                         long long rows) {
+                         long long rows, __nv_bfloat16* __restrict__ dx_drop,
+                         const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thr16, float scale) {
+  // dx_drop (nullable) = dropout-backward of dx with the decisions of site `site` (the gradient w.r.t. the linear
+  // layer's output behind a `res + dropout(y)` branch), computed from the bf16-rounded dx like the separate kernel did
   constexpr int N = 256 * K;
   __shared__ float red[4][2][N];  // per warp: [dgamma | dbeta] partials of the CTA's rows
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -245,7 +250,20 @@ layernorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
       for (int j = 0; j < 8; ++j) o[j] = rs * (g[k][j] - s1 - xh[k][j] * s2);
       uint4 u;
       u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-      *reinterpret_cast<uint4*>(dx + row * N + 256 * k + 8 * lane) = u;
+      const long long off = row * N + 256 * k + 8 * lane;
+      *reinterpret_cast<uint4*>(dx + off) = u;
+      if (dx_drop != nullptr) {
+        const uint64_t key = dropout_key(seed, site);
+        const uint32_t* pu = &u.x;
+        uint32_t t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w = dropout_word((uint64_t)(off >> 3) * 4 + j, key);
+          const float2 f = unpack_bf16(pu[j]);
+          t[j] = pack_bf16((w & 0xffffu) >= thr16 ? f.x * scale : 0.f, (w >> 16) >= thr16 ? f.y * scale : 0.f);
+        }
+        *reinterpret_cast<uint4*>(dx_drop + off) = make_uint4(t[0], t[1], t[2], t[3]);
+      }
     }
   }
   if (dgamma == nullptr) return;
@@ -262,6 +280,106 @@ layernorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
     float t = 0.f;
     for (int w = 0; w < wpb; ++w) t += red[w][which][c];
     atomicAdd((which == 0 ? dgamma : dbeta) + c, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused residual branch
+// The residual branches of the transformer layers end in  s = res + dropout(y);  out = LayerNorm(s)  and are followed
+// by  out + pos  (the positional / query embedding added before the next attention).  Unfused that is three launches
+// (dropout + residual, LayerNorm, add) per branch in a chain of ~4 us kernels; here it is one: every value is rounded
+// to bf16 exactly where the separate kernels rounded it, so the results are bit-identical to the unfused path.
+//   x [rows, N] bf16 (the linear layer's output); res (nullable) bf16; seed (nullable): dropout on x with the paired
+//   16-bit decisions of dropout_bf16_vec_kernel (same element indexing: index / 8 = row * N/8 + 32 k + lane);
+//   sum_out (nullable) = bf16(res + dropout(x)), the LayerNorm input kept for the backward; y = LayerNorm;
+//   y_add (nullable) = bf16(y + add).
+template <int K>
+__global__ void __launch_bounds__(128)
+layernorm_fused_fwd_vec_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                               const __nv_bfloat16* __restrict__ add, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, __nv_bfloat16* __restrict__ sum_out,
+                               __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y_add,
+                               float* __restrict__ mean, float* __restrict__ rstd, long long rows, float eps,
+                               const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thr16, float scale) {
+  constexpr int N = 256 * K;
+  const int lane = threadIdx.x & 31;
+  float ga[K][8], be[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float4* g4 = reinterpret_cast<const float4*>(gamma + 256 * k + 8 * lane);
+    const float4* b4 = reinterpret_cast<const float4*>(beta + 256 * k + 8 * lane);
+    const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+    ga[k][0] = g0.x; ga[k][1] = g0.y; ga[k][2] = g0.z; ga[k][3] = g0.w;
+    ga[k][4] = g1.x; ga[k][5] = g1.y; ga[k][6] = g1.z; ga[k][7] = g1.w;
+    be[k][0] = b0.x; be[k][1] = b0.y; be[k][2] = b0.z; be[k][3] = b0.w;
+    be[k][4] = b1.x; be[k][5] = b1.y; be[k][6] = b1.z; be[k][7] = b1.w;
+  }
+  pdl_prologue();
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  uint64_t key = 0;
+  if (seed != nullptr) key = dropout_key(seed, site);
+  float v[K][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const long long off = row * N + 256 * k + 8 * lane;
+    const uint4 ux = *reinterpret_cast<const uint4*>(x + off);
+    uint4 ur = make_uint4(0u, 0u, 0u, 0u);
+    if (res != nullptr) ur = *reinterpret_cast<const uint4*>(res + off);
+    const uint32_t* px = &ux.x;
+    const uint32_t* pr = &ur.x;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16(px[j]);
+      const float2 r = unpack_bf16(pr[j]);
+      if (seed != nullptr) {
+        const uint32_t w = dropout_word((uint64_t)(off >> 3) * 4 + j, key);
+        f.x = (w & 0xffffu) >= thr16 ? f.x * scale : 0.f;
+        f.y = (w >> 16) >= thr16 ? f.y * scale : 0.f;
+      }
+      o[j] = pack_bf16(f.x + r.x, f.y + r.y);  // the bf16 value the LayerNorm input holds in memory
+      const float2 q = unpack_bf16(o[j]);
+      v[k][2 * j] = q.x;
+      v[k][2 * j + 1] = q.y;
+      s += q.x + q.y;
+    }
+    if (sum_out != nullptr) *reinterpret_cast<uint4*>(sum_out + off) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  const float mu = warp_sum(s) * (1.f / N);
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[k][j] - mu;
+      sq += d * d;
+    }
+  const float rs = rsqrtf(warp_sum(sq) * (1.f / N) + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const long long off = row * N + 256 * k + 8 * lane;
+    uint32_t u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      u[j] = pack_bf16((v[k][2 * j] - mu) * rs * ga[k][2 * j] + be[k][2 * j],
+                       (v[k][2 * j + 1] - mu) * rs * ga[k][2 * j + 1] + be[k][2 * j + 1]);
+    *reinterpret_cast<uint4*>(y + off) = make_uint4(u[0], u[1], u[2], u[3]);
+    if (y_add != nullptr) {
+      const uint4 ua = *reinterpret_cast<const uint4*>(add + off);
+      const uint32_t* pa = &ua.x;
+      uint32_t t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16(u[j]), b = unpack_bf16(pa[j]);
+        t[j] = pack_bf16(a.x + b.x, a.y + b.y);
+      }
+      *reinterpret_cast<uint4*>(y_add + off) = make_uint4(t[0], t[1], t[2], t[3]);
+    }
   }
 }
 
@@ -523,6 +641,76 @@ int toist_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, cons
 }
 
 // dy (and optional dy2, same dtype) are summed; dx dtype selectable; dgamma/dbeta accumulate (may be null together)
+static int ln_bwd_vec_launch(const void* dy, const void* dy2, const void* x, const float* mean, const float* rstd,
+                             const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t n,
+                             void* dx_drop, const uint64_t* seed, uint32_t site, float p_drop, cudaStream_t st) {
+  unsigned g4 = (unsigned)((rows + 3) / 4);
+  if (g4 > 592) g4 = 592;  // 4 CTAs of 4 warps per SM; each warp then walks rows with its column sums in registers
+  const uint32_t thr16 = (uint32_t)((double)p_drop * 4294967296.0) >> 16;
+  const float scale = 1.f / (1.f - p_drop);
+#define LN_BWD_VEC(KK)                                                                                               \
+  launch_pdl((layernorm_bwd_vec_kernel<KK>), dim3(g4), dim3(128), 0, st, (const __nv_bfloat16*)dy,                   \
+             (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, dgamma,      \
+             dbeta, (long long)rows, (__nv_bfloat16*)dx_drop, (const unsigned long long*)seed, site, thr16, scale)
+  if (n == 256) LN_BWD_VEC(1);
+  else if (n == 512) LN_BWD_VEC(2);
+  else LN_BWD_VEC(3);
+#undef LN_BWD_VEC
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+static bool ln_vec_ok(int32_t n, std::initializer_list<const void*> ptrs) {
+  if (n % 256 != 0 || n > 768) return false;
+  uintptr_t al = 0;
+  for (const void* q : ptrs) al |= reinterpret_cast<uintptr_t>(q);
+  return (al & 15) == 0;
+}
+
+// s = res + dropout(x) (p_drop = 0 / seed null: no dropout; res null: none), y = LayerNorm(s), y_add = y + add;
+// sum_out (nullable) receives s.  bf16 rows of 256 / 512 / 768 elements, 16-byte aligned (TOIST_ERR_UNSUPPORTED otherwise:
+// the caller then issues the separate kernels).
+int toist_layernorm_fused_fwd(const void* x, const void* res, const void* add, const float* gamma, const float* beta,
+                              void* sum_out, void* y, void* y_add, float* mean, float* rstd, int64_t rows, int32_t n,
+                              float eps, float p_drop, const uint64_t* seed, uint32_t site, void* stream) {
+  TOIST_REQUIRE(x && gamma && beta && y, "toist_layernorm_fused_fwd: null pointer");
+  TOIST_REQUIRE((add == nullptr) == (y_add == nullptr), "toist_layernorm_fused_fwd: add needs y_add");
+  TOIST_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed != nullptr),
+                "toist_layernorm_fused_fwd: dropout needs a seed and 0 <= p < 1");
+  if (!ln_vec_ok(n, {x, res, add, gamma, beta, sum_out, y, y_add}))
+    return set_error(TOIST_ERR_UNSUPPORTED, "toist_layernorm_fused_fwd: width %d / alignment not supported", n);
+  if (rows == 0) return TOIST_OK;
+  const uint32_t thr16 = (uint32_t)((double)p_drop * 4294967296.0) >> 16;
+  const float scale = 1.f / (1.f - p_drop);
+  const unsigned long long* sd = p_drop > 0.f ? (const unsigned long long*)seed : nullptr;
+  const unsigned g4 = (unsigned)((rows + 3) / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LN_FUSED(KK)                                                                                                  \
+  launch_pdl((layernorm_fused_fwd_vec_kernel<KK>), dim3(g4), dim3(128), 0, st, (const __nv_bfloat16*)x,              \
+             (const __nv_bfloat16*)res, (const __nv_bfloat16*)add, gamma, beta, (__nv_bfloat16*)sum_out,              \
+             (__nv_bfloat16*)y, (__nv_bfloat16*)y_add, mean, rstd, (long long)rows, eps, sd, site, thr16, scale)
+  if (n == 256) LN_FUSED(1);
+  else if (n == 512) LN_FUSED(2);
+  else LN_FUSED(3);
+#undef LN_FUSED
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+// LayerNorm backward (as toist_layernorm_bwd, bf16) that also writes dx_drop = dropout-backward(dx) for site `site`
+int toist_layernorm_bwd_drop(const void* dy, const void* dy2, const void* x, const float* mean, const float* rstd,
+                             const float* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta, int64_t rows,
+                             int32_t n, float p_drop, const uint64_t* seed, uint32_t site, void* stream) {
+  TOIST_REQUIRE(dy && x && mean && rstd && gamma && dx && dx_drop && seed, "toist_layernorm_bwd_drop: null pointer");
+  TOIST_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "toist_layernorm_bwd_drop: pass both dgamma and dbeta or neither");
+  TOIST_REQUIRE(p_drop > 0.f && p_drop < 1.f, "toist_layernorm_bwd_drop: 0 < p < 1");
+  if (!ln_vec_ok(n, {dy, dy2, x, gamma, dx, dx_drop}))
+    return set_error(TOIST_ERR_UNSUPPORTED, "toist_layernorm_bwd_drop: width %d / alignment not supported", n);
+  if (rows == 0) return TOIST_OK;
+  return ln_bwd_vec_launch(dy, dy2, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, n, dx_drop, seed, site, p_drop,
+                           (cudaStream_t)stream);
+}
+
 int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const void* x, int32_t x_dtype,
                         const float* mean, const float* rstd, const float* gamma, void* dx, int32_t dx_dtype,
                         float* dgamma, float* dbeta, int64_t rows, int32_t n, void* stream) {
@@ -531,22 +719,8 @@ int toist_layernorm_bwd(const void* dy, const void* dy2, int32_t dy_dtype, const
   TOIST_REQUIRE(n >= 1 && n <= 32 * kMaxPerLane, "toist_layernorm_bwd: width %d unsupported (max 1024)", n);
   if (rows == 0) return TOIST_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == TOIST_BF16 && dy_dtype == TOIST_BF16 && dx_dtype == TOIST_BF16 && n % 256 == 0 && n <= 768 &&
-      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dy2) |
-        reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(gamma)) & 15) == 0) {
-    unsigned g4 = (unsigned)((rows + 3) / 4);
-    if (g4 > 592) g4 = 592;  // 4 CTAs of 4 warps per SM; each warp then walks rows with its column sums in registers
-#define LN_BWD_VEC(KK)                                                                                               \
-  launch_pdl((layernorm_bwd_vec_kernel<KK>), dim3(g4), dim3(128), 0, st, (const __nv_bfloat16*)dy,                   \
-             (const __nv_bfloat16*)dy2, (const __nv_bfloat16*)x, mean, rstd, gamma, (__nv_bfloat16*)dx, dgamma,      \
-             dbeta, rows)
-    if (n == 256) LN_BWD_VEC(1);
-    else if (n == 512) LN_BWD_VEC(2);
-    else LN_BWD_VEC(3);
-#undef LN_BWD_VEC
-    TOIST_CHECK_CUDA(cudaGetLastError());
-    return TOIST_OK;
-  }
+  if (x_dtype == TOIST_BF16 && dy_dtype == TOIST_BF16 && dx_dtype == TOIST_BF16 && ln_vec_ok(n, {x, dy, dy2, dx, gamma}))
+    return ln_bwd_vec_launch(dy, dy2, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, n, nullptr, nullptr, 0u, 0.f, st);
   unsigned grid = (unsigned)((rows + 7) / 8);
   if (grid > 296) grid = 296;
   const size_t smem = 2 * (size_t)n * sizeof(float);

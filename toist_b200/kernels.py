@@ -586,6 +586,56 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
     return dx
 
 
+_FUSED_LN = os.environ.get("TOIST_FUSED_LN", "1") != "0"
+
+
+def fused_ln_ok(*tensors) -> bool:
+    """bf16 rows of 256 / 512 / 768 contiguous elements, 16-byte aligned: the shapes the fused residual-branch kernels take."""
+    if not _FUSED_LN:
+        return False
+    n = None
+    for t in tensors:
+        if t is None:
+            continue
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.data_ptr() % 16:
+            return False
+        n = t.shape[-1]
+    return n in (256, 512, 768)
+
+
+def layernorm_fused_fwd(x: torch.Tensor, res: Optional[torch.Tensor], add: Optional[torch.Tensor], gamma: torch.Tensor,
+                        beta: torch.Tensor, eps: float, drop=None, want_sum: bool = True):
+    """s = res + dropout(x); y = LayerNorm(s); y_add = y + add  in one launch (csrc/norm.cu).  drop = (p, seed, site) or
+    None.  Returns (y, y_add | None, s | None, mean, rstd); s is written when there is a residual or dropout."""
+    rows, n = x.shape
+    dev = x.device
+    y = torch.empty((rows, n), dtype=torch.bfloat16, device=dev)
+    y_add = torch.empty((rows, n), dtype=torch.bfloat16, device=dev) if add is not None else None
+    need_s = want_sum and (res is not None or drop is not None)
+    s = torch.empty((rows, n), dtype=torch.bfloat16, device=dev) if need_s else None
+    mean = torch.empty(rows, dtype=torch.float32, device=dev)
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+    p, seed, site = drop if drop is not None else (0.0, None, 0)
+    _ck(_L().toist_layernorm_fused_fwd(x.data_ptr(), _ptr(res), _ptr(add), gamma.data_ptr(), beta.data_ptr(), _ptr(s),
+                                       y.data_ptr(), _ptr(y_add), mean.data_ptr(), rstd.data_ptr(), rows, n, float(eps),
+                                       float(p), _ptr(seed), int(site), _stream()))
+    return y, y_add, (s if need_s else x), mean, rstd
+
+
+def layernorm_bwd_drop(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                       drop, *, dy2: Optional[torch.Tensor] = None, dgamma: Optional[torch.Tensor] = None,
+                       dbeta: Optional[torch.Tensor] = None):
+    """LayerNorm backward + the dropout backward of the branch behind it: returns (dx, dropout_bwd(dx))."""
+    rows, n = x.shape
+    dx = torch.empty((rows, n), dtype=torch.bfloat16, device=x.device)
+    dxd = torch.empty((rows, n), dtype=torch.bfloat16, device=x.device)
+    p, seed, site = drop
+    _ck(_L().toist_layernorm_bwd_drop(dy.data_ptr(), _ptr(dy2), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                      gamma.data_ptr(), dx.data_ptr(), dxd.data_ptr(), _ptr(dgamma), _ptr(dbeta), rows, n,
+                                      float(p), seed.data_ptr(), int(site), _stream()))
+    return dx, dxd
+
+
 def l2norm_fwd(x: torch.Tensor, eps: float = 1e-12):
     rows, n = x.shape
     y = torch.empty_like(x)

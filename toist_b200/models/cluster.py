@@ -23,6 +23,7 @@ from torch import nn
 
 from .. import kernels as K
 from ..util import dist
+from ..util.misc import h2d
 from .mdetr import _token_spans
 
 

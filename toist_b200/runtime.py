@@ -679,10 +679,11 @@ def encoder_fwd(c: Call, feat: torch.Tensor, text: torch.Tensor, pos16: torch.Te
     Bk.seq_from_nhwc_fwd(feat, ip["weight"], ip["bias"], src[: hw * B], B)
     K.cast_bf16(text.contiguous().view(L * B, E), out=src[hw * B:])
     x = src
+    xp = None  # x + pos of the next layer comes out of the previous layer's last LayerNorm launch
     saved_layers = []
     for i in range(st.num_layers):
-        x, sv = Bk.encoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), x, pos16, key_mask, st.nhead, B,
-                                     c.drop(1000 + 8 * i))
+        x, sv, xp = Bk.encoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), x, pos16, key_mask, st.nhead, B,
+                                         c.drop(1000 + 8 * i), xp=xp, want_next_xp=i + 1 < st.num_layers)
         saved_layers.append(sv if c.save else None)
     mem = K.cast_f32(x).view(S, B, E)
     saved = (feat, (L, B, E), tuple(saved_layers)) if c.save else None
@@ -696,10 +697,12 @@ def encoder_bwd(c: Call, saved, needs, dmem, dsrc_proj=None):
     hw = h * wd
     grads: Dict[str, torch.Tensor] = {}
     d = K.cast_bf16(dmem.contiguous().view(-1, E))
+    d2 = None  # gradient that reached the layer's output through the next layer's (x + pos) input
     for i in range(st.num_layers - 1, -1, -1):
         pre = st.prefix + f"layers.{i}."
-        d = Bk.encoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), d, saved_layers[i], st.nhead, B,
-                                 c.drop(1000 + 8 * i))
+        d, d2 = Bk.encoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), d, saved_layers[i], st.nhead,
+                                     B, c.drop(1000 + 8 * i), dy2=d2)
+    d = K.add_bf16(d, d2)  # layer 0: x and x + pos are the same tensor plus a constant
     d_img = d[: hw * B]
     if dsrc_proj is not None:  # the mask head reads src_proj (models/segmentation.py:77-78)
         d_img = K.add_bf16(d_img, dsrc_proj.contiguous().view(-1, E))
@@ -726,9 +729,10 @@ def decoder_fwd(c: Call, mem32: torch.Tensor, qpos32: torch.Tensor, pos16: torch
     hs = torch.empty((st.num_layers, Q * B, E), dtype=BF, device=mem.device)
     nw = WView(c.w, st.prefix + "norm.")
     saved_layers = []
+    tq = None  # tgt + query_pos of the next layer comes out of the previous layer's last LayerNorm launch
     for i in range(st.num_layers):
-        tgt, sv = Bk.decoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), tgt, qpos, mem, mem_pos, key_mask,
-                                       st.nhead, B, c.drop(2000 + 8 * i))
+        tgt, sv, tq = Bk.decoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), tgt, qpos, mem, mem_pos, key_mask,
+                                           st.nhead, B, c.drop(2000 + 8 * i), tq=tq, want_next_tq=i + 1 < st.num_layers)
         _, _, m, r = K.layernorm_fwd(tgt, nw["weight"], nw["bias"], 1e-5, out16=hs[i])
         saved_layers.append((sv, tgt, m, r) if c.save else None)
     saved = ((S, B, E, Q), tuple(saved_layers)) if c.save else None
