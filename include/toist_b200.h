@@ -43,6 +43,11 @@ int toist_device_ok(void);
  * without launching, so (step time) - (step time without GEMMs) is the in-situ time of the tensor-core kernels.
  * Returns the previous setting.  Results computed while it is set are garbage by construction. */
 int toist_debug_skip_gemm(int on);
+/* Measurement hook (tools/gemm_trace.py): while `buf` is non-null every toist_gemm CTA writes 8 clock64() stamps
+ * (entry, setup done, dependency wait done, first operands landed, last MMA issued, accumulator complete, epilogue
+ * tile loop done, store done) and 2 %globaltimer stamps (entry, exit; nanoseconds) to buf[16 * cta_linear_index ..];
+ * pass NULL to switch it off.  The buffer is the caller's (device memory, >= 128 bytes per CTA of the largest grid). */
+int toist_debug_gemm_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM engine (tcgen05.mma + TMEM accumulators, operands staged by TMA, SWIZZLE_128B).

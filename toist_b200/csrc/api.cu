@@ -11,6 +11,8 @@ static thread_local char g_err[512] = "";
 static int g_skip_gemm = 0;
 
 bool skip_gemm() { return g_skip_gemm != 0; }
+static long long* g_gemm_trace = nullptr;
+long long* gemm_trace_buffer() { return g_gemm_trace; }
 
 bool pdl_enabled() {
   static const bool on = []() {
@@ -111,6 +113,11 @@ int toist_debug_skip_gemm(int on) {
   const int prev = toist::g_skip_gemm;
   toist::g_skip_gemm = on;
   return prev;
+}
+
+int toist_debug_gemm_trace(void* buf) {
+  toist::g_gemm_trace = reinterpret_cast<long long*>(buf);
+  return TOIST_OK;
 }
 
 int toist_device_ok(void) {

@@ -48,8 +48,21 @@ struct GemmKParams {
   int stages;   // depth of the TMA -> MMA shared-memory ring
   int epi;      // epilogue flavour (template parameter EPI of the kernel)
   int cluster;  // 2: CTA pairs share the B tile by TMA multicast (PAIR 1); 3: cta_group::2 MMA over the pair (PAIR 2)
+  long long* trace;  // measurement hook (toist_debug_gemm_trace): 8 clock stamps per CTA, nullptr in production
   toist_tap taps[TOIST_MAX_TAPS];
 };
+
+// Phase stamps of one CTA (tools/gemm_trace.py): 0 entry, 1 setup done (barriers, TMEM, cluster syncs), 2 dependency wait
+// done, 3 first operand stage landed, 4 last MMA issued, 5 accumulator complete, 6 epilogue tile loop done, 7 store done
+__device__ __forceinline__ void trace_stamp(const GemmKParams& p, int slot) {
+  if (p.trace != nullptr) {
+    const long long cta = (long long)blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+    long long t;
+    if (slot >= 8) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));  // slots 8 / 9: entry / exit in ns, comparable across SMs
+    else t = clock64();
+    p.trace[cta * 16 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == TOIST_ACT_RELU) return fmaxf(v, 0.f);
@@ -70,7 +83,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // ONE tcgen05.mma.cta_group::2 per k-step over a 256 x BN tile; each CTA stages its own 128 A rows and only BN / 2 rows of
 // B, so an SM ingests 32 KB instead of 48 KB per 512 MMA clocks (BN = 256) - the measured bound of the layer3 convolutions.
 template <int BN, int MODE, int EPI, int PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, BN == 256 ? 1 : 3)  // BN <= 128: up to three CTAs per SM (<= 112 registers)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
             const __grid_constant__ CUtensorMap tma_mask, const __grid_constant__ GemmKParams p) {
@@ -90,9 +103,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* accum_bar = empty_bar + STAGES;
   uint64_t* epi_bar = accum_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + 1);
+  float* s_col = reinterpret_cast<float*>(smem + STAGES * kStageBytes + 256);  // [2][BN] per-column scale | shift (EPI 0)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    trace_stamp(p, 0);
+    trace_stamp(p, 8);
+  }
 
   // ---------------- tile decode
   int x0 = 0, y0 = 0, i0 = 0;  // FWD/DGRAD: pixel-tile origin
@@ -159,7 +177,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cl_rank = CL > 1 ? cluster_ctarank() : 0u;
   constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
+  if (threadIdx.x == 0) trace_stamp(p, 1);
   pdl_wait();  // barrier init, descriptor prefetch and the TMEM allocation above overlap the previous kernel's tail
+  if (threadIdx.x == 0) trace_stamp(p, 2);
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -249,6 +269,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     for (int it = 0; it < mma_iters; ++it) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
+      if (it == 0 && lane == 0) trace_stamp(p, 3);
       if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * kStageBytes);
         const uint32_t sb = sa + kABytes;
@@ -274,6 +295,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         phase ^= 1;
       }
     }
+    if (lane == 0 && mma_iters > 0) trace_stamp(p, 4);
   } else {
     // ======================= epilogue (4 warps, one TMEM lane quadrant each) =======================
     const int q = warp & 3;
@@ -298,10 +320,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     const float rscale = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + row_global) : 1.f;
 
+    // EPI 0: per-column constants of this tile -> shared memory while the main loop runs (alpha folded into the scale)
+    float* s_scale = s_col;
+    float* s_shift = s_col + BN;
+    const bool has_scale = p.col_scale != nullptr || p.alpha != 1.f;
+    if constexpr (EPI == 0) {
+      const int last = p.n_cols - 1;  // columns past n_cols are clipped by the TMA store: clamp, do not branch
+      for (int c = (int)threadIdx.x - 64; c < BN; c += 128) {
+        const int col = min(n0 + c, last);
+        s_scale[c] = p.alpha * (p.col_scale != nullptr ? __ldg(p.col_scale + col) : 1.f);
+        s_shift[c] = p.col_shift != nullptr ? __ldg(p.col_shift + col) : 0.f;
+      }
+      named_barrier_sync(1, 128);
+    }
+
     if (n_iters > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
+    if (warp == 2 && lane == 0) trace_stamp(p, 5);
     // Main loop done: let the next kernel's CTAs be scheduled into the SM slots this grid frees from here on (its
     // prologue then overlaps our epilogue; it still waits for this grid's completion before touching memory).
     // Triggering at kernel entry instead made many-wave grids slower (39 -> 51 us on the 1600-CTA layer1 conv).
@@ -332,36 +369,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
           mbar_wait(epi_bar, 0);
         }
+        // One epilogue warp per scheduler: nothing hides a dependent instruction's latency except the warp's own
+        // independent work (measured with toist_debug_gemm_trace: ~1000 clocks per 32-column group when every group
+        // waited for its TMEM load and fetched 64 per-column constants through L1; the 128 x 256 tile's epilogue was
+        // 30 % of the CTA's lifetime).  Hence: the per-column constants come from shared memory (staged during the
+        // main loop), the TMEM load of group c+1 is in flight while group c is processed, and each 64-column slab is
+        // handed to the TMA store as soon as it is complete.
         const uint32_t rx = (uint32_t)(r & 7);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (n0 + c0 >= p.n_cols) break;  // warp-uniform
-          uint32_t raw[32];
-          if (n_iters > 0) {
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) raw[i] = 0u;
-          }
-          const int ncol = n0 + c0;
-          const int last = p.n_cols - 1;  // columns past n_cols are clipped by the TMA store: clamp, do not branch
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.alpha;
-          if (p.col_scale != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= __ldg(p.col_scale + min(ncol + i, last));
-          }
-          if (p.col_shift != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(p.col_shift + min(ncol + i, last));
-          }
-          const uint32_t row_base = (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
-          const uint32_t cb = (uint32_t)(c0 & 63) >> 3;  // first 16-byte chunk of this 32-column group (0 or 4)
-          if (has_res) {
+        const int nch = min(BN / 16, (p.n_cols - n0 + 15) >> 4);  // warp-uniform: 16-column groups with valid columns
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool relu = p.act == TOIST_ACT_RELU;
+        auto process = [&](uint32_t (&raw)[16], int c0) {  // 16 columns of this thread's row: raw -> bf16 in st_out
+          const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0);
+          const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0);
+          float v[16];
+          if (has_scale) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
+              const float4 a = sc4[g], b = sh4[g];
+              v[g * 4 + 0] = fmaf(__uint_as_float(raw[g * 4 + 0]), a.x, b.x);
+              v[g * 4 + 1] = fmaf(__uint_as_float(raw[g * 4 + 1]), a.y, b.y);
+              v[g * 4 + 2] = fmaf(__uint_as_float(raw[g * 4 + 2]), a.z, b.z);
+              v[g * 4 + 3] = fmaf(__uint_as_float(raw[g * 4 + 3]), a.w, b.w);
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b = sh4[g];
+              v[g * 4 + 0] = __uint_as_float(raw[g * 4 + 0]) + b.x;
+              v[g * 4 + 1] = __uint_as_float(raw[g * 4 + 1]) + b.y;
+              v[g * 4 + 2] = __uint_as_float(raw[g * 4 + 2]) + b.z;
+              v[g * 4 + 3] = __uint_as_float(raw[g * 4 + 3]) + b.w;
+            }
+          }
+          const uint32_t row_base = (uint32_t)(c0 >> 6) * 16384u + (uint32_t)r * 128u;
+          const uint32_t cb = (uint32_t)(c0 & 63) >> 3;  // first 16-byte chunk of this 16-column group (0, 2, 4, 6)
+          if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
               const uint4 u = *reinterpret_cast<const uint4*>(st_res + row_base + (((cb + g) ^ rx) << 4));
               const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
               v[g * 8 + 0] += f0.x; v[g * 8 + 1] += f0.y; v[g * 8 + 2] += f1.x; v[g * 8 + 3] += f1.y;
@@ -370,7 +415,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
           if (has_mask) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
               const uint4 u = *reinterpret_cast<const uint4*>(st_mask + row_base + (((cb + g) ^ rx) << 4));
               const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
               if (!(f0.x > 0.f)) v[g * 8 + 0] = 0.f;
@@ -383,12 +428,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               if (!(f3.y > 0.f)) v[g * 8 + 7] = 0.f;
             }
           }
-          if (p.act == TOIST_ACT_RELU) {
+          if (relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
           }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 2; ++g) {
             uint4 u;
             u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
             u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
@@ -396,15 +441,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
             *reinterpret_cast<uint4*>(st_out + row_base + (((cb + g) ^ rx) << 4)) = u;
           }
-        }
-        fence_proxy_async();          // generic-proxy writes above -> visible to the TMA (async proxy) reads below
-        named_barrier_sync(1, 128);   // the four epilogue warps
-        if (leader) {
+        };
+        uint32_t raw_a[16], raw_b[16];
+        if (n_iters > 0) {
+          tmem_ld_32x16(t_addr, raw_a);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            if (n0 + j * 64 < p.n_cols) tma_store_4d(&tma_out, st_out + j * 16384, n0 + j * 64, x0, y0, i0);
+          for (int i = 0; i < 16; ++i) raw_a[i] = raw_b[i] = 0u;
+        }
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          const bool more1 = c + 1 < nch, more2 = c + 2 < nch;
+          if (more1 && n_iters > 0) tmem_ld_32x16(t_addr + (uint32_t)((c + 1) * 16), raw_b);
+          process(raw_a, c * 16);
+          if (more1) {
+            if (n_iters > 0) {
+              tmem_ld_wait();
+              if (more2) tmem_ld_32x16(t_addr + (uint32_t)((c + 2) * 16), raw_a);
+            }
+            process(raw_b, (c + 1) * 16);
+            if (more2 && n_iters > 0) tmem_ld_wait();
+          }
+          if ((c & 2) != 0 || !more2) {  // the 64-column slab c / 4 is complete: hand it to the TMA store
+            fence_proxy_async();         // generic-proxy writes above -> visible to the TMA (async proxy) reads below
+            named_barrier_sync(1, 128);  // the four epilogue warps
+            if (leader) tma_store_4d(&tma_out, st_out + (c >> 2) * 16384, n0 + (c >> 2) * 64, x0, y0, i0);
+          }
+        }
+        if (leader) {
+          trace_stamp(p, 6);
           tma_store_commit();
           tma_store_wait_read();
+          trace_stamp(p, 7);
         }
       }
     }
@@ -654,6 +723,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_stamp(p, 9);
   if constexpr (kTwoSm) {
     cluster_sync();  // both CTAs are done with the paired TMEM (and with each other's barriers) before it is freed
     if (warp == 1) {
@@ -674,8 +744,8 @@ static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid
   constexpr int CL = PAIR ? 2 : 1;
   constexpr int kStage = kABytes + (PAIR == 2 ? BN / 2 : BN) * 128;
   constexpr int kMaxStages = PAIR == 2 ? 6 : ((BN == 128) ? 3 : 4);
-  constexpr int max_smem = kMaxStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
-  const int smem = kp.stages * kStage + 1024 + 256;
+  constexpr int max_smem = kMaxStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*column constants*/;
+  const int smem = kp.stages * kStage + 1024 + 256 + 2048;
   static bool configured = false;
   auto kfn = gemm_kernel<BN, MODE, EPI, PAIR>;
   if (!configured) {
@@ -834,6 +904,7 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   kp.res = d->res; kp.res_dtype = d->res_dtype; kp.mask = d->mask; kp.aux = d->aux;
   kp.act = d->act; kp.accumulate = d->accumulate;
   for (int i = 0; i < d->n_taps; ++i) kp.taps[i] = d->taps[i];
+  kp.trace = gemm_trace_buffer();
 
   // 16-byte vector path: every row start and every 32-column group must be 16-byte aligned in all streams.
   bool vec = (d->out_sx % 8 == 0) && (d->out_sy % 8 == 0) && (d->out_sn % 8 == 0) && aligned16(d->out) &&

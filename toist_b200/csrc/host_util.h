@@ -59,5 +59,7 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // measurement hook (toist_debug_skip_gemm): when set, toist_gemm validates nothing and launches nothing
 bool skip_gemm();
+// measurement hook (toist_debug_gemm_trace): device buffer of 8 clock stamps per CTA, or nullptr
+long long* gemm_trace_buffer();
 
 }  // namespace toist
