@@ -120,6 +120,12 @@ typedef struct toist_gemm_desc {
 
 /* Launches the product described by `d` on `stream`. */
 int toist_gemm(const toist_gemm_desc* d, void* stream);
+/* Scheduler workspace of the persistent variant of the engine (FWD / DGRAD with bf16 output): a ZEROED device buffer
+ * of the current device, owned by the caller for as long as launches may run (8 bytes per launch slot, handed out
+ * round robin; 512 KB = 65536 launches in flight / captured in graphs at once).  Every launch re-arms its slot before
+ * it ends.  Without a workspace (or with NULL) every launch uses the one-tile-per-CTA kernel.  The library never
+ * allocates device memory itself (safe under CUDA-graph capture). */
+int toist_gemm_set_workspace(void* zeroed, int64_t bytes);
 
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -344,3 +344,37 @@ def test_distillation_criterion_graph_replay_matches_eager(kd_gold):
         for a, b in zip(g0, g1):
             assert torch.equal(a, b)
     criterion.enable_cuda_graphs(False)
+
+
+def test_loss_nsthl2_matches_reference_golden():
+    """SetCriterion's noun / pronoun text-feature L2 term (models/mdetr.py:668-781) on the teacher / student text
+    memories frozen from the reference (tests/golden/nsthl2_cases.pt): loss value and d loss / d student text memory,
+    incl. an image without targets, an image whose teacher has no boxes, and the all-empty batch (constant zero)."""
+    from toist_b200.models.mdetr import SetCriterion
+    from toist_b200.tokenizer import CharTokenizer
+
+    gold = torch.load(GOLD / "nsthl2_cases.pt", weights_only=False)
+    args = make_args("resnet50", distillation=True, nsthl2_loss=True)
+    crit = SetCriterion(args, 255, matcher=None, eos_coef=0.1, losses=["labels", "boxes", "cardinality", "nsthl2"],
+                        temperature=0.07, contrastive_hdim=64)
+    tok = CharTokenizer()
+    for case in gold["cases"]:
+        mcs, outs, tgts = [], [], []
+        for k, key in enumerate(("text_noun", "text_sth")):
+            text = case[key].to(DEV).requires_grad_(k == 1)
+            mcs.append({"text_memory": text})
+            outs.append({"tokenized": tok.batch_encode_plus(case["captions"][k], padding="longest", return_tensors="pt")})
+            tgts.append([{"noun_tokens_positive": spans} for spans in case["noun_tokens_positive"][k]])
+        val = crit._loss_nsthl2(mcs, outs, tgts, case["counts"][1])
+        assert abs(float(val) - case["loss"]) <= 1e-6 + 1e-5 * abs(case["loss"]), (float(val), case["loss"])
+        if case["grad_text_sth"] is None:
+            assert not val.requires_grad and float(val) == 0.0
+            continue
+        val.backward()
+        assert mcs[0]["text_memory"].grad is None  # the teacher's features are detached (:775)
+        assert rel_err(mcs[1]["text_memory"].grad.cpu(), case["grad_text_sth"]) <= 1e-5
+    # the weight dict carries the term for the last layer and every auxiliary layer, without model prefix
+    from toist_b200.models import build_model
+
+    wd = build_model(make_args("resnet50", distillation=True, nsthl2_loss=True))[3]
+    assert sorted(k for k in wd if "nsthl2" in k) == sorted(gold["weight_keys"])

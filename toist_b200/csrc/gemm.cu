@@ -45,6 +45,7 @@ struct GemmKParams {
   int act;
   int accumulate;
   int vec_ok;   // 1: every row base and column tile is 16-byte aligned for all epilogue pointers
+  int slabs;    // persistent kernel: 16 KB slabs of the epilogue ring
   int stages;   // depth of the TMA -> MMA shared-memory ring
   int epi;      // epilogue flavour (template parameter EPI of the kernel)
   int cluster;  // 2: CTA pairs share the B tile by TMA multicast (PAIR 1); 3: cta_group::2 MMA over the pair (PAIR 2)
@@ -739,6 +740,83 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
 }
 
+}  // namespace toist
+#include "gemm_persist.cuh"
+namespace toist {
+
+// counters of the persistent kernel's tile scheduler: {next tile, finished CTAs} per launch, handed out round robin
+// from a caller-provided zeroed device buffer (toist_gemm_set_workspace); each launch re-arms its pair before it ends
+// Launches captured into CUDA graphs keep their slot for the life of the graph and may replay next to anything:
+// they take slots from the upper half, never reused (when it is used up, captured launches fall back to the
+// one-tile kernel); eager launches cycle through the lower half (a slot comes around again after 32768 launches).
+static unsigned int* g_persist_ws[16] = {};
+static int g_persist_slots[16] = {};
+static unsigned int g_persist_next[16] = {};
+static unsigned int g_persist_next_graph[16] = {};
+
+static unsigned int* persist_slot(int dev, cudaStream_t stream) {
+  const unsigned int half = (unsigned)g_persist_slots[dev] / 2;
+  if (half == 0) return nullptr;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) return nullptr;
+  if (st == cudaStreamCaptureStatusNone) return g_persist_ws[dev] + 2 * (g_persist_next[dev]++ % half);
+  if (g_persist_next_graph[dev] >= half) return nullptr;
+  return g_persist_ws[dev] + 2 * (half + g_persist_next_graph[dev]++);
+}
+
+// TOIST_GEMM_PERSIST=1 sends eligible launches to the persistent kernel.  OFF by default: measured on B200 in the same
+// process (tools/profile_kernels.py --graph --inner 10) it loses to the one-tile kernel on every bench shape
+// (3x3 256->256 @40^2: 28.0 vs 20.8 us, 1x1 256->1024 + residual: 20.9 vs 18.3 us, FFN1 16.8 vs 11.1 us): a lone CTA
+// per SM issues dependent tcgen05.mma into ONE accumulator and those retire no faster than one per ~135 clocks whatever
+// N is (k-block of 4 MMAs: 567 / 538 / 605 clocks for N = 64 / 128 / 256, independent of the ring depth), so N < 256
+// tiles need two or more co-resident CTAs (independent accumulation chains) to fill the tensor pipe - which the
+// one-tile kernel gets for free.  Kept as the starting point for a version that interleaves tiles per CTA.
+static bool persist_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("TOIST_GEMM_PERSIST");
+    return e ? atoi(e) != 0 : false;
+  }();
+  return on;
+}
+
+template <int BN, int MODE>
+static int launch_persist(const CUtensorMap* maps, GemmKParams& kp, int total_tiles, unsigned int* counter,
+                          cudaStream_t stream, int k_iters) {
+  using Cfg = PersistCfg<BN>;
+  // split of the 224 KB tile area: three rounds of slabs (residual + mask slabs of an output slab are prefetched while
+  // two stores are in flight), four when the reduction is short (the epilogue is then the bottleneck and the ring
+  // cannot use more than k_iters + 1 stages anyway); the operand ring takes the rest
+  const int per = std::max(1, (kp.res != nullptr ? 1 : 0) + (kp.mask != nullptr ? 1 : 0));
+  int slabs = std::min(kPMaxSlabs, (k_iters <= 4 ? 4 : 3) * per);
+  int stages = std::min(kPMaxStages, (kPTileBytes - slabs * 16384) / Cfg::kStageBytes);
+  stages = std::min(stages, std::max(2, k_iters + 1));
+  static const int force_stages = []() {  // TOIST_GEMM_PERSIST_STAGES: ring depth override (experiments)
+    const char* e = getenv("TOIST_GEMM_PERSIST_STAGES");
+    return e ? atoi(e) : 0;
+  }();
+  if (force_stages > 0) stages = std::max(2, std::min(stages, force_stages));
+  slabs = std::min(kPMaxSlabs, (kPTileBytes - stages * Cfg::kStageBytes) / 16384);
+  kp.stages = stages;
+  kp.slabs = slabs;
+  static bool configured = false;
+  auto kfn = gemm_persist_kernel<BN, MODE>;
+  if (!configured) {
+    TOIST_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  static const int n_sm = []() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("TOIST_GEMM_PERSIST_CTAS");
+    return e ? atoi(e) : n;
+  }();
+  const int grid = std::min(total_tiles, n_sm);
+  TOIST_CHECK_CUDA(launch_pdl(kfn, dim3((unsigned)grid), dim3(kPThreads), (size_t)Cfg::kSmem, stream, maps[0], maps[1],
+                              maps[2], maps[3], maps[4], kp, counter, total_tiles));
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
 template <int BN, int MODE, int EPI, int PAIR = 0>
 static int launch_gemm(const CUtensorMap* maps, const GemmKParams& kp, dim3 grid, cudaStream_t stream) {
   constexpr int CL = PAIR ? 2 : 1;
@@ -868,6 +946,18 @@ static bool reduce_epilogue_enabled() {  // TOIST_GEMM_ATOMIC_WGRAD=1 selects th
 
 using namespace toist;
 
+extern "C" int toist_gemm_set_workspace(void* zeroed, int64_t bytes) {
+  int dev = 0;
+  TOIST_CHECK_CUDA(cudaGetDevice(&dev));
+  TOIST_REQUIRE(dev >= 0 && dev < 16, "toist_gemm_set_workspace: device index %d out of range", dev);
+  TOIST_REQUIRE(zeroed == nullptr || bytes >= 8, "toist_gemm_set_workspace: need at least 8 bytes");
+  g_persist_ws[dev] = reinterpret_cast<unsigned int*>(zeroed);
+  g_persist_slots[dev] = zeroed ? (int)std::min<int64_t>(bytes / 8, 1 << 20) : 0;
+  g_persist_next[dev] = 0;
+  g_persist_next_graph[dev] = 0;
+  return TOIST_OK;
+}
+
 extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (skip_gemm()) return TOIST_OK;
@@ -985,6 +1075,30 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
                                   d->mode == TOIST_GEMM_FWD ? bbox_fwd : bbox_dg, ones)) != TOIST_OK)
       return rc;
     dim3 grid((unsigned)m_tiles, (unsigned)kp.n_tiles, 1);
+    // persistent kernel: bf16 / TMA epilogue, plain (non-batched, non-clustered) launches whose per-column constants
+    // can be read as aligned float4 groups; needs the scheduler's counter workspace
+    int dev = 0;
+    if (persist_enabled() && kp.epi == 0 && kp.cluster <= 1 && !d->b_batched && k_iters >= 1 && d->n_cols % 16 == 0 &&
+        aligned16(d->col_scale) && aligned16(d->col_shift) && cudaGetDevice(&dev) == cudaSuccess && dev < 16 &&
+        g_persist_ws[dev] != nullptr) {
+      const int64_t total = m_tiles * kp.n_tiles;
+      static const int min_tiles = []() {  // TOIST_GEMM_PERSIST_MIN: smallest tile count sent to the persistent kernel
+        const char* e = getenv("TOIST_GEMM_PERSIST_MIN");
+        return e ? atoi(e) : 1;
+      }();
+      unsigned int* ctr = (total >= min_tiles && total < (1 << 30)) ? persist_slot(dev, stream) : nullptr;
+      if (ctr != nullptr) {
+        const bool fwd = d->mode == TOIST_GEMM_FWD;
+        switch (bn) {
+          case 256: return fwd ? launch_persist<256, TOIST_GEMM_FWD>(maps, kp, (int)total, ctr, stream, (int)k_iters)
+                               : launch_persist<256, TOIST_GEMM_DGRAD>(maps, kp, (int)total, ctr, stream, (int)k_iters);
+          case 128: return fwd ? launch_persist<128, TOIST_GEMM_FWD>(maps, kp, (int)total, ctr, stream, (int)k_iters)
+                               : launch_persist<128, TOIST_GEMM_DGRAD>(maps, kp, (int)total, ctr, stream, (int)k_iters);
+          default:  return fwd ? launch_persist<64, TOIST_GEMM_FWD>(maps, kp, (int)total, ctr, stream, (int)k_iters)
+                               : launch_persist<64, TOIST_GEMM_DGRAD>(maps, kp, (int)total, ctr, stream, (int)k_iters);
+        }
+      }
+    }
     if (d->mode == TOIST_GEMM_FWD) return dispatch_bn<TOIST_GEMM_FWD>(bn, maps, kp, grid, stream, (int)k_iters);
     return dispatch_bn<TOIST_GEMM_DGRAD>(bn, maps, kp, grid, stream, (int)k_iters);
   }

@@ -179,6 +179,24 @@ def pick_tile(ext_x: int, ext_y: int, ext_n: int, rows: int = 128, max_x: int = 
     return best[1]
 
 
+_gemm_ws = {}  # device index -> zeroed scheduler workspace of the persistent GEMM kernel (kept alive for the process)
+
+
+def _ensure_gemm_workspace(dev: torch.device) -> None:
+    """Hands libtoist_b200 the tile-scheduler counters of its persistent GEMM kernel once per device: the library never
+    allocates device memory itself (toist_gemm_set_workspace).  512 KB = 65536 launch slots."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx in _gemm_ws:
+        return
+    if torch.cuda.is_current_stream_capturing():  # allocate outside of captures; until then the one-tile kernel runs
+        return
+    with torch.cuda.device(idx):
+        ws = torch.zeros(128 * 1024, dtype=torch.int32, device=torch.device("cuda", idx))
+        torch.cuda.synchronize(idx)
+        _lib.check(_lib.load().toist_gemm_set_workspace(ws.data_ptr(), ws.numel() * 4))
+    _gemm_ws[idx] = ws
+
+
 def gemm(mode: int, a: Tensor4, b: Tensor4, out: torch.Tensor, *, ext: Tuple[int, int, int],
          tile: Tuple[int, int, int], n_cols: int, out_strides: Tuple[int, int, int], k_per_tap: int = 0,
          taps: Sequence[Tuple[int, int, int, int]] = ((0, 0, 0, 0),), stride: Tuple[int, int] = (1, 1),
@@ -191,6 +209,7 @@ def gemm(mode: int, a: Tensor4, b: Tensor4, out: torch.Tensor, *, ext: Tuple[int
 
     `res`, `mask`, `aux` share the output's addressing (out_strides / out_offset).
     """
+    _ensure_gemm_workspace(out.device)
     d = GemmDesc()
     d.mode = mode
     d.a = a

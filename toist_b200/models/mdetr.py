@@ -11,6 +11,7 @@ import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -491,7 +492,7 @@ class SetCriterion(nn.Module):
         self.losses = losses
         self.temperature = temperature
         unsupported = [l for l in losses if l not in ("labels", "boxes", "cardinality", "contrastive_align", "masks",
-                                                      "softkd")]
+                                                      "nsthl2", "softkd")]
         self._unsupported = unsupported
         self._stage = Stage.empty("criterion")
         self._stage_mask = Stage.empty("mask_loss")
@@ -621,13 +622,17 @@ class SetCriterion(nn.Module):
                 for name, row in terms:
                     v = cells[row * L + i]
                     losses[f"{prefix}{name}_{i}"] = v.detach() if row == 3 else v
+        if "nsthl2" in self.losses and not prefix:  # single model: the term is a constant zero (models/mdetr.py:669-670)
+            zero = torch.zeros((), device=dev)
+            losses["loss_nsthl2"] = zero
+            if use_aux:
+                for i in range(L - 1):
+                    losses[f"loss_nsthl2_{i}"] = zero
         return losses, (st, match_q, packed, flags)
 
     def _forward_distillation(self, memory_cache, outputs, targets, positive_map):
         """models/mdetr.py:887-989: teacher (noun) and student (pronoun) losses with `noun_` / `sth_` prefixes, then the
         soft-KD term of every decoder layer."""
-        if getattr(self.args, "nsthl2_loss", False):
-            raise NotImplementedError("loss_nsthl2 (models/mdetr.py:668-781) is off in every shipped recipe; not built")
         outputs_noun, outputs_sth = outputs
         targets_noun, targets_sth = targets
         pm_noun, pm_sth = positive_map
@@ -635,6 +640,8 @@ class SetCriterion(nn.Module):
         l_sth, (st_s, mq_s, pk_s, fl_s) = self._forward_single(outputs_sth, targets_sth, pm_sth, "sth_")
         losses.update(l_sth)
         self.last_match_pair = ((mq_n, pk_n.counts, fl_n), (mq_s, pk_s.counts, fl_s))
+        if getattr(self.args, "nsthl2_loss", False):  # models/mdetr.py:974-977: last layer only, no prefix
+            losses["loss_nsthl2"] = self._loss_nsthl2(memory_cache, outputs, targets, pk_s.counts)
         if getattr(self.args, "softkd_loss", False):
             if pk_n.counts != pk_s.counts:
                 raise ValueError("soft-KD pairs the matched queries of teacher and student by target index: both "
@@ -651,6 +658,32 @@ class SetCriterion(nn.Module):
                 for i in range(L - 1):
                     losses[f"loss_softkd_{i}"] = kd[i]
         return losses
+
+    def _loss_nsthl2(self, memory_cache, outputs, targets, counts_sth) -> torch.Tensor:
+        """models/mdetr.py:668-781.  Per model (teacher: noun caption, student: pronoun caption) and image, the mean over
+        the boxes of the mean `text_memory` row over the box's `noun_tokens_positive` tokens; the loss is the MSE between
+        the student's and the (detached) teacher's vector, averaged over the images whose student assignment is not
+        empty (= images with at least one target).  An image without boxes keeps the zero vector (:695-697), a box whose
+        spans select no token makes the mean NaN, as in the reference."""
+        from .cluster import _MseRows, _selection, _TokenWeightedSum  # (cluster.py imports this module)
+
+        feats = []
+        for mc, out, tg in zip(memory_cache, outputs, targets):
+            text = mc["text_memory"]  # [T, B, D]
+            T, bs, _ = text.shape
+            w = np.zeros((bs, T), dtype=np.float32)
+            for i, t in enumerate(tg):
+                per_box = _selection(out["tokenized"], i, t["noun_tokens_positive"], T)
+                for pos in per_box:
+                    n = pos.sum()
+                    w[i] += (pos / n if n > 0 else np.full(T, np.nan, np.float32)) / len(per_box)
+            feats.append(_TokenWeightedSum.apply(text, h2d(torch.from_numpy(w), text.device)))
+        noun, sth = feats
+        dev = sth.device
+        use = [1 if c > 0 else 0 for c in counts_sth]  # len(indices_sth[i][0]) = min(Q, T_i) > 0
+        if sum(use) == 0:
+            return torch.zeros((), device=dev)
+        return _MseRows.apply(sth, noun.detach(), h2d(torch.tensor(use, dtype=torch.uint8), dev))
 
     def last_indices(self) -> List[List[tuple]]:
         """Assignments of the most recent forward as the reference's index pairs, one list per decoder layer

@@ -22,9 +22,24 @@ NAMES = ["setup", "dep wait", "first operands", "main loop issue", "drain to acc
 REGION = 16 * 4096  # int64 slots per launch
 
 
+PNAMES = ["setup", "dep wait", "first operands", "all main loops", "(first accumulator)", "epilogue end after last MMA"]
+
+
 def phases(t, label):
     lead = t[t[:, 4] != 0]  # CTAs that issued MMAs (cta_group::2: the leaders)
     print(f"   {label}: {t.shape[0]} CTAs traced ({lead.shape[0]} issuing MMAs)")
+    if 0 < int(lead[:, 7].max()) < 100000:  # persistent kernel: slot 7 is the CTA's tile count
+        tiles = lead[:, 7].float()
+        print(f"      persistent kernel: tiles per CTA min {int(tiles.min())} median {int(tiles.median())} max {int(tiles.max())}"
+              f" (sum {int(tiles.sum())})")
+        for nm, a, b in (("setup", 0, 1), ("dep wait", 1, 2), ("first operands", 2, 3), ("MMA warp: all tiles", 3, 4),
+                         ("first accumulator", 2, 5), ("epilogue: all tiles", 5, 6), ("epilogue after last MMA", 4, 6),
+                         ("CTA lifetime", 0, 6)):
+            col = (lead[:, b] - lead[:, a]).float()
+            print(f"      {nm:24s} median {col.median():9.0f}  min {col.min():9.0f}  max {col.max():9.0f} clk")
+        per = ((lead[:, 6] - lead[:, 5]).float() / tiles)
+        print(f"      {'epilogue clocks per tile':24s} median {per.median():9.0f}  min {per.min():9.0f}  max {per.max():9.0f}")
+        return
     d = lead[:, 1:8] - lead[:, 0:7]
     for i, nm in enumerate(NAMES):
         col = d[:, i].float()

@@ -14,6 +14,8 @@ Fixtures (torch.save, fp32 unless noted; library versions recorded in each file)
                      every mask-branch parameter                          (models/segmentation.py:40-273, mdetr.py:827-853)
   config5_softkd_small.pt  distillation branch of SetCriterion with soft-KD: fp32 predictions of teacher and student,
                      the 66 loss terms, d(soft-KD)/d(student logits)                        (models/mdetr.py:520-599,887-989)
+  nsthl2_cases.pt    SetCriterion.loss_nsthl2 on hand-made teacher / student text memories (incl. an image without targets
+                     and the all-empty batch): the loss and d loss / d student text memory     (models/mdetr.py:668-781)
   cluster_cases.pt   ClusterCriterion driven for 10 steps on random features (memory bank, k-means, replacement,
                      cluster-feature loss and its gradient), run on the CPU by patching .cuda()  (models/mdetr.py:29-312)
 """
@@ -287,6 +289,55 @@ def config5_softkd_small(models, tok):
     }
 
 
+def nsthl2_cases(models, tok):
+    """SetCriterion.loss_nsthl2 (models/mdetr.py:668-781) called directly on hand-made memory caches: random
+    `text_memory` [T, B, 256] of teacher and student, captions tokenised by the synthetic tokenizer, targets with
+    `noun_tokens_positive` spans, assignments with the given lengths (an image without targets included).  Stores the
+    loss and its gradient w.r.t. the student's text memory."""
+    args = shims.reference_args(["--backbone", "resnet50", "--distillation", "--nsthl2_loss"])
+    torch.manual_seed(0)
+    _, criterion, _, weight_dict = models.build_model(args)
+    cases = []
+    for seed, counts_noun, counts_sth in ((0, [2, 1, 3], [2, 1, 3]), (1, [1, 0, 2, 4], [1, 0, 2, 4]), (2, [0, 0], [0, 0]),
+                                          (3, [0, 2], [1, 2])):
+        g = torch.Generator().manual_seed(900 + seed)
+        B = len(counts_sth)
+        caps, tgts, mcs, outs, idx = [], [], [], [], []
+        for which, counts in (("noun", counts_noun), ("sth", counts_sth)):
+            _, _, captions, targets, _ = make_batch(B, 32, 10, seed=70 + seed + (0 if which == "noun" else 50))
+            if which == "noun":  # teacher captions name the object: a different span than the student's "something"
+                captions = [c[:-9] + "hammering"[: 9] for c in captions]
+            for i, t in enumerate(targets):
+                n = counts[i]
+                cap = captions[i]
+                t["boxes"] = t["boxes"][:1].repeat(max(n, 1), 1)[:n]
+                t["labels"] = torch.ones(n, dtype=torch.long)
+                spans = [[[len(cap) - 9, len(cap)]], [[len(cap) - 9, len(cap) - 4]], [[len(cap) - 5, len(cap)], [0, 2]],
+                         [[len(cap) - 9, len(cap) - 7]]]
+                t["noun_tokens_positive"] = [spans[j % 4] for j in range(n)]
+                t["tokens_positive"] = [[[0, len(cap)]] for _ in range(n)]
+            tokenized = tok.batch_encode_plus(captions, padding="longest", return_tensors="pt")
+            T = tokenized["input_ids"].shape[1]
+            text = torch.randn(T, B, 256, generator=g)
+            if which == "sth":
+                text.requires_grad_(True)
+            caps.append(captions)
+            tgts.append(targets)
+            mcs.append({"text_memory": text})
+            outs.append({"proj_queries": torch.zeros(B, 100, 64), "proj_tokens": torch.zeros(B, T, 64), "tokenized": tokenized})
+            idx.append([(torch.arange(n), torch.arange(n)) for n in counts])
+        val = criterion.loss_nsthl2(mcs, outs, tgts, [None, None], idx, [1.0, 1.0], None)["loss_nsthl2"]
+        grad = None
+        if val.requires_grad:
+            val.backward()
+            grad = mcs[1]["text_memory"].grad.clone()
+        cases.append({"captions": caps, "counts": [counts_noun, counts_sth],
+                      "noun_tokens_positive": [[t["noun_tokens_positive"] for t in tg] for tg in tgts],
+                      "text_noun": mcs[0]["text_memory"].detach().clone(), "text_sth": mcs[1]["text_memory"].detach().clone(),
+                      "loss": float(val), "grad_text_sth": grad})
+    return {"cases": cases, "weight_keys": [k for k in weight_dict if "nsthl2" in k]}
+
+
 def cluster_cases(models, tok):
     """ClusterCriterion (models/mdetr.py:29-312) driven like engine.py:182-190 for a few steps on random features.
     The reference constructor needs `.cuda()` and a process group: here `.cuda()` is patched to the identity and a
@@ -357,7 +408,7 @@ def main():
     import argparse
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="", help="comma-separated subset of: matcher,config1,config3,config5,cluster")
+    ap.add_argument("--only", default="", help="comma-separated subset of: matcher,config1,config3,config5,cluster,nsthl2")
     only = set(filter(None, ap.parse_args().only.split(",")))
     torch.set_num_threads(8)
     OUT.mkdir(parents=True, exist_ok=True)
@@ -368,7 +419,8 @@ def main():
             ("config1", "config1_r50.pt", lambda: config1(models, tok)),
             ("config3", "config3_r50_segm_small.pt", lambda: config3_small(models, tok)),
             ("config5", "config5_softkd_small.pt", lambda: config5_softkd_small(models, tok)),
-            ("cluster", "cluster_cases.pt", lambda: cluster_cases(models, tok))]
+            ("cluster", "cluster_cases.pt", lambda: cluster_cases(models, tok)),
+            ("nsthl2", "nsthl2_cases.pt", lambda: nsthl2_cases(models, tok))]
     for tag, fname, fn in jobs:
         if only and tag not in only:
             continue
