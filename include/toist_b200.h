@@ -126,6 +126,10 @@ int toist_gemm(const toist_gemm_desc* d, void* stream);
  * it ends.  Without a workspace (or with NULL) every launch uses the one-tile-per-CTA kernel.  The library never
  * allocates device memory itself (safe under CUDA-graph capture). */
 int toist_gemm_set_workspace(void* zeroed, int64_t bytes);
+/* Tile-shape hint: the caller issues `chains` independent launch sequences side by side (e.g. the two half-batch
+ * chains of the trunk, runtime.backbone_fwd), so a launch should aim at 1 / chains of the SMs when it chooses its
+ * column-tile width.  Host-side state read at launch time; returns the previous value.  1 = default. */
+int toist_gemm_concurrency(int chains);
 
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -76,7 +76,12 @@ def mark_grads() -> None:
     stream = main
     if lane.active and lane.dirty and lane.stream is not None:
         lane.stream.wait_stream(main)
+        for s_ in lane.also_wait:
+            lane.stream.wait_stream(s_)
         stream = lane.stream
+    else:
+        for s_ in lane.also_wait:
+            main.wait_stream(s_)
     ev = torch.cuda.Event(external=torch.cuda.is_current_stream_capturing())
     ev.record(stream)
     a.marks.append((a.off, ev))
@@ -408,13 +413,15 @@ def roberta_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, 
 
 
 # ------------------------------------------------------------------------------------------------ bottleneck
-def bottleneck_fwd(w: W, x, stride: int, has_ds: bool):
+def bottleneck_fwd(w: W, x, stride: int, has_ds: bool, into=None):
     """torchvision Bottleneck (v1.5: stride on the 3x3) with FrozenBatchNorm folded: conv weights carry the BN scale,
-    the epilogue adds the BN shift (models/backbone.py:48-58).  x NHWC bf16."""
-    y1 = K.conv_fwd(x, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU)
-    y2 = K.conv_fwd(y1, w["conv2.weight"], w["bn2.shift"], stride=stride, pad=1, act=ACT_RELU)
+    the epilogue adds the BN shift (models/backbone.py:48-58).  x NHWC bf16.  `into` = (y1, y2, out) buffers to write
+    (batch slices of full-batch tensors when the trunk runs as two half-batch chains)."""
+    b1, b2, bo = into if into is not None else (None, None, None)
+    y1 = K.conv_fwd(x, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU, out=b1)
+    y2 = K.conv_fwd(y1, w["conv2.weight"], w["bn2.shift"], stride=stride, pad=1, act=ACT_RELU, out=b2)
     idt = K.conv_fwd(x, w["downsample.0.weight"], w["downsample.1.shift"], stride=stride) if has_ds else x
-    out = K.conv_fwd(y2, w["conv3.weight"], w["bn3.shift"], res=idt, act=ACT_RELU)
+    out = K.conv_fwd(y2, w["conv3.weight"], w["bn3.shift"], res=idt, act=ACT_RELU, out=bo)
     return out, (x, y1, y2)
 
 
@@ -434,6 +441,45 @@ def _conv_wgrad_param(g: G, name: str, dy, x, w_shadow, scale, stride: int, pad:
             dw = _zeros((cout, kh, kw, cin), dy.device)
             K.conv_wgrad(dy, x, dw, stride=stride, pad=pad, row_scale=scale)
     g[name] = dw.view(cout, cin, kh, kw)
+
+
+def bottleneck_bwd_chains(w: W, g: G, req: Set[str], gz, saved, stride: int, has_ds: bool, need_dx: bool, streams):
+    """`bottleneck_bwd` with the data-gradient chain split into len(streams) independent batch slices, one stream each
+    (runtime.backbone_bwd); the weight gradients stay full-batch launches on the weight-gradient lane, which waits for
+    every chain before each of them (kernels._WgradLane.also_wait).  Same arithmetic per image."""
+    x, y1, y2 = saved
+    n = x.shape[0]
+    k = len(streams)
+    per = n // k
+    sls = [slice(i * per, (i + 1) * per) for i in range(k)]
+    g2 = torch.empty_like(y2)
+    g1 = torch.empty_like(y1)
+    dx = torch.empty_like(x) if need_dx else None
+    K.keep_alive(gz, g2, g1, dx)  # made on the main stream, read by the other chain's stream until the stage's join
+    if "conv3.weight" in req:
+        _conv_wgrad_param(g, "conv3.weight", gz, y2, w["conv3.weight"], w["bn3.scale"], 1, 0)
+    with K.gemm_chains(k):
+        for s_, sl in zip(streams, sls):
+            with torch.cuda.stream(s_):
+                K.conv_dgrad(gz[sl], w["conv3.weight"], y2.shape[1:3], mask=y2[sl], out=g2[sl])
+    if "conv2.weight" in req:
+        _conv_wgrad_param(g, "conv2.weight", g2, y1, w["conv2.weight"], w["bn2.scale"], stride, 1)
+    with K.gemm_chains(k):
+        for s_, sl in zip(streams, sls):
+            with torch.cuda.stream(s_):
+                K.conv_dgrad(g2[sl], w["conv2.weight"], y1.shape[1:3], stride=stride, pad=1, mask=y1[sl], out=g1[sl])
+    if "conv1.weight" in req:
+        _conv_wgrad_param(g, "conv1.weight", g1, x, w["conv1.weight"], w["bn1.scale"], 1, 0)
+    if has_ds and "downsample.0.weight" in req:
+        _conv_wgrad_param(g, "downsample.0.weight", gz, x, w["downsample.0.weight"], w["downsample.1.scale"], stride, 0)
+    if not need_dx:
+        return None
+    with K.gemm_chains(k):
+        for s_, sl in zip(streams, sls):
+            with torch.cuda.stream(s_):
+                gi = K.conv_dgrad(gz[sl], w["downsample.0.weight"], x.shape[1:3], stride=stride) if has_ds else gz[sl]
+                K.conv_dgrad(g1[sl], w["conv1.weight"], x.shape[1:3], res=gi, mask=x[sl], out=dx[sl])
+    return dx
 
 
 def bottleneck_bwd(w: W, g: G, req: Set[str], gz, saved, stride: int, has_ds: bool, need_dx: bool):

@@ -916,6 +916,8 @@ static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 gr
   }
 }
 
+static int g_concurrent = 1;  // toist_gemm_concurrency
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static bool cluster_enabled() {  // TOIST_GEMM_CLUSTER=0 disables the CTA-pair / multicast variant (A/B runs)
@@ -945,6 +947,12 @@ static bool reduce_epilogue_enabled() {  // TOIST_GEMM_ATOMIC_WGRAD=1 selects th
 }  // namespace toist
 
 using namespace toist;
+
+extern "C" int toist_gemm_concurrency(int chains) {
+  const int prev = g_concurrent;
+  g_concurrent = chains < 1 ? 1 : (chains > 8 ? 8 : chains);
+  return prev;
+}
 
 extern "C" int toist_gemm_set_workspace(void* zeroed, int64_t bytes) {
   int dev = 0;
@@ -1010,10 +1018,13 @@ extern "C" int toist_gemm(const toist_gemm_desc* d, void* stream_v) {
   const int64_t z_mult = (d->mode == TOIST_GEMM_WGRAD) ? (int64_t)kp.batch_y * kp.batch_n * kp.splits * d->n_taps : 1;
   int bn = 64;
   const int cands[3] = {256, 128, 64};
-  static const int min_ctas = []() {  // tuning knob: smallest grid for which a wider column tile is preferred
+  static const int min_ctas_env = []() {  // tuning knob: smallest grid for which a wider column tile is preferred
     const char* e = getenv("TOIST_GEMM_MIN_CTAS");
     return e ? atoi(e) : 160;  // measured on the bench step: 96 -> 9.55, 130 -> 9.47, 160 -> 9.32, 210 -> 9.83 ms
   }();
+  // the caller runs `g_concurrent` independent launch chains side by side (toist_gemm_concurrency): each launch needs
+  // only its share of the SMs
+  const int min_ctas = std::max(32, min_ctas_env / std::max(1, g_concurrent));
   // short reductions are epilogue bound: keep two CTAs per SM (BN <= 128) so epilogues overlap main loops
   const int64_t k_iters = (d->mode == TOIST_GEMM_WGRAD) ? 1 << 20 : (int64_t)ceil_div(d->k_per_tap, kBK) * d->n_taps;
   static const int bn256_min_k = []() {  // TOIST_GEMM_BN256_MINK: shortest reduction (k-blocks) that may use 256-wide tiles

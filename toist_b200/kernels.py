@@ -80,6 +80,7 @@ class _WgradLane:
     stream = None
     dirty = False
     keep: list = []
+    also_wait: list = []  # further streams producing the lane's inputs (the trunk's second data-gradient chain)
 
 
 class wgrad_lanes:
@@ -111,6 +112,8 @@ class wgrad_lane:
         if L.stream is None or L.stream.device != main.device:
             L.stream = torch.cuda.Stream(device=main.device)
         L.stream.wait_stream(main)
+        for s_ in L.also_wait:
+            L.stream.wait_stream(s_)
         L.keep.extend(t for t in self.tensors if t is not None)
         L.dirty = True
         self.ctx = torch.cuda.stream(L.stream)
@@ -124,12 +127,33 @@ class wgrad_lane:
         return False
 
 
+class gemm_chains:
+    """`with gemm_chains(n):` tells the engine that n independent launch chains run side by side (tile-shape hint)."""
+
+    def __init__(self, n: int):
+        self.n = n
+
+    def __enter__(self):
+        self.prev = _lib.load().toist_gemm_concurrency(self.n)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().toist_gemm_concurrency(self.prev)
+        return False
+
+
+def keep_alive(*tensors) -> None:
+    """Holds the tensors until the next `wgrad_join()` (end of the backward stage): buffers that a side stream still
+    reads must not go back to the allocator of the stream that made them."""
+    _WgradLane.keep.extend(t for t in tensors if t is not None)
+
+
 def wgrad_join() -> None:
     L = _WgradLane
     if L.dirty:
         torch.cuda.current_stream().wait_stream(L.stream)
-        L.keep.clear()
         L.dirty = False
+    L.keep.clear()
 
 
 def _stream() -> int:
@@ -347,13 +371,15 @@ def conv_out_size(size: int, k: int, stride: int, pad: int) -> int:
 
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, shift: Optional[torch.Tensor] = None, *, stride: int = 1, pad: int = 0,
              act: int = ACT_NONE, res: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
-             scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+             scale: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y[N,Ho,Wo,Cout] = act((conv(x[N,H,W,Cin], w[Cout,kh,kw,Cin]) * scale + shift) + res), all NHWC bf16."""
     n, h, wd, cin = x.shape
     cout, kh, kw, cin2 = w.shape
     assert cin == cin2 and w.is_contiguous()
     ho, wo = conv_out_size(h, kh, stride, pad), conv_out_size(wd, kw, stride, pad)
-    out = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=out_dtype, device=x.device)
+    assert out.shape == (n, ho, wo, cout) and out.is_contiguous() and out.dtype == out_dtype
     taps = [(kx - pad, ky - pad, 0, (ky * kw + kx) * cin) for ky in range(kh) for kx in range(kw)]
     tile = pick_tile(wo, ho, n, 128, 128 // stride if stride > 1 else 128)
     gemm(GEMM_FWD, _nhwc_t4(x), t4(w, (kh * kw * cin, cout, 1, 1), (1, kh * kw * cin, 0, 0)), out,
@@ -363,13 +389,15 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, shift: Optional[torch.Tensor] = N
 
 
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Tuple[int, int], *, stride: int = 1, pad: int = 0,
-               mask: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
+               mask: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx[N,H,W,Cin] = (conv_transpose(dy[N,Ho,Wo,Cout], w[Cout,kh,kw,Cin]) + res) * (mask > 0)."""
     n, ho, wo, cout = dy.shape  # dy may carry zero-padded channels beyond the filter count (16-byte TMA rows)
     cout2, kh, kw, cin = w.shape
     assert cout >= cout2 and w.is_contiguous()
     h, wd = in_hw
-    dx = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dy.device)
+    dx = out if out is not None else torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=dy.device)
+    assert dx.shape == (n, h, wd, cin) and dx.is_contiguous() and dx.dtype == torch.bfloat16
     a = _nhwc_t4(dy)
     # B rows = the filters that exist: the zero-padded channels of dy meet TMA zero fill, never memory past the tensor
     b = t4(w, (kh * kw * cin, cout2, 1, 1), (1, kh * kw * cin, 0, 0))
@@ -513,10 +541,11 @@ def stem_im2col(images: torch.Tensor, ldk: int = 192) -> torch.Tensor:
     return out
 
 
-def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+def maxpool3x3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, h, w, c = x.shape
     ho, wo = conv_out_size(h, 3, 2, 1), conv_out_size(w, 3, 2, 1)
-    y = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+    y = out if out is not None else torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+    assert y.shape == (n, ho, wo, c) and y.is_contiguous() and x.is_contiguous()
     _ck(_L().toist_maxpool3x3s2(x.data_ptr(), y.data_ptr(), n, h, w, c, _stream()))
     return y
 

@@ -184,7 +184,7 @@ class MDETR(nn.Module):
         """Capture each stage's forward / backward launch sequence into CUDA graphs (one per input-shape signature)
         and replay them on later steps.  For fixed-shape training / benchmarking; tensors returned by a step are
         overwritten by the next step with the same shapes."""
-        self._rt.graphs = GraphCache() if on else None
+        self._rt.graphs = GraphCache(priority=-1) if on else None  # the critical chain; text / wgrad lanes fill around it
         self._rt.graphs_text = GraphCache() if on else None
         return self
 

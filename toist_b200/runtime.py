@@ -311,12 +311,18 @@ class GraphCache:
 
     timing = None  # list collecting (phase, stage signature, launches, start event, end event) when profiling
 
-    def __init__(self):
+    def __init__(self, priority: int = 0):
         self.entries: Dict[tuple, _GraphEntry] = {}
         self.pool = None
+        # Stream priority the graphs are captured under (kernel nodes inherit it): the trunk / transformer chain is the
+        # critical path of the step, the text branch and the weight-gradient lane run next to it and should only fill
+        # the SMs it leaves idle.  Measured (B200, bench step): 9.39 ms with the priority vs 9.18 ms without - the starved
+        # weight-gradient lane piles up behind the chain - so it is OFF unless TOIST_GRAPH_PRIO=1.
+        self.priority = priority if os.environ.get("TOIST_GRAPH_PRIO", "0") != "0" else 0
+        self._stream = None
 
     def __deepcopy__(self, memo):
-        return GraphCache()
+        return GraphCache(self.priority)
 
     def clear(self) -> None:
         self.entries.clear()
@@ -348,7 +354,9 @@ class GraphCache:
         torch.cuda.synchronize()
         n0 = K.launches()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=self.pool):
+        if self.priority != 0 and (self._stream is None or self._stream.device != cur.device):
+            self._stream = torch.cuda.Stream(device=cur.device, priority=self.priority)
+        with torch.cuda.graph(g, pool=self.pool, stream=self._stream if self.priority != 0 else None):
             outputs = fn(*static_in)
         if self.pool is None:
             self.pool = g.pool()
@@ -523,7 +531,71 @@ def run_stage(spec: Spec, c: Call, *inputs):
 
 
 # ------------------------------------------------------------------------------------------------ backbone
+_TRUNK_CHAINS = int(os.environ.get("TOIST_TRUNK_CHAINS", "2"))
+# The backward data-gradient chain can be split the same way (TOIST_TRUNK_BWD_CHAINS=1); measured without gain (8.98 vs
+# 8.96 ms per bench step): the weight-gradient lane already fills the chain's gaps there.  Off by default.
+_TRUNK_BWD_CHAINS = os.environ.get("TOIST_TRUNK_BWD_CHAINS", "0") != "0"
+_trunk_lane: Dict[torch.device, torch.cuda.Stream] = {}
+
+
+def _backbone_fwd_chains(c: Call, images: torch.Tensor, chains: int):
+    """The trunk forward as `chains` independent half-batch launch chains on separate streams (FrozenBatchNorm makes
+    the images independent, models/backbone.py:48-58).  The trunk is a strictly serial chain of ~106 launches whose
+    100..400-CTA grids leave SMs idle and whose launch / prologue / epilogue latencies are all exposed; two chains fill
+    each other's gaps exactly as the weight-gradient lane does in the backward pass (measured there: 1.07 ms of 3.2).
+    Every chain writes batch slices of full-batch activation tensors, so what the backward sees is unchanged."""
+    st = c.stage
+    w = WView(c.w, st.prefix)
+    n, _, hh, ww = images.shape
+    dev = images.device
+    ho, wo = K.conv_out_size(hh, 7, 2, 3), K.conv_out_size(ww, 7, 2, 3)
+    hp, wp = K.conv_out_size(ho, 3, 2, 1), K.conv_out_size(wo, 3, 2, 1)
+
+    def buf(h, w_, ch):
+        return torch.empty((n, h, w_, ch), dtype=BF, device=dev)
+
+    pooled = buf(hp, wp, 64)
+    plan = []  # per block: (li, bi, stride, has_ds, y1, y2, out)
+    h, wd = hp, wp
+    for li, (planes, nblocks) in enumerate(zip((64, 128, 256, 512), st.blocks), start=1):
+        for bi in range(nblocks):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            h2, w2 = K.conv_out_size(h, 3, stride, 1), K.conv_out_size(wd, 3, stride, 1)
+            plan.append((li, bi, stride, bi == 0, buf(h, wd, planes), buf(h2, w2, planes), buf(h2, w2, planes * 4)))
+            h, wd = h2, w2
+    main = torch.cuda.current_stream()
+    lane = _trunk_lane.get(dev)
+    if lane is None:
+        lane = _trunk_lane[dev] = torch.cuda.Stream(device=dev)
+    lane.wait_stream(main)
+    per = n // chains
+    with K.gemm_chains(chains):
+        for ch in range(chains):
+            sl = slice(ch * per, (ch + 1) * per)
+            with torch.cuda.stream(main if ch == 0 else lane):
+                patches = K.stem_im2col(images[sl], STEM_LDK)
+                y = K.linear_fwd(patches, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU).view(per, ho, wo, 64)
+                del patches
+                x = K.maxpool3x3s2(y, out=pooled[sl])
+                del y
+                for (li, bi, stride, has_ds, y1, y2, out) in plan:
+                    x, _ = Bk.bottleneck_fwd(w.sub(f"layer{li}.{bi}."), x, stride, has_ds, into=(y1[sl], y2[sl], out[sl]))
+    main.wait_stream(lane)
+    feats, saved = [], {}
+    x = pooled
+    for (li, bi, stride, has_ds, y1, y2, out) in plan:
+        if c.save and li >= st.first_trainable:
+            saved[(li, bi)] = (x, y1, y2)
+        x = out
+        if bi == st.blocks[li - 1] - 1:
+            feats.append(out)
+    return feats, saved
+
+
 def backbone_fwd(c: Call, images: torch.Tensor):
+    n = images.shape[0]
+    if _TRUNK_CHAINS > 1 and n >= 2 * _TRUNK_CHAINS and n % _TRUNK_CHAINS == 0:
+        return _backbone_fwd_chains(c, images, _TRUNK_CHAINS)
     st = c.stage
     w = WView(c.w, st.prefix)
     n, _, hh, ww = images.shape
@@ -550,21 +622,51 @@ def backbone_bwd(c: Call, gfeats: Dict[int, torch.Tensor], feats: Sequence[torch
     grads: Dict[str, torch.Tensor] = {}
     w = WView(c.w, st.prefix)
     gz = None
+    n = feats[-1].shape[0]
+    chains = _TRUNK_CHAINS if (_TRUNK_BWD_CHAINS and _TRUNK_CHAINS > 1 and n >= 2 * _TRUNK_CHAINS
+                               and n % _TRUNK_CHAINS == 0) else 1
+    main = torch.cuda.current_stream()
+    streams = [main]
+    if chains > 1:  # the data-gradient chain as independent half-batch chains (see _backbone_fwd_chains)
+        dev = feats[-1].device
+        lane = _trunk_lane.get(dev)
+        if lane is None:
+            lane = _trunk_lane[dev] = torch.cuda.Stream(device=dev)
+        streams = [main] + [lane] * (chains - 1) if chains == 2 else [main]
+        chains = len(streams)
+    forked = False
     for li in range(4, st.first_trainable - 1, -1):
         nblocks = st.blocks[li - 1]
         ext = gfeats.get(li)
         if ext is not None:
+            if forked:  # full-batch work on the main stream: the chains meet here
+                main.wait_stream(streams[1])
             ext = K.relu_bwd(ext.contiguous(), feats[li - 1])
             gz = ext if gz is None else K.add_bf16(gz, ext)
+            if forked:
+                streams[1].wait_stream(main)
         if gz is None:
             continue
         for bi in range(nblocks - 1, -1, -1):
             stride = 2 if (li > 1 and bi == 0) else 1
             pre = f"layer{li}.{bi}."
             need_dx = not (li == st.first_trainable and bi == 0)
-            gz = Bk.bottleneck_bwd(w.sub(pre), GView(grads, st.prefix + pre), RView(c.req, st.prefix + pre), gz,
-                                   saved[(li, bi)], stride, bi == 0, need_dx)
+            if chains > 1:
+                if not forked:
+                    streams[1].wait_stream(main)
+                    K._WgradLane.also_wait = [streams[1]]
+                    forked = True
+                gz = Bk.bottleneck_bwd_chains(w.sub(pre), GView(grads, st.prefix + pre), RView(c.req, st.prefix + pre), gz,
+                                              saved[(li, bi)], stride, bi == 0, need_dx, streams)
+            else:
+                gz = Bk.bottleneck_bwd(w.sub(pre), GView(grads, st.prefix + pre), RView(c.req, st.prefix + pre), gz,
+                                       saved[(li, bi)], stride, bi == 0, need_dx)
             Bk.mark_grads()
+    if forked:
+        main.wait_stream(streams[1])
+        if K._WgradLane.active and K._WgradLane.stream is not None:
+            K._WgradLane.stream.wait_stream(streams[1])  # (the lane's last launches may still read the chain's outputs)
+        K._WgradLane.also_wait = []
     return grads
 
 
