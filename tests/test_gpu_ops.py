@@ -430,3 +430,35 @@ def test_scale_layers(K):
     z = torch.empty(1000, device=DEV)
     _lib.check(_lib.load().toist_scale_layers(x.data_ptr(), g.data_ptr(), z.data_ptr(), 6, 1000, 1, st))
     assert rel_err(z, (x * g[:, None]).sum(0)) < 1e-5
+
+
+def test_embed_rows_merge_is_the_sparse_form_of_the_dense_mean():
+    """Receive side of the sparse word-embedding gradient exchange (util/dist.FlatGradSync._sparse_exchange; replaces
+    the dense all-reduce of main.py:336 for that table): table[id] = scale * sum of the gathered rows with that id in
+    list order; padding-id slots are skipped, untouched rows keep what they held, the result is the same on every call
+    (fixed summation order: bit-identical across ranks)."""
+    from toist_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(3)
+    vocab, e, world, slots, pad = 50265, 768, 4, 64, 1
+    ids = torch.full((world * slots,), pad, dtype=torch.int64)
+    rows = torch.randn(world * slots, e, generator=g)
+    for r in range(world):  # every rank fills a different number of its fixed slots; ids repeat within and across ranks
+        n = 10 + 7 * r
+        ids[r * slots: r * slots + n] = torch.randint(2, 40, (n,), generator=g)
+    table = torch.full((vocab, e), 7.0)
+    want = table.clone()
+    used = ids != pad
+    acc = torch.zeros(vocab, e, dtype=torch.float64)
+    acc.index_add_(0, ids[used], rows[used].double())
+    touched = torch.zeros(vocab, dtype=torch.bool)
+    touched[ids[used]] = True
+    want[touched] = (acc[touched] / world).float()
+    outs = []
+    for _ in range(2):
+        t = table.clone().cuda()
+        K.embed_rows_merge(t, ids.cuda(), rows.cuda(), pad, 1.0 / world)
+        outs.append(t.cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0][~touched], table[~touched])
+    assert max_err(outs[0][touched], want[touched]) <= 1e-5
