@@ -469,6 +469,30 @@ def run_ours(a):
                     "method": "sum over the step's launch list of each distinct launch's isolated duration (CUDA graph of "
                               "10 back-to-back identical launches, CUDA events, best of 3, L2 warm); the step overlaps "
                               "streams, so the serial share may exceed what the step spends on these kernels"}
+            # In situ: the same timed region with every toist_gemm launch removed (toist_debug_skip_gemm while the
+            # graphs are re-captured: same launch sequence minus the GEMM nodes; the other kernels then run on
+            # uninitialised activations, their durations depend on shapes only).  The difference is the time the step
+            # spends on the GEMM family as it actually runs - next to the text branch, the second trunk chain and the
+            # weight-gradient lane - which is what the isolated sum cannot see.
+            try:
+                from toist_b200 import _lib as _L
+
+                _L.load().toist_debug_skip_gemm(1)
+                model.enable_cuda_graphs(True)
+                criterion.enable_cuda_graphs(True)
+                for _ in range(3):
+                    step(d_samples, d_targets, d_pm)
+                ms_skip = timed(lambda: step(d_samples, d_targets, d_pm), a.steps)
+                _L.load().toist_debug_skip_gemm(0)
+                in_situ = (ms - ms_skip) * 1e-3 / a.steps
+                roof["in_situ"] = {"seconds_per_step": in_situ, "step_ms_without_gemm_launches": ms_skip / a.steps,
+                                   "achieved": fl_g / in_situ / 1e12, "frac": fl_g / in_situ / 1e12 / peaks["tf_sustained"],
+                                   "method": "step time minus step time with every toist_gemm launch skipped, same timed "
+                                             "region, CUDA events, max over ranks"}
+            finally:
+                _L.load().toist_debug_skip_gemm(0)
+                model.enable_cuda_graphs(False)
+                criterion.enable_cuda_graphs(False)
             if "attn_core" in agg:
                 f, t, n = agg["attn_core"]
                 attn = {"kernels": "QK^T / softmax / PV and their backward (enc-self, dec-self, dec-cross, RoBERTa)",
