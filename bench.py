@@ -395,15 +395,16 @@ def run_ours(a):
     # (toist_b200.util.misc.Prefetcher, what a prefetching data loader does), the loss is read back every step.
     from toist_b200.util.misc import Prefetcher
 
+    h_targets = [{k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in t.items()} for t in targets]
+
     def host_batches():
         while True:
-            yield (NestedTensor(h_images, h_mask), h_pm)
+            yield (NestedTensor(h_images, h_mask), h_pm, h_targets)
 
     feed = Prefetcher(host_batches(), dev)
 
     def e2e_step():
-        s, pmap = next(feed)
-        tg = targets_to(targets, dev)
+        s, pmap, tg = next(feed)  # this step's batch (copied under the previous step); the next one's copy starts here
         total = step(s, tg, pmap)
         return float(total.item())
 
@@ -665,6 +666,7 @@ def run_other(a):
         images, mask, captions, targets, pm = make_batch(batch, SIZE, TOKENS, seed=seed, masks=seg)
         for i, t in enumerate(targets):
             t["dataset_name"] = f"tdod_{1 + (i + rank) % 14}"
+        targets = [{k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in t.items()} for t in targets]
         return {"images": images.pin_memory(), "mask": mask.pin_memory(), "pm": pm.pin_memory(), "captions": captions,
                 "targets": targets}
 
@@ -732,13 +734,13 @@ def run_other(a):
 
     def host_batches():
         while True:
-            yield [{"samples": NestedTensor(h["images"], h["mask"]), "pm": h["pm"]} for h in hb]
+            yield [{"samples": NestedTensor(h["images"], h["mask"]), "pm": h["pm"], "targets": h["targets"]} for h in hb]
 
     feed = Prefetcher(host_batches(), dev)
 
     def e2e_step():
         got = next(feed)
-        bs = [{"samples": g["samples"], "pm": g["pm"], "captions": h["captions"], "targets": targets_to(h["targets"], dev)}
+        bs = [{"samples": g["samples"], "pm": g["pm"], "captions": h["captions"], "targets": g["targets"]}
               for g, h in zip(got, hb)]
         return float(step(bs).item())
 
