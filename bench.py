@@ -490,6 +490,8 @@ def run_ours(a):
                                    "achieved": fl_g / in_situ / 1e12, "frac": fl_g / in_situ / 1e12 / peaks["tf_sustained"],
                                    "method": "step time minus step time with every toist_gemm launch skipped, same timed "
                                              "region, CUDA events, max over ranks"}
+            except Exception as e:  # the isolated-launch roofline above must survive
+                roof["in_situ"] = {"error": f"{type(e).__name__}: {e}"[:200]}
             finally:
                 _L.load().toist_debug_skip_gemm(0)
                 model.enable_cuda_graphs(False)
