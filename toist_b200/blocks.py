@@ -200,10 +200,19 @@ def branch_ln_bwd(w: W, g: G, req: Set[str], ln_pre: str, dy, s, mean, rstd, dro
 
 
 # ------------------------------------------------------------------------------------------------ attention
-def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int, drop_site=None):
-    """nn.MultiheadAttention up to (excluding) out_proj.  xq/xk/xv: [rows, E] bf16; xq is xk -> fused q|k GEMM."""
+def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int, drop_site=None, kv=None):
+    """nn.MultiheadAttention up to (excluding) out_proj.  xq/xk/xv: [rows, E] bf16; xq is xk -> fused q|k GEMM.
+    `kv` = (k2, v2): key / value projections computed by the caller (the decoder projects the encoder memory for all of
+    its layers in one GEMM each, runtime.decoder_fwd); column slices of wider tensors are fine."""
     E = xq.shape[1]
     Wi, bi = w[pre + "in_proj_weight"], w[pre + "in_proj_bias"]
+    if kv is not None:
+        q2 = K.linear_fwd(xq, Wi[:E], bi[:E])
+        k2, v2 = kv
+        Sq, Sk = xq.shape[0] // B, xk.shape[0] // B
+        ctx, probs = K.attention_fwd(q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), key_mask, nhead,
+                                     drop=drop_site)
+        return ctx.view(Sq * B, E), (xq, xk, xv, q2, k2, v2, probs)
     if xq is xk:
         qk = K.linear_fwd(xq, Wi[: 2 * E], bi[: 2 * E])
         q2, k2 = qk[:, :E], qk[:, E:]
@@ -218,8 +227,10 @@ def mha_fwd(w: W, pre: str, xq, xk, xv, key_mask, nhead: int, B: int, drop_site=
 
 
 def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int, need=(True, True, True),
-            drop_site=None):
-    """Returns (dxq, dxk, dxv); for self-attention (xq is xk) dxq is the gradient of the shared input and dxk None."""
+            drop_site=None, dkv=None):
+    """Returns (dxq, dxk, dxv); for self-attention (xq is xk) dxq is the gradient of the shared input and dxk None.
+    `dkv` = (dk2, dv2): buffers (column slices) that receive the gradients of the key / value projections when the
+    caller projected them itself (see mha_fwd); their data gradients are then the caller's business (need[1:] False)."""
     xq, xk, xv, q2, k2, v2, probs = saved
     E = xq.shape[1]
     Sq, Sk = xq.shape[0] // B, xk.shape[0] // B
@@ -231,8 +242,8 @@ def mha_bwd(w: W, g: G, req: Set[str], pre: str, dctx, saved, nhead: int, B: int
         dq2, dk2 = dqk[:, :E], dqk[:, E:]
     else:
         dq2 = torch.empty((xq.shape[0], E), dtype=BF, device=dev)
-        dk2 = torch.empty((xk.shape[0], E), dtype=BF, device=dev)
-    dv2 = torch.empty((xv.shape[0], E), dtype=BF, device=dev)
+        dk2 = dkv[0] if dkv is not None else torch.empty((xk.shape[0], E), dtype=BF, device=dev)
+    dv2 = dkv[1] if dkv is not None else torch.empty((xv.shape[0], E), dtype=BF, device=dev)
     K.attention_bwd(dctx.view(Sq, B, E), q2.view(Sq, B, E), k2.view(Sk, B, E), v2.view(Sk, B, E), probs, nhead,
                     dq2.view(Sq, B, E), dk2.view(Sk, B, E), dv2.view(Sk, B, E), drop=drop_site)
     wn, bn = pre + "in_proj_weight", pre + "in_proj_bias"
@@ -322,7 +333,7 @@ def encoder_layer_bwd(w: W, g: G, req: Set[str], dy, saved, nhead: int, B: int, 
 
 # ------------------------------------------------------------------------------------------------ decoder layer
 def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: int, drop: Optional[Drop] = None,
-                      tq=None, want_next_tq: bool = False):
+                      tq=None, want_next_tq: bool = False, kv=None):
     """models/transformer.py:362-408 (post-norm; the text cross-attention is disabled in the reference).  Dropout
     sites: 0 self-attention weights, 1 dropout1, 2 cross-attention weights, 3 dropout3, 4 FFN hidden, 5 dropout4.
     `tq` = tgt + qpos when the previous layer already produced it (want_next_tq)."""
@@ -331,7 +342,7 @@ def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: in
     ctx1, sv1 = mha_fwd(w, "self_attn.", tq, tq, tgt, None, nhead, B, _site(drop, 0))
     t1, cq, s1, m1, r1 = branch_ln_fwd(w, ctx1, "self_attn.out_proj.weight", "self_attn.out_proj.bias", tgt,
                                        _site(drop, 1), "norm1.", 1e-5, add=qpos)
-    ctx2, sv2 = mha_fwd(w, "cross_attn_image.", cq, mem_pos, mem, key_mask, nhead, B, _site(drop, 2))
+    ctx2, sv2 = mha_fwd(w, "cross_attn_image.", cq, mem_pos, mem, key_mask, nhead, B, _site(drop, 2), kv=kv)
     t2, _, s2, m2, r2 = branch_ln_fwd(w, ctx2, "cross_attn_image.out_proj.weight", "cross_attn_image.out_proj.bias", t1,
                                       _site(drop, 3), "norm3.", 1e-5)
     h = _ffn_hidden(w, t2, drop, 4)
@@ -341,8 +352,9 @@ def decoder_layer_fwd(w: W, tgt, qpos, mem, mem_pos, key_mask, nhead: int, B: in
 
 
 def decoder_layer_bwd(w: W, g: G, req: Set[str], dy, dy2, saved, nhead: int, B: int, need_tgt: bool = True,
-                      drop: Optional[Drop] = None):
-    """dy (+ dy2): gradient of the layer output.  Returns (d_tgt, d_qpos, d_mem_pos, d_mem)."""
+                      drop: Optional[Drop] = None, dkv=None):
+    """dy (+ dy2): gradient of the layer output.  Returns (d_tgt, d_qpos, d_mem_pos, d_mem); with `dkv` (hoisted key /
+    value projections of the memory, see mha_fwd) the last two are None and dkv's buffers hold dK / dV."""
     sv1, ctx1, s1, m1, r1, t1, sv2, ctx2, s2, m2, r2, t2, h, s3, m3, r3 = saved
     ds3, dlin3 = branch_ln_bwd(w, g, req, "norm4.", dy, s3, m3, r3, _site(drop, 5), dy2=dy2)
     dt2 = _ffn_bwd(w, g, req, ds3, dlin3, t2, h, drop)
@@ -350,7 +362,8 @@ def decoder_layer_bwd(w: W, g: G, req: Set[str], dy, dy2, saved, nhead: int, B: 
     lin_param_grads(g, req, "cross_attn_image.out_proj.weight", "cross_attn_image.out_proj.bias", dy2_, ctx2,
                     w["cross_attn_image.out_proj.weight"].shape)
     dctx2 = K.linear_dgrad(dy2_, w["cross_attn_image.out_proj.weight"])
-    dcq, dmem_pos, dmem = mha_bwd(w, g, req, "cross_attn_image.", dctx2, sv2, nhead, B, drop_site=_site(drop, 2))
+    dcq, dmem_pos, dmem = mha_bwd(w, g, req, "cross_attn_image.", dctx2, sv2, nhead, B, drop_site=_site(drop, 2),
+                                  need=(True, dkv is None, dkv is None), dkv=dkv)
     ds1, dy1 = branch_ln_bwd(w, g, req, "norm1.", ds2, s1, m1, r1, _site(drop, 1), dy2=dcq)
     lin_param_grads(g, req, "self_attn.out_proj.weight", "self_attn.out_proj.bias", dy1, ctx1,
                     w["self_attn.out_proj.weight"].shape)

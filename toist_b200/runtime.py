@@ -104,6 +104,7 @@ def _load(ctx):
 
 # ------------------------------------------------------------------------------------------------ shadow weights
 _SHADOW_ALWAYS = os.environ.get("TOIST_SHADOW_ALWAYS", "0") != "0"
+_CROSS_KV_HOIST = os.environ.get("TOIST_CROSS_KV_HOIST", "1") != "0"
 _EMBEDDING_KEYS = ("word_embeddings", "position_embeddings", "token_type_embeddings", "query_embed")
 RESNET_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
 STEM_LDK = 192  # 7*7*3 = 147 patch columns padded to a multiple of 64
@@ -162,6 +163,8 @@ class ShadowBank:
     def run_rest(self) -> None:
         if self._stale_rest:
             self.prep_rest.run()
+            for dst, parts in getattr(self, "_cat", ()):
+                torch.cat(parts, out=dst)
             self._stale_rest = False
 
     def _build(self, params, backbone_prefix: Optional[str], body) -> None:
@@ -216,6 +219,30 @@ class ShadowBank:
                 for i, nm in enumerate(("query", "key", "value")):
                     prep.add(params[base + nm + ".weight"].detach(), qkv[i * E:(i + 1) * E], E, E)
                 w[base + "qkv"] = qkv
+        # ---- decoder: the key / value projections of the encoder memory of ALL layers as one [layers * E, E] weight each
+        # (they depend on the memory only, not on the decoder state: one M = S * B, N = layers * E GEMM in front of the
+        # decoder instead of two small GEMMs inside every layer)
+        self._cat = []  # (destination fp32, [source slices]) refreshed by torch.cat in run_rest
+        cross = sorted((n for n in params if n.endswith("cross_attn_image.in_proj_weight") and ".decoder.layers." in n),
+                       key=lambda n: int(n.split(".layers.")[1].split(".")[0]))
+        if cross and _CROSS_KV_HOIST:
+            pre = cross[0].split("layers.")[0]  # "transformer.decoder."
+            E = params[cross[0]].shape[1]
+            L = len(cross)
+            k_all = torch.empty((L * E, E), dtype=BF, device=dev)
+            v_all = torch.empty((L * E, E), dtype=BF, device=dev)
+            bk, bv = [], []
+            for l, n in enumerate(cross):
+                pw = params[n].detach()
+                prep.add(pw[E: 2 * E], k_all[l * E:(l + 1) * E], E, E)
+                prep.add(pw[2 * E:], v_all[l * E:(l + 1) * E], E, E)
+                pb = params[n[: -len("weight")] + "bias"].detach()
+                bk.append(pb[E: 2 * E])
+                bv.append(pb[2 * E:])
+            w[pre + "cross_kv.k_weight"], w[pre + "cross_kv.v_weight"] = k_all, v_all
+            w[pre + "cross_kv.k_bias"] = torch.empty((L * E,), dtype=torch.float32, device=dev)
+            w[pre + "cross_kv.v_bias"] = torch.empty((L * E,), dtype=torch.float32, device=dev)
+            self._cat = [(w[pre + "cross_kv.k_bias"], bk), (w[pre + "cross_kv.v_bias"], bv)]
         self.w, self.prep, self.prep_rest = w, trunk, prep
 
 
@@ -832,31 +859,48 @@ def decoder_fwd(c: Call, mem32: torch.Tensor, qpos32: torch.Tensor, pos16: torch
     nw = WView(c.w, st.prefix + "norm.")
     saved_layers = []
     tq = None  # tgt + query_pos of the next layer comes out of the previous layer's last LayerNorm launch
+    k_all = v_all = None
+    wk = c.w.get(st.prefix + "cross_kv.k_weight")
+    if wk is not None and wk.shape[0] == st.num_layers * E:  # models/transformer.py:394: k = memory + pos, v = memory
+        k_all = K.linear_fwd(mem_pos, wk, c.w[st.prefix + "cross_kv.k_bias"])
+        v_all = K.linear_fwd(mem, c.w[st.prefix + "cross_kv.v_weight"], c.w[st.prefix + "cross_kv.v_bias"])
     for i in range(st.num_layers):
+        kv = None if k_all is None else (k_all[:, i * E:(i + 1) * E], v_all[:, i * E:(i + 1) * E])
         tgt, sv, tq = Bk.decoder_layer_fwd(WView(c.w, st.prefix + f"layers.{i}."), tgt, qpos, mem, mem_pos, key_mask,
-                                           st.nhead, B, c.drop(2000 + 8 * i), tq=tq, want_next_tq=i + 1 < st.num_layers)
+                                           st.nhead, B, c.drop(2000 + 8 * i), tq=tq, want_next_tq=i + 1 < st.num_layers,
+                                           kv=kv)
         _, _, m, r = K.layernorm_fwd(tgt, nw["weight"], nw["bias"], 1e-5, out16=hs[i])
         saved_layers.append((sv, tgt, m, r) if c.save else None)
-    saved = ((S, B, E, Q), tuple(saved_layers)) if c.save else None
+    saved = ((S, B, E, Q, int(k_all is not None)), tuple(saved_layers)) if c.save else None
     return (hs,), saved
 
 
 def decoder_bwd(c: Call, saved, needs, dhs):
     st = c.stage
-    (S, B, E, Q), saved_layers = saved
+    (S, B, E, Q, hoisted), saved_layers = saved
     grads: Dict[str, torch.Tensor] = {}
     np_ = st.prefix + "norm."
     d_next = None
     d_qpos = d_mem = None
+    dk_all = dv_all = None
+    if hoisted:  # gradients of the hoisted key / value projections of all layers, one column block per layer
+        dev = dhs.device
+        dk_all = torch.empty((S * B, st.num_layers * E), dtype=BF, device=dev)
+        dv_all = torch.empty((S * B, st.num_layers * E), dtype=BF, device=dev)
     for i in range(st.num_layers - 1, -1, -1):
         sv, t3, m, r = saved_layers[i]
         dy = Bk.ln_bwd(WView(c.w, np_), GView(grads, np_), RView(c.req, np_), "", dhs[i], t3, m, r)
         pre = st.prefix + f"layers.{i}."
+        dkv = (dk_all[:, i * E:(i + 1) * E], dv_all[:, i * E:(i + 1) * E]) if hoisted else None
         d_tgt, dq, dmp, dm = Bk.decoder_layer_bwd(WView(c.w, pre), GView(grads, pre), RView(c.req, pre), dy, d_next,
-                                                  sv, st.nhead, B, need_tgt=i > 0, drop=c.drop(2000 + 8 * i))
+                                                  sv, st.nhead, B, need_tgt=i > 0, drop=c.drop(2000 + 8 * i), dkv=dkv)
         d_next = d_tgt
         d_qpos = dq if d_qpos is None else K.add_bf16(d_qpos, dq)
-        d_mem = K.add_bf16(dmp, dm) if d_mem is None else K.add_bf16(d_mem, dmp, dm)
+        if not hoisted:
+            d_mem = K.add_bf16(dmp, dm) if d_mem is None else K.add_bf16(d_mem, dmp, dm)
+    if hoisted and needs[0]:  # d memory = dK_all Wk_all (through memory + pos) + dV_all Wv_all: two K = layers * E GEMMs
+        d_k = K.linear_dgrad(dk_all, c.w[st.prefix + "cross_kv.k_weight"])
+        d_mem = K.linear_dgrad(dv_all, c.w[st.prefix + "cross_kv.v_weight"], res=d_k)
     dmem32 = K.cast_f32(d_mem).view(S, B, E) if needs[0] else None
     dqpos32 = K.cast_f32(d_qpos).view(Q, B, E) if needs[1] else None
     return (dmem32, dqpos32, None, None), grads
