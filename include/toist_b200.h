@@ -205,6 +205,12 @@ int toist_cast_pad_f32_bf16(const float* src, void* dst, int64_t rows, int32_t n
 int toist_add_bf16(const void* a, const void* b, const void* c /* may be null */, void* out, int64_t n, void* stream);
 /* 7x7 stride-2 pad-3 stem (torchvision resnet conv1 via backbone.py:75): fp32 NCHW -> bf16 patches [N*Ho*Wo, ldk] */
 int toist_stem_im2col(const float* images, void* patches, int32_t n, int32_t h, int32_t w, int32_t ldk, void* stream);
+/* Stem input of the implicit-GEMM path (no im2col matrix): images fp32 NCHW [n, 3, h, w] -> out bf16 [n, hp, wp, 8]
+ * (hp >= h + 6, wp >= w + 6; 3 zero pixels on top / left, channels 3..7 zero).  The 7 x 7 stride-2 convolution of
+ * torchvision's ResNet stem (models/backbone.py:75) is then toist_gemm with one tap per kernel row over a tensor map whose
+ * rows overlap (row pitch = 2 padded pixels, 64 elements per row). */
+int toist_stem_pad_nhwc8(const float* images, void* out, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
+                         void* stream);
 int toist_maxpool3x3s2(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
 int toist_colsum(const void* x, int32_t dtype, float* out, int64_t rows, int32_t cols, int64_t ld, void* stream);
 int toist_gelu_bwd(const void* dy, const void* pre, void* dx, int64_t n, void* stream);

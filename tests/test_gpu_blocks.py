@@ -301,3 +301,33 @@ def test_heads_linear_layouts():
         assert rel_err(dhs.float(), hr.grad) < BWD_TOL, N
         assert rel_err(g["w"], wr.grad) < BWD_TOL, N
         assert rel_err(g["b"], br.grad) < BWD_TOL, N
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 64, 64), (3, 70, 58), (1, 33, 47)])
+def test_stem_without_im2col_matches_the_im2col_stem_and_torch(n, h, w):
+    """ResNet stem (7x7 stride 2 pad 3 + FrozenBatchNorm + ReLU, torchvision resnet via models/backbone.py:75) as an
+    implicit GEMM over the padded NHWC-8 image (kernels.stem_conv7x7: overlapping TMA rows, one tap per kernel row) against
+    the round-1 path (explicit im2col matrix + GEMM) and against fp32 torch on the bf16-rounded operands; odd sizes
+    exercise the right / bottom border."""
+    import torch.nn.functional as F
+
+    from toist_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(7)
+    images = torch.randn(n, 3, h, w, generator=g).to(DEV)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * 0.1).to(DEV)
+    scale = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(64, generator=g).to(DEV)
+    ws = (wt * scale.view(-1, 1, 1, 1))
+    w7 = torch.zeros(64, 7, 8, 8, dtype=BF, device=DEV)
+    w7[:, :, :7, :3] = ws.permute(0, 2, 3, 1).to(BF)
+    y = K.stem_conv7x7(images, w7.view(64, 448), shift)
+    ho, wo = K.conv_out_size(h, 7, 2, 3), K.conv_out_size(w, 7, 2, 3)
+    assert y.shape == (n, ho, wo, 64)
+    # im2col path on the same bf16 weights
+    sh = torch.zeros(64, 192, dtype=BF, device=DEV)
+    sh[:, :147] = ws.permute(0, 2, 3, 1).reshape(64, 147).to(BF)
+    y0 = K.linear_fwd(K.stem_im2col(images, 192), sh, shift, act=1).view(n, ho, wo, 64)
+    assert rel_err(y.float(), y0.float()) <= 2e-3
+    ref = F.relu(F.conv2d(images.to(BF).float(), ws.to(BF).float(), stride=2, padding=3) + shift.view(1, -1, 1, 1))
+    assert rel_err(y.float().permute(0, 3, 1, 2), ref) <= 4e-3

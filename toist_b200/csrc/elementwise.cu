@@ -111,6 +111,32 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 // 16-byte chunks (8 patch columns) of the output rows from a column -> shared-offset table and stores them coalesced.
 constexpr int kStemStrip = 64;
 constexpr int kStemCols = 2 * kStemStrip + 5;  // input columns touched by a strip (stride 2, 7 taps)
+// Stem input for the implicit-GEMM path: fp32 NCHW [n, 3, h, w] -> bf16 [n, hp, wp, 8] (channels 3..7 zero) with a zero
+// border of 3 pixels on top / left (and at least 3 on the bottom / right): one 16-byte store per output pixel.  A 7 x 7
+// stride-2 window row of output pixel x is then the 64 contiguous elements starting at padded pixel 2 x (7 pixels x 8
+// channels + one pixel that meets zero weights), which a TMA box with overlapping rows (row pitch 2 pixels) fetches
+// directly: the 315 MB im2col matrix of the round-1 stem (written once, read once) is never materialised.
+__global__ void stem_pad_nhwc8_kernel(const float* __restrict__ img, uint4* __restrict__ out, int N, int H, int W, int Hp,
+                                      int Wp) {
+  pdl_prologue();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * Hp * Wp;
+  if (i >= total) return;
+  const int xp = (int)(i % Wp);
+  const long long t = i / Wp;
+  const int yp = (int)(t % Hp);
+  const int n = (int)(t / Hp);
+  const int x = xp - 3, y = yp - 3;
+  uint4 u = make_uint4(0u, 0u, 0u, 0u);
+  if (x >= 0 && x < W && y >= 0 && y < H) {
+    const long long plane = (long long)H * W;
+    const float* p = img + (long long)n * 3 * plane + (long long)y * W + x;
+    u.x = pack_bf16(__ldg(p), __ldg(p + plane));
+    u.y = pack_bf16(__ldg(p + 2 * plane), 0.f);
+  }
+  out[i] = u;
+}
+
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int H, int W, int Ho, int Wo,
                    int ldk) {
@@ -492,6 +518,17 @@ int toist_stem_im2col(const float* images, void* patches, int32_t n, int32_t h, 
   const long long blocks = (long long)n * ho * ((wo + kStemStrip - 1) / kStemStrip);
   launch_pdl(stem_im2col_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, images,
              (__nv_bfloat16*)patches, n, h, w, ho, wo, ldk);
+  TOIST_CHECK_CUDA(cudaGetLastError());
+  return TOIST_OK;
+}
+
+int toist_stem_pad_nhwc8(const float* images, void* out, int32_t n, int32_t h, int32_t w, int32_t hp, int32_t wp,
+                         void* stream) {
+  TOIST_REQUIRE(images && out && hp >= h + 6 && wp >= w + 6, "toist_stem_pad_nhwc8: bad arguments");
+  TOIST_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "toist_stem_pad_nhwc8: output must be 16-byte aligned");
+  const long long total = (long long)n * hp * wp;
+  launch_pdl(stem_pad_nhwc8_kernel, dim3(nblk(total, 256)), dim3(256), 0, (cudaStream_t)stream, images,
+             reinterpret_cast<uint4*>(out), n, h, w, hp, wp);
   TOIST_CHECK_CUDA(cudaGetLastError());
   return TOIST_OK;
 }

@@ -541,6 +541,26 @@ def stem_im2col(images: torch.Tensor, ldk: int = 192) -> torch.Tensor:
     return out
 
 
+def stem_conv7x7(images: torch.Tensor, w7: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+    """relu(conv7x7 stride 2 pad 3 (images) * bn_scale + bn_shift) as an implicit GEMM without an im2col matrix.
+    images fp32 NCHW [n, 3, h, w]; w7 bf16 [64, 7 * 64]: row o, tap ky, then 8 kernel columns x 8 channels (kx = 7 and
+    channels 3..7 zero), BatchNorm scale folded; returns NHWC bf16 [n, ho, wo, 64]."""
+    n, c, h, w = images.shape
+    assert c == 3 and images.dtype == torch.float32 and images.is_contiguous() and w7.shape == (64, 448)
+    ho, wo = conv_out_size(h, 7, 2, 3), conv_out_size(w, 7, 2, 3)
+    hp, wp = max(h + 6, 2 * (ho - 1) + 7), max(w + 6, 2 * (wo - 1) + 8)
+    xp = torch.empty((n, hp, wp, 8), dtype=torch.bfloat16, device=images.device)
+    _ck(_L().toist_stem_pad_nhwc8(images.data_ptr(), xp.data_ptr(), n, h, w, hp, wp, _stream()))
+    y = torch.empty((n, ho, wo, 64), dtype=torch.bfloat16, device=images.device)
+    # A: "row" x of the map = the 64 elements starting at padded pixel 2 x of an image row (rows overlap by 48 elements)
+    a = t4(xp, (64, wo, hp, n), (1, 16, wp * 8, hp * wp * 8))
+    b = t4(w7, (448, 64, 1, 1), (1, 448, 0, 0))
+    taps = [(0, ky, 0, ky * 64) for ky in range(7)]
+    gemm(GEMM_FWD, a, b, y, ext=(wo, ho, n), tile=pick_tile(wo, ho, n, 128, 128), n_cols=64,
+         out_strides=(64, wo * 64, ho * wo * 64), k_per_tap=64, taps=taps, stride=(1, 2), col_shift=shift, act=ACT_RELU)
+    return y
+
+
 def maxpool3x3s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, h, w, c = x.shape
     ho, wo = conv_out_size(h, 3, 2, 1), conv_out_size(w, 3, 2, 1)

@@ -105,6 +105,7 @@ def _load(ctx):
 # ------------------------------------------------------------------------------------------------ shadow weights
 _SHADOW_ALWAYS = os.environ.get("TOIST_SHADOW_ALWAYS", "0") != "0"
 _CROSS_KV_HOIST = os.environ.get("TOIST_CROSS_KV_HOIST", "1") != "0"
+_STEM_NHWC8 = os.environ.get("TOIST_STEM_NHWC8", "1") != "0"
 _EMBEDDING_KEYS = ("word_embeddings", "position_embeddings", "token_type_embeddings", "query_embed")
 RESNET_BLOCKS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
 STEM_LDK = 192  # 7*7*3 = 147 patch columns padded to a multiple of 64
@@ -157,8 +158,20 @@ class ShadowBank:
         self._ver = ver
         if self._stale_rest:
             self.prep.run()
+            self._refresh_stem7()
             if not defer_rest:
                 self.run_rest()
+
+    def _refresh_stem7(self) -> None:
+        st = getattr(self, "_stem", None)
+        if st is None:
+            return
+        conv_w, scale, w7 = st
+        if self._stem_ver == conv_w._version:  # the stem is frozen in every recipe: this runs once per (re)build / load
+            return
+        with torch.no_grad():
+            w7.view(64, 7, 8, 8)[:, :, :7, :3].copy_((conv_w.detach() * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1))
+        self._stem_ver = conv_w._version
 
     def run_rest(self) -> None:
         if self._stale_rest:
@@ -171,6 +184,7 @@ class ShadowBank:
         dev = next(iter(params.values())).device
         if dev.type != "cuda":
             raise RuntimeError("toist_b200 runs on CUDA devices only (sm_100a); there is no CPU path")
+        self._stem = None
         trunk = K.WeightPrep(dev)   # conv + FrozenBatchNorm pairs of the backbone
         prep = K.WeightPrep(dev)    # everything else
         w: Dict[str, torch.Tensor] = {}
@@ -185,6 +199,12 @@ class ShadowBank:
             if conv_name == "conv1":  # 7x7 stem, consumed as an im2col GEMM
                 sh = torch.zeros((cout, STEM_LDK), dtype=BF, device=dev)
                 trunk.add(conv_w.detach(), sh, cout, cin * kh * kw, STEM_LDK, scale, taps=kh * kw)
+                if (cout, cin, kh, kw) == (64, 3, 7, 7) and _STEM_NHWC8:
+                    # the same filter as [64, 7 rows, 8 kernel columns x 8 channels] for kernels.stem_conv7x7 (kernel column 7
+                    # and channels 3..7 are zero); derived from the master in _refresh_stem7 when it changed
+                    w[backbone_prefix + "conv1.weight7"] = torch.zeros((64, 7 * 64), dtype=BF, device=dev)
+                    self._stem = (conv_w, scale, w[backbone_prefix + "conv1.weight7"])
+                    self._stem_ver = None
             else:
                 sh = torch.empty((cout, kh, kw, cin), dtype=BF, device=dev)
                 trunk.add(conv_w.detach(), sh, cout, cin * kh * kw, None, scale, taps=kh * kw)
@@ -595,14 +615,18 @@ def _backbone_fwd_chains(c: Call, images: torch.Tensor, chains: int):
     if lane is None:
         lane = _trunk_lane[dev] = torch.cuda.Stream(device=dev)
     lane.wait_stream(main)
+    w7 = c.w.get(st.prefix + "conv1.weight7")
     per = n // chains
     with K.gemm_chains(chains):
         for ch in range(chains):
             sl = slice(ch * per, (ch + 1) * per)
             with torch.cuda.stream(main if ch == 0 else lane):
-                patches = K.stem_im2col(images[sl], STEM_LDK)
-                y = K.linear_fwd(patches, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU).view(per, ho, wo, 64)
-                del patches
+                if w7 is not None:
+                    y = K.stem_conv7x7(images[sl], w7, w["bn1.shift"])
+                else:
+                    patches = K.stem_im2col(images[sl], STEM_LDK)
+                    y = K.linear_fwd(patches, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU).view(per, ho, wo, 64)
+                    del patches
                 x = K.maxpool3x3s2(y, out=pooled[sl])
                 del y
                 for (li, bi, stride, has_ds, y1, y2, out) in plan:
@@ -626,10 +650,14 @@ def backbone_fwd(c: Call, images: torch.Tensor):
     st = c.stage
     w = WView(c.w, st.prefix)
     n, _, hh, ww = images.shape
-    patches = K.stem_im2col(images, STEM_LDK)
     ho, wo = K.conv_out_size(hh, 7, 2, 3), K.conv_out_size(ww, 7, 2, 3)
-    y = K.linear_fwd(patches, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU).view(n, ho, wo, 64)
-    del patches
+    w7 = c.w.get(st.prefix + "conv1.weight7")
+    if w7 is not None:
+        y = K.stem_conv7x7(images, w7, w["bn1.shift"])
+    else:
+        patches = K.stem_im2col(images, STEM_LDK)
+        y = K.linear_fwd(patches, w["conv1.weight"], w["bn1.shift"], act=ACT_RELU).view(n, ho, wo, 64)
+        del patches
     x = K.maxpool3x3s2(y)
     del y
     feats, saved = [], {}
