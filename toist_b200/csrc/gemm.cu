@@ -893,7 +893,7 @@ static int dispatch_bn(int bn, const CUtensorMap* maps, GemmKParams& kp, dim3 gr
   int sk = short_k_stages();
   static const int short_max = []() {  // TOIST_GEMM_SHORTK_MAX: longest reduction (k-blocks) given the shallow ring
     const char* e = getenv("TOIST_GEMM_SHORTK_MAX");
-    return e ? atoi(e) : 4;
+    return e ? atoi(e) : 8;  // bench step with the two trunk chains: 4 -> 8.775 ms, 8 -> 8.728 ms (same box)
   }();
   const bool short_k = sk > 0 && k_iters <= short_max;
   if (short_k && kp.epi == 0) {  // the bf16 epilogue stages [res = out | mask] tiles of BN * 256 bytes in the idle ring
